@@ -1,0 +1,134 @@
+/*
+ * rt_b200.h -- C ABI of librt_b200.so: the B200-native replacement for the
+ * native calls on raoteh's data-parallel hot path.
+ *
+ * The reference's only native boundary is Python -> `pyfelscore` (Cython,
+ * un-vendored; README.md:8-9).  Each entry point below is the BATCHED
+ * (many sites / chains per call) replacement of one or more of those calls
+ * and of the scipy calls around them; the reference interface replaced is
+ * cited per function (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C types only; every array argument is a DEVICE pointer into
+ *     caller-owned memory unless its name ends in `_h` (host pointer);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on
+ *     it, hold no global state and are re-entrant per stream;
+ *   - return value: RT_OK (0) or an RT_ERR_* code; rt_last_error_string()
+ *     describes the last failure on the calling thread;
+ *   - nodes are numbered in DFS preorder from the root (root = 0,
+ *     parent < child), per-edge matrices are indexed by the CHILD node
+ *     (slot 0 unused) -- the reference's own convention for its native calls
+ *     (raoteh/sampler/_density.py:104-180);
+ *   - site-major arrays are laid out [row][site] with `site_stride` elements
+ *     between rows (site-minor => coalesced), states 0..S-1;
+ *   - per-site status (int8): 0 ok, 1 structural zero, 2 numerical zero
+ *     (raoteh/sampler/_util.py:14-21: StructuralZeroProb / NumericalZeroProb).
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_OK 0
+#define RT_ERR_ARG 1
+#define RT_ERR_CUDA 2
+#define RT_ERR_UNSUPPORTED 3
+
+/* observation encodings (argument `obs_kind`) */
+#define RT_OBS_CODES 0 /* uint8  [n_obs][site_stride]     hard state, 255 = unobserved */
+#define RT_OBS_MASK 1  /* uint64 [n_obs][site_stride]     bitmask of allowed states     */
+#define RT_OBS_DENSE 2 /* double [n_obs][S][site_stride]  emission likelihoods          */
+
+int rt_version(void);
+const char* rt_last_error_string(void);
+
+/*
+ * P[m] = expm(Q[q_index[m]] * t[m]),  m = 0..n_mat-1   (S <= 128)
+ * Q: [n_q][S][S] row-major with diagonal; q_index: [n_mat] or NULL (all use Q[0]).
+ * Replaces scipy.linalg.expm called once per edge PER SITE at
+ * raoteh/sampler/_mjp_dense.py:357 (custom_expm :24) and _linalg.py:81
+ * (sparse_expm_naive), and pyfelscore.get_tolerance_rate_matrix
+ * (_tmjp_dense.py:239) / get_mmpp_block (_linalg.py:44-46) for S = 3.
+ */
+int rt_expm_batched(const double* Q, const int32_t* q_index, const double* t,
+                    int n_mat, int S, double* P, void* stream);
+
+/*
+ * M[m] = L(t[m] Q^T, t[m] W[m]) -- Frechet derivative of expm; equals
+ * sum_ab W[m][a][b] * expm_frechet(tQ, t E_cd)[a][b] at entry [c][d].  (S <= 64)
+ * Replaces the S + nnz(Q) scipy.linalg.expm_frechet calls per edge per site at
+ * raoteh/sampler/_mjp_dense.py:497-520 (sparse twin _mjp.py:531-580) and
+ * pyfelscore.get_mmpp_frechet_* (_linalg.py:107-118) /
+ * get_tolerance_expectations (_tmjp_dense.py:339).
+ */
+int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t,
+                        const double* W, int n_mat, int S, double* M, void* stream);
+
+/*
+ * Structural support of every node for every site (integer work):
+ * backward pass (state kept iff every child has a reachable kept state) then
+ * forward pass (state kept iff reachable from a kept parent state).
+ * mask: uint64 [n_nodes][site_stride] in/out; parent: int32 [n_nodes];
+ * P: [n_nodes][S][S] (only the > 0 pattern is used).  S <= 64.
+ * Replaces pyfelscore.mcy_esd_get_node_to_pset + esd_get_node_to_set
+ * (raoteh/sampler/_mcy_dense.py:168-179,270-281; _mcy.py:219-230,508-519;
+ * specs _mcy.py:397-470 and _mc0.py:89-138) and the shared-pattern variants
+ * mcy_get_node_to_pset / get_node_to_set (_mcy.py:158-174).
+ */
+int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                    const int32_t* parent, const double* P, uint64_t* mask, void* stream);
+
+/*
+ * Felsenstein pruning + root combine, batched over sites.
+ *   L[a,s] = obs[a,s] * prod_{b in ch(a)} sum_s' P_b[s,s'] L[b,s'];
+ *   loglik = log(sum_s pi[s] L[root,s])      (pi = 1 if root_distn == NULL)
+ * program: int32 [n_ops][4] upward program (see raoteh_b200/lowering.py),
+ * n_slots its stack depth.  partials (nullable): [n_store][S][site_stride]
+ * scaled partials of the internal nodes, exponents (nullable):
+ * [n_store][site_stride] with true partial = partial * 2^exponent.
+ * loglik: [n_sites]; status: [n_sites]; loglik_sum (nullable): [1], += sum of
+ * the finite log-likelihoods (the value the site-sharded job allreduces).
+ * Replaces pyfelscore.mcy_esd_get_node_to_pmap (raoteh/sampler/_mcy_dense.py:
+ * 184-189,286-291; _mcy.py:533-538; spec _mcy.py:611-682; emission form
+ * _mcz.py:94-166) + _mc0_dense.get_likelihood (_mc0_dense.py:147-212).
+ */
+int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                    const int32_t* program, int n_ops, int n_slots,
+                    const double* P, const double* root_distn,
+                    int obs_kind, const void* obs,
+                    double* partials, int32_t* exponents,
+                    double* loglik, int8_t* status, double* loglik_sum, void* stream);
+
+/*
+ * Downward pass + sufficient statistics, batched over sites.
+ *   D[root] = norm(pi * L_root); for each edge (a -> b):
+ *   G_b = D[a] / (P_b L_b);  D[b] = L_b * (P_b^T G_b);
+ *   W[b] += sum_sites G_b (x) L_b   restricted to P_b > 0   (= sum J_b / P_b)
+ * edges: int32 [n_edges][4] downward program rows (child node, parent store
+ * idx, child store idx or -1, child obs slot), sorted by depth of the child;
+ * level_ptr_h: HOST int32 [n_levels+1], rows level_ptr_h[l]..level_ptr_h[l+1]
+ * form level l (one launch per level: parents before children).
+ * partials: from rt_prune_loglik; node_distn: [n_store][S][site_stride] out
+ * (posterior marginals of the internal nodes); W: [n_nodes][S][S], += ;
+ * root_post_sum (nullable): [S], += sum_sites D[root].
+ * Sites whose status != 0 are skipped.
+ * Replaces pyfelscore.mc0_esd_get_node_to_distn (raoteh/sampler/
+ * _mc0_dense.py:381, _mcy_dense.py:195; spec _mc0_dense.py:400-489) and
+ * mc0_esd_get_joint_endpoint_distn (_mcy_dense.py:205; spec
+ * _mc0_dense.py:217-270); the joint J is consumed on chip (never stored).
+ */
+int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                       const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
+                       const double* P, const double* root_distn,
+                       int obs_kind, const void* obs,
+                       const double* partials, const int8_t* status,
+                       double* node_distn, double* W, double* root_post_sum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -1,0 +1,195 @@
+"""
+TEST INFRASTRUCTURE -- container only (needs /root/reference).
+
+Generates the committed golden fixtures under tests/golden/ by running the
+UNMODIFIED reference through oracle/ref_shim.py:
+
+  code2x3.json      every _mjp_dense.get_likelihood / extras.get_expected_ntransitions
+                    call made by examples/code2x3/run.py main() (pure primary,
+                    switching, blinking models; data levels L0/L1/L2), inputs
+                    and outputs recorded by wrapping the two functions.  The
+                    printed values are the reference's published golden vectors
+                    (examples/code2x3/full-description.tex:165-370).
+  mjp_random.json   random small trees / rate matrices / allowed-state maps:
+                    _mjp_dense.get_likelihood, get_expected_history_statistics,
+                    _mcy_dense.get_node_to_pmap, _mc0_dense.get_node_to_distn,
+                    get_joint_endpoint_distn outputs (seeded).
+  jukes_cantor.json the closed-form check of raoteh/sampler/tests/test_mjp.py:166-240.
+
+usage: python oracle/gen_golden.py
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+OUT = os.path.join(HERE, '..', 'tests', 'golden')
+
+
+def tree_to_json(T, root):
+    import networkx as nx
+    edges = [(int(a), int(b), float(T[a][b]['weight'])) for a, b in nx.bfs_edges(T, root)]
+    return dict(root=int(root), edges=edges, nodes=[int(v) for v in T])
+
+
+def allowed_to_json(d):
+    return dict((str(int(k)), sorted(int(s) for s in v)) for k, v in d.items())
+
+
+def gen_code2x3():
+    ref_shim.load_reference()
+    ex = os.path.join(ref_shim.REFERENCE_ROOT, 'examples', 'code2x3')
+    sys.path.insert(0, ex)
+    import extras
+    import run
+    from raoteh.sampler import _mjp_dense
+    calls = []
+    orig_lik = _mjp_dense.get_likelihood
+    orig_exp = extras.get_expected_ntransitions
+
+    def rec_lik(T, node_to_allowed_states, root, nstates, root_distn=None, Q_default=None):
+        out = orig_lik(T, node_to_allowed_states, root, nstates,
+                       root_distn=root_distn, Q_default=Q_default)
+        calls.append(dict(kind='likelihood', tree=tree_to_json(T, root), nstates=int(nstates),
+                          allowed=allowed_to_json(node_to_allowed_states),
+                          root_distn=np.asarray(root_distn).tolist(),
+                          Q=np.asarray(Q_default).tolist(), out=float(out)))
+        return out
+
+    def rec_exp(T, node_to_allowed_states, root, nstates, root_distn=None, Q_default=None, E=None):
+        out = orig_exp(T, node_to_allowed_states, root, nstates,
+                       root_distn=root_distn, Q_default=Q_default, E=E)
+        calls.append(dict(kind='edge_expectations', tree=tree_to_json(T, root),
+                          nstates=int(nstates), allowed=allowed_to_json(node_to_allowed_states),
+                          root_distn=np.asarray(root_distn).tolist(),
+                          Q=np.asarray(Q_default).tolist(),
+                          E=None if E is None else np.asarray(E).tolist(),
+                          out=[[int(a), int(b), float(v)] for (a, b), v in out.items()]))
+        return out
+
+    _mjp_dense.get_likelihood = rec_lik
+    run._mjp_dense.get_likelihood = rec_lik
+    extras.get_expected_ntransitions = rec_exp
+    run.extras.get_expected_ntransitions = rec_exp
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        run.main()
+    _mjp_dense.get_likelihood = orig_lik
+    extras.get_expected_ntransitions = orig_exp
+    with open(os.path.join(OUT, 'code2x3.json'), 'w') as f:
+        json.dump(dict(source='examples/code2x3/run.py main() via oracle/ref_shim.py',
+                       printed=buf.getvalue(), calls=calls), f)
+    print('code2x3: %d calls recorded' % len(calls))
+
+
+def random_tree(rng, n):
+    import networkx as nx
+    T = nx.Graph()
+    for b in range(1, n):
+        a = int(rng.integers(0, b))
+        T.add_edge(a, b, weight=float(rng.exponential(0.3) + 0.01))
+    return T
+
+
+def gen_mjp_random():
+    ref_shim.load_reference()
+    import networkx as nx
+    mjpd = ref_shim.ref_module('_mjp_dense')
+    mcyd = ref_shim.ref_module('_mcy_dense')
+    mc0d = ref_shim.ref_module('_mc0_dense')
+    util = ref_shim.ref_module('_util')
+    rng = np.random.default_rng(1234)
+    cases = []
+    for S, n, sparse in [(2, 3, False), (3, 5, False), (4, 7, False), (4, 9, True),
+                         (5, 8, False), (6, 10, True), (8, 12, False), (11, 9, False),
+                         (16, 8, True), (20, 10, False),
+                         (3, 5, 'tri'), (4, 6, 'tri'), (6, 7, 'tri'), (12, 6, 'tri')]:
+        for rep in range(3 if sparse != 'tri' else 6):
+            T = random_tree(rng, n)
+            root = int(rng.integers(0, n))
+            Q = rng.exponential(1.0, size=(S, S))
+            if sparse == 'tri':   # reducible: structural zeros, some sites infeasible
+                Q = np.triu(Q, 1)
+            elif sparse:
+                Q *= rng.random((S, S)) < 0.4
+                for i in range(S):        # keep the chain irreducible-ish
+                    Q[i, (i + 1) % S] += 0.5
+            if sparse == 'tri':
+                pass
+            np.fill_diagonal(Q, 0)
+            Q -= np.diag(Q.sum(axis=1))
+            pi = rng.dirichlet(np.ones(S))
+            allowed = {}
+            deg = dict(T.degree())
+            for v in T:
+                r = rng.random()
+                if deg[v] == 1 and r < 0.7:
+                    allowed[v] = {int(rng.integers(0, S))}
+                elif r < 0.3:
+                    k = int(rng.integers(1, S + 1))
+                    allowed[v] = set(int(x) for x in rng.choice(S, size=k, replace=False))
+                else:
+                    allowed[v] = set(range(S))
+            case = dict(tree=tree_to_json(T, root), nstates=S, Q=Q.tolist(), root_distn=pi.tolist(),
+                        allowed=allowed_to_json(allowed))
+            try:
+                lk = mjpd.get_likelihood(T, allowed, root, S, root_distn=pi, Q_default=Q)
+                case['likelihood'] = float(lk)
+                dwell, rootp, trans = mjpd.get_expected_history_statistics(
+                    T, allowed, root, S, root_distn=pi, Q_default=Q)
+                case['dwell'] = [float(dwell.get(s, 0.0)) for s in range(S)]
+                case['root_post'] = np.asarray(rootp).tolist()
+                tr = np.zeros((S, S))
+                for a, b, d in trans.edges(data=True):
+                    tr[a, b] = d['weight']
+                case['trans'] = tr.tolist()
+                T_aug = mjpd.get_expm_augmented_tree(T, root, Q_default=Q)
+                pmap = mcyd.get_node_to_pmap(T_aug, root, S, node_to_allowed_states=allowed)
+                case['pmap'] = dict((str(int(v)), np.asarray(p).tolist()) for v, p in pmap.items())
+                distn = mc0d.get_node_to_distn(T_aug, root, pmap, S, root_distn=pi)
+                case['node_distn'] = dict((str(int(v)), np.asarray(p).tolist()) for v, p in distn.items())
+                TJ = mc0d.get_joint_endpoint_distn(T_aug, root, pmap, distn, S)
+                case['joint'] = [[int(a), int(b), np.asarray(TJ[a][b]['J']).tolist()]
+                                 for a, b in nx.bfs_edges(T, root)]
+                case['P'] = [[int(a), int(b), np.asarray(T_aug[a][b]['P']).tolist()]
+                             for a, b in nx.bfs_edges(T, root)]
+            except util.ZeroProbError as e:
+                case['raises'] = type(e).__name__
+            cases.append(case)
+    with open(os.path.join(OUT, 'mjp_random.json'), 'w') as f:
+        json.dump(dict(source='oracle/gen_golden.py gen_mjp_random, seed 1234', cases=cases), f)
+    print('mjp_random: %d cases (%d raise)' % (len(cases), sum('raises' in c for c in cases)))
+
+
+def gen_jukes_cantor():
+    ref_shim.load_reference()
+    ce = ref_shim.ref_module('_conditional_expectation')
+    t = 0.5
+    n = 4
+    rows = []
+    for a in range(n):
+        for b in range(n):
+            exp = [ce.get_jukes_cantor_interaction(a, b, i, i, t, n) /
+                   ce.get_jukes_cantor_probability(a, b, t, n) for i in range(n)]
+            rows.append(dict(a=a, b=b, dwell=[float(x) for x in exp]))
+    with open(os.path.join(OUT, 'jukes_cantor.json'), 'w') as f:
+        json.dump(dict(source='raoteh/sampler/tests/test_mjp.py:166-240 closed forms '
+                       '(_conditional_expectation.py:25-46)', t=t, nstates=n,
+                       path_weights=[0.1 * t, 0.2 * t, 0.3 * t, 0.4 * t], rows=rows), f)
+    print('jukes_cantor: %d rows' % len(rows))
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    gen_code2x3()
+    gen_mjp_random()
+    gen_jukes_cantor()

@@ -1,0 +1,77 @@
+"""ctypes binding of librt_b200.so (include/rt_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, the
+product raises.  Building is explicit (`python -m raoteh_b200._build` or
+`__graft_entry__.build()`); importing never compiles.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'librt_b200.so')
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int64 = ctypes.c_int64
+
+EXPORTS = {
+    'rt_version': ([], c_int),
+    'rt_last_error_string': ([], ctypes.c_char_p),
+    'rt_expm_batched': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
+    'rt_frechet_contract': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                             c_void_p], c_int),
+    'rt_support_sets': ([c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
+                        c_int),
+    'rt_prune_loglik': ([c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p,
+                         c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_void_p], c_int),
+    'rt_posterior_stats': ([c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p,
+                            c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p], c_int),
+    'rt_raoteh_init': None,      # filled in below when present
+    'rt_raoteh_sweeps': None,
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load librt_b200.so once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                'librt_b200.so not found at %s -- build it with '
+                '`python -m raoteh_b200._build` (needs nvcc); there is no CPU fallback'
+                % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, sig in EXPORTS.items():
+            if sig is None:
+                continue
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = sig
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rt_last_error_string()
+        raise NativeError('%s failed with code %d: %s'
+                          % (what, rc, msg.decode() if msg else ''))
+
+
+def declared_symbols():
+    """Symbols include/rt_b200.h declares (parsed, for the export test)."""
+    import re
+    hdr = os.path.join(HERE, '..', 'include', 'rt_b200.h')
+    text = open(hdr).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(rt_[a-z0-9_]+)\s*\(', text)))

@@ -1,0 +1,112 @@
+// C-ABI entry points of librt_b200.so (see include/rt_b200.h).
+#include "rt_common.cuh"
+#include "../../include/rt_b200.h"
+#include <stdio.h>
+
+static thread_local char g_err[512] = "";
+
+void rt_set_last_error(cudaError_t e, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+}
+static int arg_error(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "argument error: %s", msg);
+  return RT_ERR_ARG;
+}
+static int unsupported(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "unsupported: %s", msg);
+  return RT_ERR_UNSUPPORTED;
+}
+
+// implemented in the kernel translation units
+int rt_expm_batched_impl(const double*, const int32_t*, const double*, int, int, double*, cudaStream_t);
+int rt_frechet_contract_impl(const double*, const int32_t*, const double*, const double*, int, int,
+                             double*, cudaStream_t);
+int rt_support_sets_impl(int, int, int64_t, int64_t, const int32_t*, const double*, uint64_t*, cudaStream_t);
+int rt_prune_small_dispatch(int, int, bool, int64_t, int64_t, const int32_t*, int, int, int,
+                            const double*, const double*, const void*, double*, int32_t*, double*,
+                            int8_t*, double*, cudaStream_t);
+int rt_prune_dmma_dispatch(int, int, bool, int64_t, int64_t, const int32_t*, int, int, int,
+                           const double*, const double*, const void*, double*, int32_t*, double*,
+                           int8_t*, double*, cudaStream_t);
+int rt_posterior_small_dispatch(int, int, int64_t, int64_t, const int32_t*, const int32_t*, int,
+                                const double*, const double*, const void*, const double*,
+                                const int8_t*, double*, double*, double*, cudaStream_t);
+int rt_posterior_dmma_dispatch(int, int, int64_t, int64_t, const int32_t*, const int32_t*, int,
+                               const double*, const double*, const void*, const double*,
+                               const int8_t*, double*, double*, double*, cudaStream_t);
+
+extern "C" {
+
+int rt_version(void) { return 100; }
+const char* rt_last_error_string(void) { return g_err; }
+
+int rt_expm_batched(const double* Q, const int32_t* q_index, const double* t, int n_mat, int S,
+                    double* P, void* stream) {
+  if (!Q || !t || !P) return arg_error("null pointer");
+  if (S < 1 || S > 128) return unsupported("rt_expm_batched needs 1 <= S <= 128");
+  return rt_expm_batched_impl(Q, q_index, t, n_mat, S, P, (cudaStream_t)stream);
+}
+
+int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t, const double* W,
+                        int n_mat, int S, double* M, void* stream) {
+  if (!Q || !t || !W || !M) return arg_error("null pointer");
+  if (S < 1 || S > 64) return unsupported("rt_frechet_contract needs 1 <= S <= 64");
+  return rt_frechet_contract_impl(Q, q_index, t, W, n_mat, S, M, (cudaStream_t)stream);
+}
+
+int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride, const int32_t* parent,
+                    const double* P, uint64_t* mask, void* stream) {
+  if (!parent || !P || !mask) return arg_error("null pointer");
+  if (site_stride < n_sites) return arg_error("site_stride < n_sites");
+  return rt_support_sets_impl(S, n_nodes, n_sites, site_stride, parent, P, mask, (cudaStream_t)stream);
+}
+
+int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                    const int32_t* program, int n_ops, int n_slots, const double* P,
+                    const double* root_distn, int obs_kind, const void* obs, double* partials,
+                    int32_t* exponents, double* loglik, int8_t* status, double* loglik_sum,
+                    void* stream) {
+  if (!program || !P || !loglik || !status) return arg_error("null pointer");
+  if (obs_kind < 0 || obs_kind > 2) return arg_error("obs_kind");
+  if (site_stride < n_sites) return arg_error("site_stride < n_sites");
+  if (n_sites <= 0) return RT_OK;
+  if (n_ops <= 0 || n_slots <= 0 || n_nodes <= 1) return arg_error("empty program");
+  const bool store = partials != nullptr;
+  int rc;
+  if (S >= 2 && S <= 8)
+    rc = rt_prune_small_dispatch(S, obs_kind, store, n_sites, site_stride, program, n_ops, n_slots,
+                                 n_nodes, P, root_distn, obs, partials, exponents, loglik, status,
+                                 loglik_sum, (cudaStream_t)stream);
+  else if (S >= 1 && S <= 64)
+    rc = rt_prune_dmma_dispatch(S, obs_kind, store, n_sites, site_stride, program, n_ops, n_slots,
+                                n_nodes, P, root_distn, obs, partials, exponents, loglik, status,
+                                loglik_sum, (cudaStream_t)stream);
+  else
+    return unsupported("rt_prune_loglik needs 1 <= S <= 64");
+  if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: shared-memory budget exceeded");
+  return rc;
+}
+
+int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                       const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
+                       const double* P, const double* root_distn, int obs_kind, const void* obs,
+                       const double* partials, const int8_t* status, double* node_distn, double* W,
+                       double* root_post_sum, void* stream) {
+  if (!edges || !level_ptr_h || !P || !partials || !status || !node_distn || !W)
+    return arg_error("null pointer");
+  if (obs_kind < 0 || obs_kind > 2) return arg_error("obs_kind");
+  if (site_stride < n_sites) return arg_error("site_stride < n_sites");
+  if (n_sites <= 0) return RT_OK;
+  (void)n_nodes;
+  if (S >= 2 && S <= 8)
+    return rt_posterior_small_dispatch(S, obs_kind, n_sites, site_stride, edges, level_ptr_h,
+                                       n_levels, P, root_distn, obs, partials, status, node_distn,
+                                       W, root_post_sum, (cudaStream_t)stream);
+  if (S >= 1 && S <= 64)
+    return rt_posterior_dmma_dispatch(S, obs_kind, n_sites, site_stride, edges, level_ptr_h,
+                                      n_levels, P, root_distn, obs, partials, status, node_distn, W,
+                                      root_post_sum, (cudaStream_t)stream);
+  return unsupported("rt_posterior_stats needs 1 <= S <= 64");
+}
+
+}  // extern "C"

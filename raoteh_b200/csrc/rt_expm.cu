@@ -1,0 +1,313 @@
+// K1: batched matrix exponential, one CTA per matrix, Pade-13 scaling and
+// squaring (Higham 2005), fp64.
+//
+// Replaces the reference's per-edge-per-site scipy.linalg.expm
+// (raoteh/sampler/_mjp_dense.py:24,357; sparse twin _linalg.py:72-90) with one
+// launch for every edge of the tree, computed once per (Q, tree) and shared by
+// all sites.  The same kernel exponentiates the 2S x 2S block-triangular
+// matrix [[tQ^T, tW],[0, tQ^T]] whose top-right block is the Frechet
+// derivative L(tQ^T, tW) that contracts the posterior edge weights into
+// expected dwell times / transition counts (replaces the S + nnz(Q)
+// scipy.linalg.expm_frechet calls per edge per site at _mjp_dense.py:497-520).
+//
+// Work is negligible next to pruning, so matrices
+// live in a global scratch (L2 resident) and products are smem-tiled FMA.
+#include "rt_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTile = 64;   // C tile 64x64, 4x4 per thread
+constexpr int kTK = 16;
+
+__device__ const double kPade13[14] = {
+    64764752532480000.0, 32382376266240000.0, 7771770303897600.0, 1187353796428800.0,
+    129060195264000.0,   10559470521600.0,    670442572800.0,     33522128640.0,
+    1323241920.0,        40840800.0,          960960.0,           16380.0,
+    182.0,               1.0};
+constexpr double kTheta13 = 5.371920351148152;
+
+// C = A * B, all n x n row-major in global memory; whole CTA cooperates.
+__device__ void mm(double* __restrict__ C, const double* __restrict__ A,
+                   const double* __restrict__ B, int n, double* sm) {
+  double (*As)[kTK + 1] = reinterpret_cast<double (*)[kTK + 1]>(sm);             // [64][17]
+  double (*Bs)[kTile + 4] = reinterpret_cast<double (*)[kTile + 4]>(sm + kTile * (kTK + 1));  // [16][68]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, each 4x4
+  for (int i0 = 0; i0 < n; i0 += kTile) {
+    for (int j0 = 0; j0 < n; j0 += kTile) {
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      for (int k0 = 0; k0 < n; k0 += kTK) {
+        __syncthreads();
+        for (int idx = tid; idx < kTile * kTK; idx += kThreads) {
+          int r = idx / kTK, c = idx % kTK;
+          int gi = i0 + r, gk = k0 + c;
+          As[r][c] = (gi < n && gk < n) ? A[(size_t)gi * n + gk] : 0.0;
+        }
+        for (int idx = tid; idx < kTK * kTile; idx += kThreads) {
+          int r = idx / kTile, c = idx % kTile;
+          int gk = k0 + r, gj = j0 + c;
+          Bs[r][c] = (gk < n && gj < n) ? B[(size_t)gk * n + gj] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTK; ++k) {
+          double a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][k];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int gi = i0 + ty * 4 + i, gj = j0 + tx * 4 + j;
+          if (gi < n && gj < n) C[(size_t)gi * n + gj] = acc[i][j];
+        }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ double block_max(double v, double* red) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  __syncthreads();
+  double r = red[0];
+  for (int i = 1; i < kThreads / 32; ++i) r = fmax(r, red[i]);
+  __syncthreads();
+  return r;
+}
+
+// In-place expm of mats[blockIdx.x] (n x n).  scratch: 7 n^2 doubles per matrix.
+__global__ void __launch_bounds__(kThreads)
+expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
+  __shared__ double sm[kTile * (kTK + 1) + kTK * (kTile + 4)];
+  __shared__ double red[kThreads / 32];
+  __shared__ int piv_s;
+  const int tid = threadIdx.x;
+  const size_t nn = (size_t)n * n;
+  double* A = mats + (size_t)blockIdx.x * nn;
+  double* W = scratch + (size_t)blockIdx.x * 7 * nn;
+  double *A2 = W, *A4 = W + nn, *A6 = W + 2 * nn, *T1 = W + 3 * nn, *U = W + 4 * nn,
+         *V = W + 5 * nn, *T2 = W + 6 * nn;
+
+  // 1-norm (max column sum of |a_ij|)
+  double cmax = 0.0;
+  for (int j = tid; j < n; j += kThreads) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += fabs(A[(size_t)i * n + j]);
+    cmax = fmax(cmax, s);
+  }
+  const double norm1 = block_max(cmax, red);
+  int s = 0;
+  if (norm1 > kTheta13) {
+    s = (int)ceil(log2(norm1 / kTheta13));
+    if (s < 0) s = 0;
+    const double sc = ldexp(1.0, -s);
+    for (size_t i = tid; i < nn; i += kThreads) A[i] *= sc;
+  }
+  __syncthreads();
+
+  const double* b = kPade13;
+  mm(A2, A, A, n, sm);
+  mm(A4, A2, A2, n, sm);
+  mm(A6, A4, A2, n, sm);
+  // T1 = b13 A6 + b11 A4 + b9 A2 ; T2 = b12 A6 + b10 A4 + b8 A2
+  for (size_t i = tid; i < nn; i += kThreads) {
+    const double a2 = A2[i], a4 = A4[i], a6 = A6[i];
+    T1[i] = b[13] * a6 + b[11] * a4 + b[9] * a2;
+    T2[i] = b[12] * a6 + b[10] * a4 + b[8] * a2;
+  }
+  __syncthreads();
+  mm(U, A6, T1, n, sm);     // U = A6*T1
+  mm(V, A6, T2, n, sm);     // V = A6*T2
+  for (size_t i = tid; i < nn; i += kThreads) {
+    const double a2 = A2[i], a4 = A4[i], a6 = A6[i];
+    const bool diag = (i / n) == (i % n);
+    T1[i] = U[i] + b[7] * a6 + b[5] * a4 + b[3] * a2 + (diag ? b[1] : 0.0);
+    V[i] = V[i] + b[6] * a6 + b[4] * a4 + b[2] * a2 + (diag ? b[0] : 0.0);
+  }
+  __syncthreads();
+  mm(U, A, T1, n, sm);      // U = A * (...)
+  // M = V - U (into T1), B = V + U (into T2)
+  for (size_t i = tid; i < nn; i += kThreads) {
+    const double u = U[i], v = V[i];
+    T1[i] = v - u;
+    T2[i] = v + u;
+  }
+  __syncthreads();
+
+  // Solve T1 * X = T2 by Gaussian elimination with partial pivoting; X -> T2.
+  double* M = T1;
+  double* B = T2;
+  for (int k = 0; k < n; ++k) {
+    if (tid < 32) {
+      double best = -1.0;
+      int bi = k;
+      for (int i = k + tid; i < n; i += 32) {
+        double v = fabs(M[(size_t)i * n + k]);
+        if (v > best) { best = v; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (tid == 0) piv_s = bi;
+    }
+    __syncthreads();
+    const int p = piv_s;
+    if (p != k) {
+      for (int j = tid; j < 2 * n; j += kThreads) {
+        double* X = (j < n) ? M : B;
+        const int jj = (j < n) ? j : j - n;
+        double t = X[(size_t)k * n + jj];
+        X[(size_t)k * n + jj] = X[(size_t)p * n + jj];
+        X[(size_t)p * n + jj] = t;
+      }
+      __syncthreads();
+    }
+    const double pinv = 1.0 / M[(size_t)k * n + k];
+    // eliminate rows below k: each thread handles (row i, column chunk)
+    const int rows = n - k - 1;
+    const int cols = (n - k - 1) + n;   // M columns k+1..n-1, then all B columns
+    for (long idx = tid; idx < (long)rows * cols; idx += kThreads) {
+      const int i = k + 1 + (int)(idx / cols);
+      const int c = (int)(idx % cols);
+      const double l = M[(size_t)i * n + k] * pinv;
+      if (c < n - k - 1) {
+        const int j = k + 1 + c;
+        M[(size_t)i * n + j] = fma(-l, M[(size_t)k * n + j], M[(size_t)i * n + j]);
+      } else {
+        const int j = c - (n - k - 1);
+        B[(size_t)i * n + j] = fma(-l, B[(size_t)k * n + j], B[(size_t)i * n + j]);
+      }
+    }
+    __syncthreads();
+  }
+  // back substitution, one thread per column of B
+  for (int j = tid; j < n; j += kThreads) {
+    for (int k = n - 1; k >= 0; --k) {
+      double v = B[(size_t)k * n + j];
+      for (int c = k + 1; c < n; ++c) v = fma(-M[(size_t)k * n + c], B[(size_t)c * n + j], v);
+      B[(size_t)k * n + j] = v / M[(size_t)k * n + k];
+    }
+  }
+  __syncthreads();
+
+  // squaring: R = B; ping-pong between B(T2) and U
+  double* R = B;
+  double* O = U;
+  for (int i = 0; i < s; ++i) {
+    mm(O, R, R, n, sm);
+    double* t = R; R = O; O = t;
+  }
+  for (size_t i = tid; i < nn; i += kThreads) A[i] = R[i];
+}
+
+__global__ void build_scaled_kernel(const double* __restrict__ Q, const int32_t* __restrict__ q_index,
+                                    const double* __restrict__ t, int S, double* __restrict__ out) {
+  const int m = blockIdx.x;
+  const double* Qm = Q + (size_t)(q_index ? q_index[m] : 0) * S * S;
+  const double tm = t[m];
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) out[(size_t)m * S * S + i] = Qm[i] * tm;
+}
+
+// out[m] = [[tQ^T, c*W_m],[0, tQ^T]] with c = 1/(S*max|W_m|) (0 if W_m == 0), so
+// the direction block has 1-norm <= 1 and never drives the scaling;
+// scale[m] = 1/c so that L(tQ^T, tW) = t * scale * topright(expm(out)).
+__global__ void build_frechet_kernel(const double* __restrict__ Q, const int32_t* __restrict__ q_index,
+                                     const double* __restrict__ t, const double* __restrict__ W,
+                                     int S, double* __restrict__ out, double* __restrict__ scale) {
+  __shared__ double red[32];
+  const int m = blockIdx.x;
+  const int n = 2 * S;
+  const double* Qm = Q + (size_t)(q_index ? q_index[m] : 0) * S * S;
+  const double* Wm = W + (size_t)m * S * S;
+  const double tm = t[m];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) mx = fmax(mx, fabs(Wm[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.0;
+  for (int i = 0; i < (blockDim.x + 31) / 32; ++i) mx = fmax(mx, red[i]);
+  const double c = mx > 0.0 ? 1.0 / (mx * S) : 0.0;
+  if (threadIdx.x == 0) scale[m] = mx * S;
+  double* O = out + (size_t)m * n * n;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx / n, j = idx % n;
+    double v = 0.0;
+    if (i < S && j < S) v = tm * Qm[(size_t)j * S + i];
+    else if (i >= S && j >= S) v = tm * Qm[(size_t)(j - S) * S + (i - S)];
+    else if (i < S && j >= S) v = c * Wm[(size_t)i * S + (j - S)];
+    O[idx] = v;
+  }
+}
+
+__global__ void extract_frechet_kernel(const double* __restrict__ blk, const double* __restrict__ t,
+                                       const double* __restrict__ scale, int S,
+                                       double* __restrict__ M) {
+  const int m = blockIdx.x;
+  const int n = 2 * S;
+  const double f = t[m] * scale[m];
+  const double* O = blk + (size_t)m * n * n;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, j = idx % S;
+    M[(size_t)m * S * S + idx] = f * O[(size_t)i * n + (S + j)];
+  }
+}
+
+}  // namespace
+
+// P[m] = expm(Q[q_index[m]] * t[m]) for m in [0, n_mat)
+int rt_expm_batched_impl(const double* Q, const int32_t* q_index, const double* t, int n_mat, int S,
+                         double* P, cudaStream_t stream) {
+  if (n_mat <= 0) return RT_OK;
+  if (S < 1 || S > 128) return RT_ERR_UNSUPPORTED;
+  double* scratch = nullptr;
+  RT_CUDA_CHECK(cudaMallocAsync(&scratch, sizeof(double) * 7 * (size_t)S * S * n_mat, stream));
+  build_scaled_kernel<<<n_mat, 256, 0, stream>>>(Q, q_index, t, S, P);
+  expm_kernel<<<n_mat, kThreads, 0, stream>>>(P, S, scratch);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(scratch, stream);
+  RT_CUDA_CHECK(e);
+  return RT_OK;
+}
+
+// M[m] = L(t Q^T, t W[m]) (Frechet derivative of expm), m in [0, n_mat)
+int rt_frechet_contract_impl(const double* Q, const int32_t* q_index, const double* t,
+                             const double* W, int n_mat, int S, double* M, cudaStream_t stream) {
+  if (n_mat <= 0) return RT_OK;
+  if (S < 1 || 2 * S > 128) return RT_ERR_UNSUPPORTED;
+  const int n = 2 * S;
+  double* buf = nullptr;
+  const size_t nn = (size_t)n * n;
+  RT_CUDA_CHECK(cudaMallocAsync(&buf, sizeof(double) * (8 * nn + 1) * n_mat, stream));
+  double* blk = buf;
+  double* scratch = buf + nn * n_mat;
+  double* scale = buf + 8 * nn * n_mat;
+  build_frechet_kernel<<<n_mat, 256, 0, stream>>>(Q, q_index, t, W, S, blk, scale);
+  expm_kernel<<<n_mat, kThreads, 0, stream>>>(blk, n, scratch);
+  extract_frechet_kernel<<<n_mat, 256, 0, stream>>>(blk, t, scale, S, M);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(buf, stream);
+  RT_CUDA_CHECK(e);
+  return RT_OK;
+}

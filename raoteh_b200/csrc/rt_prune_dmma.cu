@@ -1,0 +1,501 @@
+// K3: Felsenstein pruning for large state spaces (9 <= S <= 64, e.g. 61 codons)
+// on the FP64 tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4).
+//
+// Replaces, batched over sites, pyfelscore.mcy_esd_get_node_to_pmap
+// (raoteh/sampler/_mcy_dense.py:286-291, spec _mcy.py:611-682, emissions
+// _mcz.py:138-163) + _mc0_dense.get_likelihood (_mc0_dense.py:147-212).
+//
+// One CTA = 8 warps owns a tile of 8*16 = 128 sites and walks the whole upward
+// program.  A message is the dense contraction
+//     M^T[s, site] = sum_s' P_c[s, s'] * L_c^T[s', site]
+// i.e. A = P_c (states x states), B = L_c^T (states x sites), C = messages.
+// Every warp owns 16 site columns, so a warp's B operand is always its own
+// earlier output: warps share only P_c, which one elected thread stages into
+// shared memory with a TMA bulk copy (cp.async.bulk + mbarrier), double
+// buffered, one edge ahead of the math.  The product over children, the
+// observation mask, the exact power-of-two rescale and the root combine run on
+// the C fragments in registers; a finished partial goes to the warp's private
+// shared tile (the next B operand) and, coalesced, to HBM.
+// Leaf messages with hard codes are column gathers from P^T (no flops).
+#include "rt_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kNT = 2;                 // n-tiles (8 sites each) per warp
+constexpr int kWarpSites = 8 * kNT;    // 16
+constexpr int kTileSites = kWarps * kWarpSites;  // 128
+constexpr int kLdB = kWarpSites + 4;   // 20: B tile row stride (== 4 mod 16 -> conflict-free)
+constexpr int kMaxSlots = 32;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- packing: P[n][S][S] -> Ppad[n][SP][SP+4], PT[n][SP][SP], rowsum[n][SP] ----
+__global__ void pack_kernel(const double* __restrict__ P, int S, int SP, int n_nodes,
+                            double* __restrict__ Ppad, double* __restrict__ PT,
+                            double* __restrict__ rowsum) {
+  const int b = blockIdx.x;
+  const int ld = SP + 4;
+  const double* Pb = P + (size_t)b * S * S;
+  for (int idx = threadIdx.x; idx < SP * ld; idx += blockDim.x) {
+    const int r = idx / ld, c = idx % ld;
+    Ppad[(size_t)b * SP * ld + idx] = (r < S && c < S) ? Pb[r * S + c] : 0.0;
+  }
+  for (int idx = threadIdx.x; idx < SP * SP; idx += blockDim.x) {
+    const int r = idx / SP, c = idx % SP;   // PT[r][c] = P[c][r]
+    PT[(size_t)b * SP * SP + idx] = (r < S && c < S) ? Pb[c * S + r] : 0.0;
+  }
+  for (int r = threadIdx.x; r < SP; r += blockDim.x) {
+    double s = 0.0;
+    if (r < S)
+      for (int c = 0; c < S; ++c) s += Pb[r * S + c];
+    rowsum[(size_t)b * SP + r] = s;
+  }
+}
+
+template <int MT>
+struct Smem {
+  static constexpr int SP = 8 * MT;
+  static constexpr int LDP = SP + 4;
+  static constexpr size_t kPBytes = sizeof(double) * SP * LDP;
+};
+
+// MT = number of 8-row m-tiles (padded states SP = 8*MT)
+template <int MT, int OBS, bool STORE>
+__global__ void __launch_bounds__(kThreads, 1)
+prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict__ program,
+                  int n_ops, int n_slots, const double* __restrict__ Ppad,
+                  const double* __restrict__ PT, const double* __restrict__ rowsum,
+                  const double* __restrict__ root_distn, const void* __restrict__ obs,
+                  double* __restrict__ slots_ws, double* __restrict__ partials,
+                  int32_t* __restrict__ exponents, double* __restrict__ loglik,
+                  int8_t* __restrict__ status, double* __restrict__ loglik_sum) {
+  constexpr int SP = 8 * MT;
+  constexpr int LDP = SP + 4;
+  constexpr int KS = SP / 4;   // k-steps
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Pbuf0 = reinterpret_cast<double*>(smem_raw);
+  double* Pbuf1 = Pbuf0 + SP * LDP;
+  double* Ball = Pbuf1 + SP * LDP;                       // [kWarps][SP][kLdB]
+  double* pi_s = Ball + (size_t)kWarps * SP * kLdB;      // [SP]
+  int* estk = reinterpret_cast<int*>(pi_s + SP);         // [kWarps][n_slots][kWarpSites]
+  int4* prog_s = reinterpret_cast<int4*>(estk + kWarps * n_slots * kWarpSites);
+  __shared__ __align__(8) uint64_t full_bar[2];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  double* Bw = Ball + (size_t)warp * SP * kLdB;
+  int* estk_w = estk + warp * n_slots * kWarpSites;
+
+  for (int i = tid; i < n_ops; i += kThreads) prog_s[i] = program[i];
+  for (int i = tid; i < SP; i += kThreads) pi_s[i] = (i < S) ? (root_distn ? root_distn[i] : 1.0) : 0.0;
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto needs_stage = [&](const int4& op) -> bool {
+    const int code = op.x & 0xff;
+    return code == OP_MSG_SLOT || (code == OP_MSG_OBS && OBS != OBS_CODES);
+  };
+  // producer state (thread 0 only)
+  int scan_ip = 0;
+  int issued = 0;
+  auto issue_next = [&]() {
+    while (scan_ip < n_ops && !needs_stage(prog_s[scan_ip])) ++scan_ip;
+    if (scan_ip < n_ops) {
+      const int node = prog_s[scan_ip].y;
+      const int buf = issued & 1;
+      uint64_t* bar = &full_bar[buf];
+      mbar_expect_tx(bar, (uint32_t)(sizeof(double) * SP * LDP));
+      tma_load_1d(buf ? Pbuf1 : Pbuf0, Ppad + (size_t)node * SP * LDP,
+                  (uint32_t)(sizeof(double) * SP * LDP), bar);
+      ++issued;
+      ++scan_ip;
+    }
+  };
+  if (tid == 0) { issue_next(); issue_next(); }
+  int consumed = 0;
+
+  // the sites this thread's C-fragment columns map to
+  const int64_t site0 = (int64_t)blockIdx.x * kTileSites + warp * kWarpSites;
+  int64_t csite[kNT][2];
+  bool cvalid[kNT][2];
+#pragma unroll
+  for (int j = 0; j < kNT; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      csite[j][h] = site0 + 8 * j + 2 * t + h;
+      cvalid[j][h] = csite[j][h] < n_sites;
+    }
+
+  double acc[MT][kNT][2];
+  int esum[kNT][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < kNT; ++j) acc[i][j][0] = acc[i][j][1] = 1.0;
+#pragma unroll
+  for (int j = 0; j < kNT; ++j) esum[j][0] = esum[j][1] = 0;
+  double my_ll = 0.0;
+
+  for (int ip = 0; ip < n_ops; ++ip) {
+    const int4 op = prog_s[ip];
+    const int code = op.x & 0xff;
+    const bool fresh = (op.x >> 8) & 1;
+
+    if (needs_stage(op)) {
+      // ---- fill the warp's B tile (L_c^T, [SP][16 sites]) --------------------
+      if (code == OP_MSG_SLOT) {
+        if (!fresh) {
+          const double* src = STORE ? partials + (int64_t)op.w * S * stride
+                                    : slots_ws + (int64_t)op.z * S * stride;
+          __syncwarp();
+#pragma unroll 4
+          for (int r0 = 0; r0 < SP; r0 += 2) {
+            const int r = r0 + (lane >> 4), c = lane & 15;
+            const int64_t sg = site0 + c;
+            double v = 0.0;
+            if (r < S && sg < n_sites) v = src[(int64_t)r * stride + sg];
+            Bw[r * kLdB + c] = v;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kNT; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) esum[j][h] += estk_w[op.z * kWarpSites + 8 * j + 2 * t + h];
+      } else {   // OP_MSG_OBS with mask / dense observations at a leaf
+        __syncwarp();
+        if (OBS == OBS_MASK) {
+          const unsigned long long* mk = reinterpret_cast<const unsigned long long*>(obs);
+          const int c = lane & 15;
+          const int64_t sg = site0 + c;
+          const unsigned long long m = (sg < n_sites) ? mk[(int64_t)op.z * stride + sg] : ~0ull;
+          for (int r0 = 0; r0 < SP; r0 += 2) {
+            const int r = r0 + (lane >> 4);
+            Bw[r * kLdB + c] = (r < S && ((m >> r) & 1ull)) ? 1.0 : 0.0;
+          }
+        } else {
+          const double* d = reinterpret_cast<const double*>(obs) + (int64_t)op.z * S * stride;
+          for (int r0 = 0; r0 < SP; r0 += 2) {
+            const int r = r0 + (lane >> 4), c = lane & 15;
+            const int64_t sg = site0 + c;
+            double v = (r < S) ? 1.0 : 0.0;
+            if (r < S && sg < n_sites) v = d[(int64_t)r * stride + sg];
+            Bw[r * kLdB + c] = v;
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---- wait for P_c, contract on the tensor pipe --------------------------
+      const int buf = consumed & 1;
+      mbar_wait(&full_bar[buf], (uint32_t)((consumed >> 1) & 1));
+      const double* Ps = buf ? Pbuf1 : Pbuf0;
+      double msg[MT][kNT][2];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) msg[i][j][0] = msg[i][j][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        double bfrag[kNT];
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) bfrag[j] = Bw[(4 * kk + t) * kLdB + 8 * j + g];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const double a = Ps[(8 * i + g) * LDP + 4 * kk + t];
+#pragma unroll
+          for (int j = 0; j < kNT; ++j) dmma884(msg[i][j][0], msg[i][j][1], a, bfrag[j]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) {
+          acc[i][j][0] *= msg[i][j][0];
+          acc[i][j][1] *= msg[i][j][1];
+        }
+      __syncthreads();           // every warp is done with Ps[buf]
+      ++consumed;
+      if (tid == 0) issue_next();
+      continue;
+    }
+
+    switch (code) {
+      case OP_MSG_OBS: {   // leaf with a hard code: column gather from P^T
+        const uint8_t* codes = reinterpret_cast<const uint8_t*>(obs);
+        const double* PTc = PT + (size_t)op.y * SP * SP;
+        const double* rs = rowsum + (size_t)op.y * SP;
+#pragma unroll
+        for (int j = 0; j < kNT; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = cvalid[j][h] ? codes[(int64_t)op.z * stride + csite[j][h]] : RT_MISSING;
+            if (k == RT_MISSING) {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] *= rs[8 * i + g];
+            } else if (k < S) {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] *= PTc[k * SP + 8 * i + g];
+            } else {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] = 0.0;
+            }
+          }
+      } break;
+      case OP_MSG_ONES: {
+        const double* rs = rowsum + (size_t)op.y * SP;
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const double r = rs[8 * i + g];
+#pragma unroll
+          for (int j = 0; j < kNT; ++j) { acc[i][j][0] *= r; acc[i][j][1] *= r; }
+        }
+      } break;
+      case OP_APPLY_OBS: {
+#pragma unroll
+        for (int j = 0; j < kNT; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (!cvalid[j][h]) continue;
+            if (OBS == OBS_CODES) {
+              const int k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + csite[j][h]];
+              if (k != RT_MISSING) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i) acc[i][j][h] = (8 * i + g == k) ? acc[i][j][h] : 0.0;
+              }
+            } else if (OBS == OBS_MASK) {
+              const unsigned long long m =
+                  reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + csite[j][h]];
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] = ((m >> (8 * i + g)) & 1ull) ? acc[i][j][h] : 0.0;
+            } else {
+              const double* d = reinterpret_cast<const double*>(obs) + (int64_t)op.z * S * stride;
+#pragma unroll
+              for (int i = 0; i < MT; ++i) {
+                const int s = 8 * i + g;
+                if (s < S) acc[i][j][h] *= d[(int64_t)s * stride + csite[j][h]];
+              }
+            }
+          }
+      } break;
+      case OP_STORE:
+      case OP_ROOT: {
+        // rows >= S are padding: force them to zero so they never win the max
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+          if (8 * i + g >= S) {
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+          }
+#pragma unroll
+        for (int j = 0; j < kNT; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            double mx = acc[0][j][h];
+#pragma unroll
+            for (int i = 1; i < MT; ++i) mx = fmax(mx, acc[i][j][h]);
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+            if (mx > 0.0) {
+              const int e = rt_exponent(mx);
+              const double sc = rt_pow2_neg(e);
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] *= sc;
+              esum[j][h] += e;
+            }
+          }
+        if (code == OP_STORE) {
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) {
+              double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+              *reinterpret_cast<double2*>(&Bw[(8 * i + g) * kLdB + 8 * j + 2 * t]) = v;
+            }
+          if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < kNT; ++j)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) estk_w[op.z * kWarpSites + 8 * j + 2 * t + h] = esum[j][h];
+          }
+          __syncwarp();
+          // coalesced copy of the tile to HBM (parked slot, or the kept partials)
+          double* dst = STORE ? partials + (int64_t)op.w * S * stride
+                              : slots_ws + (int64_t)op.z * S * stride;
+          for (int r0 = 0; r0 < S; r0 += 2) {
+            const int r = r0 + (lane >> 4), c = lane & 15;
+            const int64_t sg = site0 + c;
+            if (r < S && sg < n_sites) dst[(int64_t)r * stride + sg] = Bw[r * kLdB + c];
+          }
+          if (STORE && exponents && lane < kWarpSites) {
+            const int64_t sg = site0 + lane;
+            if (sg < n_sites) exponents[(int64_t)op.w * stride + sg] = estk_w[op.z * kWarpSites + lane];
+          }
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) acc[i][j][0] = acc[i][j][1] = 1.0;
+#pragma unroll
+          for (int j = 0; j < kNT; ++j) esum[j][0] = esum[j][1] = 0;
+        } else {
+          if (STORE) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+              for (int j = 0; j < kNT; ++j) {
+                double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                *reinterpret_cast<double2*>(&Bw[(8 * i + g) * kLdB + 8 * j + 2 * t]) = v;
+              }
+            __syncwarp();
+            double* dst = partials + (int64_t)op.w * S * stride;
+            for (int r0 = 0; r0 < S; r0 += 2) {
+              const int r = r0 + (lane >> 4), c = lane & 15;
+              const int64_t sg = site0 + c;
+              if (r < S && sg < n_sites) dst[(int64_t)r * stride + sg] = Bw[r * kLdB + c];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < kNT; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              double lk = 0.0;
+#pragma unroll
+              for (int i = 0; i < MT; ++i) lk = fma(pi_s[8 * i + g], acc[i][j][h], lk);
+              lk += __shfl_xor_sync(0xffffffffu, lk, 4);
+              lk += __shfl_xor_sync(0xffffffffu, lk, 8);
+              lk += __shfl_xor_sync(0xffffffffu, lk, 16);
+              if (g == 0 && cvalid[j][h]) {
+                if (STORE && exponents) exponents[(int64_t)op.w * stride + csite[j][h]] = esum[j][h];
+                if (lk > 0.0) {
+                  const double ll = log(lk) + (double)esum[j][h] * RT_LN2;
+                  loglik[csite[j][h]] = ll;
+                  status[csite[j][h]] = RT_SITE_OK;
+                  my_ll += ll;
+                } else {
+                  loglik[csite[j][h]] = -INFINITY;
+                  status[csite[j][h]] = RT_SITE_STRUCTURAL_ZERO;
+                }
+              }
+            }
+        }
+      } break;
+      default: break;
+    }
+  }
+
+  if (loglik_sum) {
+    const double w = rt_warp_sum(my_ll);
+    if (lane == 0 && w != 0.0) atomicAdd(loglik_sum, w);
+  }
+}
+
+template <int MT, int OBS, bool STORE>
+int launch(int S, int64_t n_sites, int64_t stride, const int4* program, int n_ops, int n_slots,
+           const double* Ppad, const double* PT, const double* rowsum, const double* root_distn,
+           const void* obs, double* slots_ws, double* partials, int32_t* exponents, double* loglik,
+           int8_t* status, double* loglik_sum, cudaStream_t stream) {
+  constexpr int SP = 8 * MT;
+  constexpr int LDP = SP + 4;
+  auto kern = prune_dmma_kernel<MT, OBS, STORE>;
+  size_t smem = sizeof(double) * (2 * SP * LDP + (size_t)kWarps * SP * kLdB + SP) +
+                sizeof(int) * (size_t)kWarps * n_slots * kWarpSites + sizeof(int4) * (size_t)n_ops;
+  smem = (smem + 15) & ~(size_t)15;
+  if (smem > 220 * 1024) return RT_ERR_UNSUPPORTED;
+  RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((n_sites + kTileSites - 1) / kTileSites);
+  kern<<<grid, kThreads, smem, stream>>>(S, n_sites, stride, program, n_ops, n_slots, Ppad, PT,
+                                         rowsum, root_distn, obs, slots_ws, partials, exponents,
+                                         loglik, status, loglik_sum);
+  RT_CUDA_CHECK(cudaGetLastError());
+  return RT_OK;
+}
+
+template <int MT>
+int launch_mt(int S, int obs_kind, bool store, int64_t n_sites, int64_t stride, const int4* program,
+              int n_ops, int n_slots, const double* Ppad, const double* PT, const double* rowsum,
+              const double* root_distn, const void* obs, double* slots_ws, double* partials,
+              int32_t* exponents, double* loglik, int8_t* status, double* loglik_sum,
+              cudaStream_t stream) {
+#define RT_ARGS S, n_sites, stride, program, n_ops, n_slots, Ppad, PT, rowsum, root_distn, obs, \
+                slots_ws, partials, exponents, loglik, status, loglik_sum, stream
+  switch (obs_kind) {
+    case OBS_CODES: return store ? launch<MT, OBS_CODES, true>(RT_ARGS) : launch<MT, OBS_CODES, false>(RT_ARGS);
+    case OBS_MASK:  return store ? launch<MT, OBS_MASK, true>(RT_ARGS)  : launch<MT, OBS_MASK, false>(RT_ARGS);
+    case OBS_DENSE: return store ? launch<MT, OBS_DENSE, true>(RT_ARGS) : launch<MT, OBS_DENSE, false>(RT_ARGS);
+  }
+#undef RT_ARGS
+  return RT_ERR_ARG;
+}
+
+}  // namespace
+
+int rt_prune_dmma_dispatch(int S, int obs_kind, bool store, int64_t n_sites, int64_t stride,
+                           const int32_t* program, int n_ops, int n_slots, int n_nodes,
+                           const double* P, const double* root_distn, const void* obs,
+                           double* partials, int32_t* exponents, double* loglik, int8_t* status,
+                           double* loglik_sum, cudaStream_t stream) {
+  if (n_slots > kMaxSlots) return RT_ERR_UNSUPPORTED;
+  const int MT = (S + 15) / 16 * 2;     // padded states 16 / 32 / 48 / 64
+  const int SP = 8 * MT, LDP = SP + 4;
+  double* ws = nullptr;
+  const size_t n_pad = (size_t)n_nodes * SP * LDP, n_pt = (size_t)n_nodes * SP * SP,
+               n_rs = (size_t)n_nodes * SP;
+  const size_t n_slot = store ? 0 : (size_t)n_slots * S * (size_t)stride;
+  RT_CUDA_CHECK(cudaMallocAsync(&ws, sizeof(double) * (n_pad + n_pt + n_rs + n_slot), stream));
+  double* Ppad = ws;
+  double* PT = Ppad + n_pad;
+  double* rowsum = PT + n_pt;
+  double* slots_ws = store ? nullptr : rowsum + n_rs;
+  pack_kernel<<<n_nodes, 256, 0, stream>>>(P, S, SP, n_nodes, Ppad, PT, rowsum);
+  const int4* prog = reinterpret_cast<const int4*>(program);
+  int rc;
+#define RT_ARGS S, obs_kind, store, n_sites, stride, prog, n_ops, n_slots, Ppad, PT, rowsum, \
+                root_distn, obs, slots_ws, partials, exponents, loglik, status, loglik_sum, stream
+  switch (MT) {
+    case 2: rc = launch_mt<2>(RT_ARGS); break;
+    case 4: rc = launch_mt<4>(RT_ARGS); break;
+    case 6: rc = launch_mt<6>(RT_ARGS); break;
+    case 8: rc = launch_mt<8>(RT_ARGS); break;
+    default: rc = RT_ERR_UNSUPPORTED;
+  }
+#undef RT_ARGS
+  cudaFreeAsync(ws, stream);
+  return rc;
+}

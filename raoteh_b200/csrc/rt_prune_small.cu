@@ -1,0 +1,264 @@
+// K2: Felsenstein pruning for small state spaces (S <= 8), one thread per site.
+//
+// Replaces, batched over sites, the reference's per-site chain
+//   pyfelscore.mcy_esd_get_node_to_pmap  (called raoteh/sampler/_mcy_dense.py:286-291,
+//   spec _mcy.py:611-682, emissions _mcz.py:138-163)
+//   + _mc0_dense.get_likelihood (raoteh/sampler/_mc0_dense.py:147-212).
+//
+// Each thread walks the host-built upward program (lowering.TreeSchedule.
+// up_program) for its site.  Partials of nodes whose parent has not been
+// processed yet live in a per-thread stack in shared memory
+// ([slot][state][thread], conflict-free); transition matrices are staged once
+// per CTA in shared memory and read as warp-uniform broadcasts.  Every stored
+// partial is rescaled by an exact power of two and the integer exponent is
+// carried, so log-likelihoods never underflow and the scaling adds no rounding.
+// HBM traffic per site: the observation row(s) in, 8 B log-lik + 1 B status out
+// (+ the stored partials when the posterior pass will follow).
+#include "rt_common.cuh"
+
+namespace {
+
+constexpr int kBlock = 128;
+
+template <int S>
+struct ObsCodes {
+  const uint8_t* p; int64_t stride;
+  __device__ __forceinline__ int code(int slot, int64_t site) const {
+    return p[(int64_t)slot * stride + site];
+  }
+};
+
+template <int S, int OBS, bool STORE>
+__global__ void __launch_bounds__(kBlock)
+prune_small_kernel(int64_t n_sites, int64_t stride,
+                   const int4* __restrict__ program, int n_ops, int n_slots, int n_nodes,
+                   const double* __restrict__ P, int p_in_smem,
+                   const double* __restrict__ root_distn,
+                   const void* __restrict__ obs,
+                   double* __restrict__ partials, int32_t* __restrict__ exponents,
+                   double* __restrict__ loglik, int8_t* __restrict__ status,
+                   double* __restrict__ loglik_sum) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // carve: program | pi | rowsum | P (optional) | stack doubles | stack exponents
+  int4* prog_s = reinterpret_cast<int4*>(smem_raw);
+  double* pi_s = reinterpret_cast<double*>(prog_s + n_ops);
+  double* rowsum_s = pi_s + S;
+  double* P_s = rowsum_s + (size_t)n_nodes * S;
+  double* stk = P_s + (p_in_smem ? (size_t)n_nodes * S * S : 0);
+  int* estk = reinterpret_cast<int*>(stk + (size_t)n_slots * S * kBlock);
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_ops; i += kBlock) prog_s[i] = program[i];
+  if (tid < S) pi_s[tid] = root_distn ? root_distn[tid] : 1.0;
+  for (int i = tid; i < n_nodes * S; i += kBlock) {
+    double r = 0.0;
+#pragma unroll
+    for (int b = 0; b < S; ++b) r += P[(size_t)i * S + b];
+    rowsum_s[i] = r;
+  }
+  if (p_in_smem)
+    for (int i = tid; i < n_nodes * S * S; i += kBlock) P_s[i] = P[i];
+  __syncthreads();
+  const double* Pm = p_in_smem ? P_s : P;
+
+  const int64_t site = (int64_t)blockIdx.x * kBlock + tid;
+  const bool active = site < n_sites;
+  double my_ll = 0.0;
+
+  if (active) {
+    double acc[S];
+#pragma unroll
+    for (int a = 0; a < S; ++a) acc[a] = 1.0;
+    int esum = 0;
+
+    for (int ip = 0; ip < n_ops; ++ip) {
+      const int4 op = prog_s[ip];
+      const double* Pc = Pm + (size_t)op.y * S * S;
+      switch (op.x & 0xff) {
+        case OP_MSG_SLOT: {
+          double v[S];
+#pragma unroll
+          for (int b = 0; b < S; ++b) v[b] = stk[(op.z * S + b) * kBlock + tid];
+          esum += estk[op.z * kBlock + tid];
+#pragma unroll
+          for (int a = 0; a < S; ++a) {
+            double m = 0.0;
+#pragma unroll
+            for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], v[b], m);
+            acc[a] *= m;
+          }
+        } break;
+        case OP_MSG_OBS: {
+          if (OBS == OBS_CODES) {
+            const int k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site];
+            if (k == RT_MISSING) {
+#pragma unroll
+              for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y * S + a];
+            } else if (k < S) {
+#pragma unroll
+              for (int a = 0; a < S; ++a) acc[a] *= Pc[a * S + k];
+            } else {
+#pragma unroll
+              for (int a = 0; a < S; ++a) acc[a] = 0.0;
+            }
+          } else {
+            double v[S];
+            if (OBS == OBS_MASK) {
+              const unsigned long long mk =
+                  reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site];
+#pragma unroll
+              for (int b = 0; b < S; ++b) v[b] = ((mk >> b) & 1ull) ? 1.0 : 0.0;
+            } else {
+              const double* d = reinterpret_cast<const double*>(obs);
+#pragma unroll
+              for (int b = 0; b < S; ++b) v[b] = d[((int64_t)op.z * S + b) * stride + site];
+            }
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+              double m = 0.0;
+#pragma unroll
+              for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], v[b], m);
+              acc[a] *= m;
+            }
+          }
+        } break;
+        case OP_MSG_ONES: {
+#pragma unroll
+          for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y * S + a];
+        } break;
+        case OP_APPLY_OBS: {
+          if (OBS == OBS_CODES) {
+            const int k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site];
+            if (k != RT_MISSING) {
+#pragma unroll
+              for (int a = 0; a < S; ++a) acc[a] = (a == k) ? acc[a] : 0.0;
+            }
+          } else if (OBS == OBS_MASK) {
+            const unsigned long long mk =
+                reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site];
+#pragma unroll
+            for (int a = 0; a < S; ++a) acc[a] = ((mk >> a) & 1ull) ? acc[a] : 0.0;
+          } else {
+            const double* d = reinterpret_cast<const double*>(obs);
+#pragma unroll
+            for (int a = 0; a < S; ++a) acc[a] *= d[((int64_t)op.z * S + a) * stride + site];
+          }
+        } break;
+        case OP_STORE:
+        case OP_ROOT: {
+          double mx = acc[0];
+#pragma unroll
+          for (int a = 1; a < S; ++a) mx = fmax(mx, acc[a]);
+          if (mx > 0.0) {
+            const int e = rt_exponent(mx);
+            const double sc = rt_pow2_neg(e);
+#pragma unroll
+            for (int a = 0; a < S; ++a) acc[a] *= sc;
+            esum += e;
+          }
+          if (STORE && op.w >= 0) {
+#pragma unroll
+            for (int a = 0; a < S; ++a)
+              partials[((int64_t)op.w * S + a) * stride + site] = acc[a];
+            if (exponents) exponents[(int64_t)op.w * stride + site] = esum;
+          }
+          if ((op.x & 0xff) == OP_STORE) {
+#pragma unroll
+            for (int a = 0; a < S; ++a) stk[(op.z * S + a) * kBlock + tid] = acc[a];
+            estk[op.z * kBlock + tid] = esum;
+#pragma unroll
+            for (int a = 0; a < S; ++a) acc[a] = 1.0;
+            esum = 0;
+          } else {
+            double lk = 0.0;
+#pragma unroll
+            for (int a = 0; a < S; ++a) lk = fma(pi_s[a], acc[a], lk);
+            if (lk > 0.0) {
+              my_ll = log(lk) + (double)esum * RT_LN2;
+              loglik[site] = my_ll;
+              status[site] = RT_SITE_OK;
+            } else {
+              loglik[site] = -INFINITY;
+              status[site] = RT_SITE_STRUCTURAL_ZERO;
+              my_ll = 0.0;
+            }
+          }
+        } break;
+        default: break;
+      }
+    }
+  }
+
+  if (loglik_sum) {
+    __shared__ double red[kBlock / 32];
+    double w = rt_warp_sum(my_ll);
+    if ((tid & 31) == 0) red[tid >> 5] = w;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int i = 0; i < kBlock / 32; ++i) t += red[i];
+      atomicAdd(loglik_sum, t);
+    }
+  }
+}
+
+template <int S, int OBS, bool STORE>
+int launch_t(int64_t n_sites, int64_t stride, const int4* program, int n_ops, int n_slots,
+             int n_nodes, const double* P, const double* root_distn, const void* obs,
+             double* partials, int32_t* exponents, double* loglik, int8_t* status,
+             double* loglik_sum, cudaStream_t stream) {
+  auto kern = prune_small_kernel<S, OBS, STORE>;
+  size_t base = (size_t)n_ops * sizeof(int4) + sizeof(double) * (S + (size_t)n_nodes * S);
+  size_t stack = (size_t)n_slots * S * kBlock * sizeof(double) + (size_t)n_slots * kBlock * sizeof(int);
+  size_t pbytes = (size_t)n_nodes * S * S * sizeof(double);
+  const size_t limit = 200 * 1024;
+  int p_in_smem = (base + stack + pbytes <= 96 * 1024) ? 1 : 0;
+  size_t smem = base + stack + (p_in_smem ? pbytes : 0);
+  if (smem > limit) return RT_ERR_UNSUPPORTED;
+  RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t grid = (n_sites + kBlock - 1) / kBlock;
+  kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
+                                                P, p_in_smem, root_distn, obs, partials, exponents,
+                                                loglik, status, loglik_sum);
+  RT_CUDA_CHECK(cudaGetLastError());
+  return RT_OK;
+}
+
+template <int S>
+int launch_s(int obs_kind, bool store, int64_t n_sites, int64_t stride, const int4* program,
+             int n_ops, int n_slots, int n_nodes, const double* P, const double* root_distn,
+             const void* obs, double* partials, int32_t* exponents, double* loglik,
+             int8_t* status, double* loglik_sum, cudaStream_t stream) {
+#define RT_ARGS n_sites, stride, program, n_ops, n_slots, n_nodes, P, root_distn, obs, partials, \
+                exponents, loglik, status, loglik_sum, stream
+  switch (obs_kind) {
+    case OBS_CODES: return store ? launch_t<S, OBS_CODES, true>(RT_ARGS) : launch_t<S, OBS_CODES, false>(RT_ARGS);
+    case OBS_MASK:  return store ? launch_t<S, OBS_MASK, true>(RT_ARGS)  : launch_t<S, OBS_MASK, false>(RT_ARGS);
+    case OBS_DENSE: return store ? launch_t<S, OBS_DENSE, true>(RT_ARGS) : launch_t<S, OBS_DENSE, false>(RT_ARGS);
+  }
+#undef RT_ARGS
+  return RT_ERR_ARG;
+}
+
+}  // namespace
+
+int rt_prune_small_dispatch(int S, int obs_kind, bool store, int64_t n_sites, int64_t stride,
+                            const int32_t* program, int n_ops, int n_slots, int n_nodes,
+                            const double* P, const double* root_distn, const void* obs,
+                            double* partials, int32_t* exponents, double* loglik, int8_t* status,
+                            double* loglik_sum, cudaStream_t stream) {
+  const int4* prog = reinterpret_cast<const int4*>(program);
+#define RT_ARGS obs_kind, store, n_sites, stride, prog, n_ops, n_slots, n_nodes, P, root_distn, \
+                obs, partials, exponents, loglik, status, loglik_sum, stream
+  switch (S) {
+    case 2: return launch_s<2>(RT_ARGS);
+    case 3: return launch_s<3>(RT_ARGS);
+    case 4: return launch_s<4>(RT_ARGS);
+    case 5: return launch_s<5>(RT_ARGS);
+    case 6: return launch_s<6>(RT_ARGS);
+    case 7: return launch_s<7>(RT_ARGS);
+    case 8: return launch_s<8>(RT_ARGS);
+  }
+#undef RT_ARGS
+  return RT_ERR_UNSUPPORTED;
+}

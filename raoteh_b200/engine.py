@@ -1,0 +1,223 @@
+"""
+Batched tree-MJP engine: the host side of the hot path.
+
+Lowers (tree, Q, observations) to device tensors (PyTorch owns memory and
+streams), then calls the CUDA kernels through the C ABI (include/rt_b200.h).
+One `TreeMJP` = one (tree, rate matrices, root prior); its methods take a
+whole batch of sites.  The scalar, reference-shaped functions in
+raoteh_b200.sampler are thin wrappers over batch size 1.
+
+Reference call stacks replaced:
+  _mjp_dense.get_likelihood                  raoteh/sampler/_mjp_dense.py:362-407
+  _mjp_dense.get_expected_history_statistics raoteh/sampler/_mjp_dense.py:410-539
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native
+from .lowering import TreeSchedule, MISSING
+
+OBS_CODES, OBS_MASK, OBS_DENSE = 0, 1, 2
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Observations(object):
+    """Device-resident observations for a batch of sites.
+
+    kind OBS_CODES: data uint8  [n_obs, stride]      (255 = unobserved)
+    kind OBS_MASK : data int64  [n_obs, stride]      (bit s set = state s allowed)
+    kind OBS_DENSE: data float64[n_obs, S, stride]   (emission likelihoods)
+    obs_slot[n_nodes]: row of `data` per tree node, -1 = unobserved node.
+    """
+
+    def __init__(self, kind, data, obs_slot, n_sites):
+        self.kind = kind
+        self.data = data
+        self.obs_slot = np.asarray(obs_slot, dtype=np.int32)
+        self.n_sites = int(n_sites)
+        self.stride = int(data.shape[-1])
+
+    @classmethod
+    def from_leaf_codes(cls, sched, codes, leaf_nodes=None, device='cuda', pinned=None):
+        """codes: uint8 [n_leaves, n_sites] host array (numpy) or device tensor."""
+        leaf_nodes = sched.leaves if leaf_nodes is None else np.asarray(leaf_nodes)
+        obs_slot = np.full(sched.n, -1, dtype=np.int32)
+        obs_slot[leaf_nodes] = np.arange(len(leaf_nodes), dtype=np.int32)
+        if isinstance(codes, np.ndarray):
+            host = torch.from_numpy(np.ascontiguousarray(codes, dtype=np.uint8))
+            data = host.to(device, non_blocking=False)
+        else:
+            data = codes.to(device=device, dtype=torch.uint8).contiguous()
+        return cls(OBS_CODES, data, obs_slot, data.shape[1])
+
+    @classmethod
+    def from_masks(cls, sched, mask, device='cuda'):
+        """mask: uint64 [n_nodes, n_sites]; full-mask rows may be dropped by the caller."""
+        mask = np.ascontiguousarray(mask).view(np.int64)
+        obs_slot = np.arange(sched.n, dtype=np.int32)
+        data = torch.from_numpy(mask).to(device)
+        return cls(OBS_MASK, data, obs_slot, data.shape[1])
+
+    @classmethod
+    def from_dense(cls, sched, lik, nodes, device='cuda'):
+        """lik: float64 [len(nodes), S, n_sites] emission likelihoods of `nodes`."""
+        obs_slot = np.full(sched.n, -1, dtype=np.int32)
+        obs_slot[np.asarray(nodes)] = np.arange(len(nodes), dtype=np.int32)
+        data = torch.from_numpy(np.ascontiguousarray(lik, dtype=np.float64)).to(device)
+        return cls(OBS_DENSE, data, obs_slot, data.shape[2])
+
+
+class TreeMJP(object):
+    """Markov jump process on a rooted tree, evaluated for batches of sites."""
+
+    def __init__(self, sched, Q, root_distn=None, q_index=None, device='cuda', P=None):
+        if not torch.cuda.is_available():
+            raise _native.NativeError('raoteh_b200 needs a CUDA device; there is no CPU fallback')
+        _native.lib()
+        self.sched = sched
+        self.device = torch.device(device)
+        Q = np.asarray(Q, dtype=np.float64)
+        self.Q_host = Q if Q.ndim == 3 else Q[None]
+        self.S = int(self.Q_host.shape[-1])
+        if self.S < 2 or self.S > 64:
+            raise ValueError('number of states must be in 2..64')
+        self.q_index_host = None if q_index is None else np.asarray(q_index, dtype=np.int32)
+        self.Q = torch.from_numpy(np.ascontiguousarray(self.Q_host)).to(self.device)
+        self.q_index = (None if self.q_index_host is None
+                        else torch.from_numpy(self.q_index_host).to(self.device))
+        self.length = torch.from_numpy(sched.length.copy()).to(self.device)
+        self.root_distn_host = None if root_distn is None else np.asarray(root_distn, np.float64)
+        self.root_distn = (None if root_distn is None
+                           else torch.from_numpy(self.root_distn_host.copy()).to(self.device))
+        self.parent = torch.from_numpy(sched.parent.copy()).to(self.device)
+        self._P = None
+        if P is not None:   # caller-supplied per-edge transition matrices [n,S,S]
+            self._P = torch.from_numpy(np.ascontiguousarray(P, dtype=np.float64)).to(self.device)
+        self._prog_cache = {}
+
+    # ---- K1 ---------------------------------------------------------------
+    def transition_matrices(self):
+        """P[b] = expm(Q_b t_b) for every node b (slot 0 = identity); cached."""
+        if self._P is None:
+            n, S = self.sched.n, self.S
+            P = torch.empty((n, S, S), dtype=torch.float64, device=self.device)
+            rc = _native.lib().rt_expm_batched(_ptr(self.Q), _ptr(self.q_index), _ptr(self.length),
+                                               n, S, _ptr(P), _stream())
+            _native.check(rc, 'rt_expm_batched')
+            self._P = P
+        return self._P
+
+    def _programs(self, obs):
+        key = obs.obs_slot.tobytes()
+        hit = self._prog_cache.get(key)
+        if hit is None:
+            ops, n_slots = self.sched.up_program(obs.obs_slot)
+            edges, level_ptr = self.sched.down_program(obs.obs_slot)
+            hit = dict(ops=torch.from_numpy(ops).to(self.device), n_ops=len(ops), n_slots=n_slots,
+                       edges=torch.from_numpy(edges).to(self.device),
+                       level_ptr=np.ascontiguousarray(level_ptr, dtype=np.int32))
+            self._prog_cache[key] = hit
+        return hit
+
+    # ---- A4 ---------------------------------------------------------------
+    def support_sets(self, mask):
+        """In-place structural-support pruning of int64 bitmasks [n_nodes, stride]."""
+        P = self.transition_matrices()
+        n_sites = mask.shape[1]
+        rc = _native.lib().rt_support_sets(self.S, self.sched.n, n_sites, mask.shape[1],
+                                           _ptr(self.parent), _ptr(P), _ptr(mask), _stream())
+        _native.check(rc, 'rt_support_sets')
+        return mask
+
+    # ---- K2 / K3 ------------------------------------------------------------
+    def log_likelihood(self, obs, keep_partials=False, want_exponents=False, out=None,
+                       loglik_sum=None):
+        """Per-site log-likelihood.  Returns dict(loglik, status[, partials, exponents])."""
+        P = self.transition_matrices()
+        prog = self._programs(obs)
+        N, stride = obs.n_sites, obs.stride
+        dev = self.device
+        if out is None:
+            loglik = torch.empty(N, dtype=torch.float64, device=dev)
+            status = torch.empty(N, dtype=torch.int8, device=dev)
+        else:
+            loglik, status = out
+        partials = exponents = None
+        if keep_partials:
+            partials = torch.empty((self.sched.n_store, self.S, stride), dtype=torch.float64, device=dev)
+            if want_exponents:
+                exponents = torch.empty((self.sched.n_store, stride), dtype=torch.int32, device=dev)
+        rc = _native.lib().rt_prune_loglik(
+            self.S, self.sched.n, N, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
+            _ptr(P), _ptr(self.root_distn), obs.kind, _ptr(obs.data), _ptr(partials),
+            _ptr(exponents), _ptr(loglik), _ptr(status), _ptr(loglik_sum), _stream())
+        _native.check(rc, 'rt_prune_loglik')
+        res = dict(loglik=loglik, status=status)
+        if keep_partials:
+            res['partials'] = partials
+            res['exponents'] = exponents
+        return res
+
+    # ---- K4 / K5 ------------------------------------------------------------
+    def posterior(self, obs, want_exponents=False):
+        """Up + down pass.  Returns loglik, status, partials, node_distn (internal
+        nodes, by store index), W[n,S,S] (site-summed J/P weights), root_post_sum[S]."""
+        up = self.log_likelihood(obs, keep_partials=True, want_exponents=want_exponents)
+        prog = self._programs(obs)
+        N, stride = obs.n_sites, obs.stride
+        dev = self.device
+        P = self.transition_matrices()
+        node_distn = torch.empty((self.sched.n_store, self.S, stride), dtype=torch.float64, device=dev)
+        W = torch.zeros((self.sched.n, self.S, self.S), dtype=torch.float64, device=dev)
+        root_post_sum = torch.zeros(self.S, dtype=torch.float64, device=dev)
+        lp = prog['level_ptr']
+        rc = _native.lib().rt_posterior_stats(
+            self.S, self.sched.n, N, stride, _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
+            _ptr(P), _ptr(self.root_distn), obs.kind, _ptr(obs.data), _ptr(up['partials']),
+            _ptr(up['status']), _ptr(node_distn), _ptr(W), _ptr(root_post_sum), _stream())
+        _native.check(rc, 'rt_posterior_stats')
+        up.update(node_distn=node_distn, W=W, root_post_sum=root_post_sum)
+        return up
+
+    def frechet_contract(self, W):
+        """M[b] = L(t_b Q_b^T, t_b W[b]) for every node b (slot 0 -> 0)."""
+        n, S = self.sched.n, self.S
+        M = torch.empty((n, S, S), dtype=torch.float64, device=self.device)
+        rc = _native.lib().rt_frechet_contract(_ptr(self.Q), _ptr(self.q_index), _ptr(self.length),
+                                               _ptr(W), n, S, _ptr(M), _stream())
+        _native.check(rc, 'rt_frechet_contract')
+        return M
+
+    def expected_history_statistics(self, obs):
+        """Site-summed expected dwell[S], transition counts[S,S], root posterior sum[S],
+        per-site loglik, per-edge contraction matrices M_edges[n,S,S].
+
+        dwell[c] = sum_b M_b[c,c]; trans[c,d] = Q_b[c,d] * M_b[c,d] summed over
+        edges (raoteh/sampler/_mjp_dense.py:497-533 with one Frechet derivative per
+        edge, the form of examples/code2x3/extras.py:108-129)."""
+        post = self.posterior(obs)
+        M = self.frechet_contract(post['W'])
+        M[0].zero_()
+        S = self.S
+        if self.q_index is None:
+            Qe = self.Q[0].expand(self.sched.n, S, S)
+        else:
+            Qe = self.Q[self.q_index.long()]
+        eye = torch.eye(S, dtype=torch.bool, device=self.device)
+        dwell = torch.diagonal(M, dim1=1, dim2=2).sum(dim=0)
+        trans = (Qe.masked_fill(eye, 0.0) * M).sum(dim=0)
+        post.update(dwell=dwell, trans=trans, M_edges=M, Q_edges=Qe)
+        return post

@@ -1,0 +1,285 @@
+"""Parity of the CUDA path (through the C ABI) against the pinned oracle and the
+committed golden fixtures.  Tolerance: relative 1e-10 on log-likelihoods and
+expectations in fp64 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import scipy.linalg
+
+from oracle import np_oracle
+from helpers import load_golden, case_sched_mask, oracle_obs_from_mask
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+@pytest.fixture(scope='module')
+def rt():
+    import torch
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    import raoteh_b200.engine as engine
+    return engine
+
+
+def _engine_case(rt, case):
+    T, root, sched, mask = case_sched_mask(case)
+    S = case['nstates']
+    Q = np.array(case['Q'])
+    pi = None if case.get('root_distn') is None else np.array(case['root_distn'])
+    mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+    obs = rt.Observations.from_masks(sched, mask[:, None])
+    return sched, Q, pi, mjp, obs, mask
+
+
+@pytest.mark.parametrize('S', [2, 3, 4, 6, 20, 48, 61, 64])
+def test_expm_matches_scipy(rt, S):
+    # t in 2^[-5,5] as raoteh/sampler/tests/test_expm.py:48-82
+    import torch
+    rng = np.random.default_rng(1234 + S)
+    Q = rng.exponential(1.0, size=(3, S, S))
+    Q[1] *= rng.random((S, S)) < 0.3
+    for q in Q:
+        np.fill_diagonal(q, 0)
+        q -= np.diag(q.sum(axis=1))
+    t = 2.0 ** rng.uniform(-5, 5, size=24)
+    q_index = rng.integers(0, 3, size=24).astype(np.int32)
+    dev = torch.device('cuda')
+    P = torch.empty((24, S, S), dtype=torch.float64, device=dev)
+    from raoteh_b200 import _native
+    rc = _native.lib().rt_expm_batched(
+        torch.from_numpy(Q).to(dev).data_ptr(), torch.from_numpy(q_index).to(dev).data_ptr(),
+        torch.from_numpy(t).to(dev).data_ptr(), 24, S, P.data_ptr(),
+        torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, 'rt_expm_batched')
+    P = P.cpu().numpy()
+    for m in range(24):
+        ref = scipy.linalg.expm(Q[q_index[m]] * t[m])
+        np.testing.assert_allclose(P[m], ref, rtol=0, atol=2e-13)
+        np.testing.assert_allclose(P[m].sum(axis=1), 1.0, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('S', [2, 4, 6, 20, 48, 61])
+def test_frechet_contract_matches_scipy(rt, S):
+    import torch
+    from raoteh_b200 import _native
+    rng = np.random.default_rng(99 + S)
+    Q = rng.exponential(1.0, size=(1, S, S))
+    np.fill_diagonal(Q[0], 0)
+    Q[0] -= np.diag(Q[0].sum(axis=1))
+    Q[0] /= np.abs(np.diag(Q[0])).mean()
+    n = 12
+    t = 2.0 ** rng.uniform(-5, 3, size=n)
+    W = rng.exponential(1.0, size=(n, S, S)) * (rng.random((n, S, S)) < 0.5)
+    W[3] = 0.0
+    dev = torch.device('cuda')
+    M = torch.empty((n, S, S), dtype=torch.float64, device=dev)
+    rc = _native.lib().rt_frechet_contract(
+        torch.from_numpy(Q).to(dev).data_ptr(), None, torch.from_numpy(t).to(dev).data_ptr(),
+        torch.from_numpy(W).to(dev).data_ptr(), n, S, M.data_ptr(),
+        torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, 'rt_frechet_contract')
+    M = M.cpu().numpy()
+    for m in range(n):
+        ref = np_oracle.frechet_contract(Q[0], t[m], W[m])
+        scale = max(np.abs(ref).max(), 1e-300)
+        np.testing.assert_allclose(M[m] / scale, ref / scale, rtol=0, atol=1e-12)
+
+
+def test_golden_code2x3(rt):
+    g = load_golden('code2x3.json')
+    for call in g['calls']:
+        sched, Q, pi, mjp, obs, mask = _engine_case(rt, call)
+        if call['kind'] == 'likelihood':
+            r = mjp.log_likelihood(obs)
+            assert int(r['status'][0]) == 0
+            np.testing.assert_allclose(np.exp(float(r['loglik'][0])), call['out'], rtol=RTOL)
+        else:
+            E = np.ones_like(Q) - np.eye(len(Q)) if call['E'] is None else np.array(call['E'])
+            r = mjp.expected_history_statistics(obs)
+            per_edge = (E[None] * Q[None] * r['M_edges'].cpu().numpy()).sum(axis=(1, 2))
+            for a, b, v in call['out']:
+                np.testing.assert_allclose(per_edge[sched.node_index[b]], v, rtol=1e-9, atol=1e-12)
+
+
+def test_golden_random_cases(rt):
+    g = load_golden('mjp_random.json')
+    for case in g['cases']:
+        sched, Q, pi, mjp, obs, mask = _engine_case(rt, case)
+        S = case['nstates']
+        r = mjp.expected_history_statistics(obs)
+        if 'raises' in case:
+            assert int(r['status'][0]) == 1
+            continue
+        assert int(r['status'][0]) == 0
+        np.testing.assert_allclose(np.exp(float(r['loglik'][0])), case['likelihood'], rtol=RTOL)
+        np.testing.assert_allclose(r['dwell'].cpu().numpy(), case['dwell'], rtol=1e-9, atol=1e-12)
+        ref_trans = np.array(case['trans'])
+        np.fill_diagonal(ref_trans, 0.0)   # dense-reference quirk, see np_oracle._finish_ehs
+        np.testing.assert_allclose(r['trans'].cpu().numpy(), ref_trans, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(r['root_post_sum'].cpu().numpy(), case['root_post'],
+                                   rtol=1e-10, atol=1e-14)
+        nd = r['node_distn'].cpu().numpy()
+        for v, d in case['node_distn'].items():
+            i = sched.node_index[int(v)]
+            if sched.store_index[i] >= 0:
+                np.testing.assert_allclose(nd[sched.store_index[i], :, 0], d, rtol=1e-10, atol=1e-14)
+
+
+def _synthetic(name, n_sites, seed, n_leaves, S):
+    from raoteh_b200 import synth
+    rng = np.random.default_rng(seed)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.1 if S == 4 else 0.05, rng)
+    if S == 4:
+        Q, pi = synth.hky85()
+    else:
+        Q, pi, _ = synth.mg94()
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.01)
+    return parent, length, leaves, Q, pi, codes
+
+
+@pytest.mark.parametrize('S,n_leaves,n_sites', [(4, 32, 3001), (61, 16, 300), (61, 128, 515)])
+def test_loglik_codes_matches_oracle(rt, S, n_leaves, n_sites):
+    from raoteh_b200.lowering import TreeSchedule
+    parent, length, leaves, Q, pi, codes = _synthetic('x', n_sites, 7 + S, n_leaves, S)
+    sched = TreeSchedule(parent, length)
+    mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+    obs = rt.Observations.from_leaf_codes(sched, codes, leaves)
+    r = mjp.log_likelihood(obs, keep_partials=True, want_exponents=True)
+    P_gpu = mjp.transition_matrices().cpu().numpy()
+    P = np_oracle.expm_edges(Q, length)
+    np.testing.assert_allclose(P_gpu[1:], P[1:], rtol=0, atol=1e-13)
+    oobs = np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes)
+    ll, st = np_oracle.log_likelihood(parent, P, oobs, pi)
+    assert (r['status'].cpu().numpy() == st).all()
+    np.testing.assert_allclose(r['loglik'].cpu().numpy(), ll, rtol=RTOL)
+    # stored partials: true value = partial * 2^exponent
+    L, ls = np_oracle.prune(parent, P, oobs)
+    part = r['partials'].cpu().numpy()
+    expo = r['exponents'].cpu().numpy()
+    for v in sched.internal[:: max(1, len(sched.internal) // 7)]:
+        k = sched.store_index[v]
+        mine = np.log(part[k].T) + expo[k][:, None] * np.log(2.0)
+        with np.errstate(divide='ignore'):
+            ref = np.log(L[v]) + ls[v][:, None]
+        ok = np.isfinite(ref)
+        np.testing.assert_allclose(mine[ok], ref[ok], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize('S,n_leaves,n_sites', [(4, 32, 2000), (5, 9, 700), (61, 24, 260)])
+def test_loglik_mask_and_dense_match_oracle(rt, S, n_leaves, n_sites):
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200 import synth
+    rng = np.random.default_rng(31 + S)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.1, rng)
+    if S == 61:
+        Q, pi, _ = synth.mg94()
+    else:
+        Q = rng.exponential(1.0, size=(S, S))
+        np.fill_diagonal(Q, 0)
+        Q -= np.diag(Q.sum(axis=1))
+        pi = rng.dirichlet(np.ones(S))
+    n = len(parent)
+    sched = TreeSchedule(parent, length)
+    mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+    P = np_oracle.expm_edges(Q, length)
+    # y-type: random allowed sets at every node (internal nodes mostly unrestricted)
+    bits = rng.random((n, n_sites, S)) < 0.5
+    bits[np.arange(n)[:, None], np.arange(n_sites)[None, :], rng.integers(0, S, size=(n, n_sites))] = True
+    unrestricted = rng.random((n, n_sites)) < 0.6
+    unrestricted[leaves] = rng.random((len(leaves), n_sites)) < 0.1
+    bits[unrestricted] = True
+    mask = (bits.astype(np.uint64) << np.arange(S, dtype=np.uint64)[None, None, :]).sum(axis=2).astype(np.uint64)
+    obs = rt.Observations.from_masks(sched, mask)
+    r = mjp.log_likelihood(obs)
+    ll, st = np_oracle.log_likelihood(parent, P, np_oracle.Obs('mask', S, n_sites, mask=mask), pi)
+    assert (r['status'].cpu().numpy() == st).all()
+    np.testing.assert_allclose(r['loglik'].cpu().numpy(), ll, rtol=RTOL)
+    # z-type: emission likelihoods at the leaves and at two internal nodes
+    nodes = np.concatenate([leaves, sched.internal[:2]])
+    lik = rng.random((len(nodes), S, n_sites)) ** 3
+    obs = rt.Observations.from_dense(sched, lik, nodes)
+    r = mjp.log_likelihood(obs)
+    full = np.ones((n, n_sites, S))
+    has = np.zeros(n, dtype=bool)
+    has[nodes] = True
+    full[nodes] = lik.transpose(0, 2, 1)
+    ll, st = np_oracle.log_likelihood(parent, P, np_oracle.Obs('dense', S, n_sites, lik=full, has=has), pi)
+    np.testing.assert_allclose(r['loglik'].cpu().numpy(), ll, rtol=RTOL)
+
+
+@pytest.mark.parametrize('S,n_leaves,n_sites', [(4, 32, 5000), (3, 6, 100)])
+def test_expectations_match_oracle(rt, S, n_leaves, n_sites):
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200 import synth
+    rng = np.random.default_rng(5 + S)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.1, rng)
+    Q = rng.exponential(1.0, size=(S, S))
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    pi = rng.dirichlet(np.ones(S))
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.02)
+    sched = TreeSchedule(parent, length)
+    mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+    obs = rt.Observations.from_leaf_codes(sched, codes, leaves)
+    r = mjp.expected_history_statistics(obs)
+    P = np_oracle.expm_edges(Q, length)
+    o = np_oracle.expected_history_statistics(
+        parent, length, Q, P, np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes), pi)
+    np.testing.assert_allclose(r['loglik'].cpu().numpy(), o['loglik'], rtol=RTOL)
+    np.testing.assert_allclose(r['dwell'].cpu().numpy(), o['dwell'], rtol=RTOL)
+    np.testing.assert_allclose(r['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(r['root_post_sum'].cpu().numpy(), o['root_post'].sum(axis=0), rtol=RTOL)
+    # total expected dwell time = tree length per site
+    np.testing.assert_allclose(float(r['dwell'].sum()), length.sum() * n_sites, rtol=1e-10)
+
+
+def test_support_sets_match_oracle(rt):
+    import torch
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200 import synth
+    rng = np.random.default_rng(77)
+    S, n_sites = 7, 400
+    parent, length, leaves = synth.random_binary_tree(10, 0.3, rng)
+    n = len(parent)
+    Q = np.triu(rng.exponential(1.0, size=(S, S)), 1)
+    Q -= np.diag(Q.sum(axis=1))
+    sched = TreeSchedule(parent, length)
+    mjp = rt.TreeMJP(sched, Q)
+    P = np_oracle.expm_edges(Q, length)
+    bits = rng.random((n, n_sites, S)) < 0.4
+    bits[np.arange(n)[:, None], np.arange(n_sites)[None, :], rng.integers(0, S, size=(n, n_sites))] = True
+    mask = (bits.astype(np.uint64) << np.arange(S, dtype=np.uint64)[None, None, :]).sum(axis=2).astype(np.uint64)
+    ref = np_oracle.support_masks(parent, P, bits)
+    ref_mask = (ref.astype(np.uint64) << np.arange(S, dtype=np.uint64)[None, None, :]).sum(axis=2)
+    dev_mask = torch.from_numpy(mask.view(np.int64).copy()).cuda()
+    mjp.support_sets(dev_mask)
+    got = dev_mask.cpu().numpy().view(np.uint64)
+    assert (got == ref_mask).all()
+
+
+def test_c2_full_size_properties(rt):
+    """Full C2 size: size-independent properties (the oracle is too slow here)."""
+    import torch
+    from raoteh_b200 import synth
+    from raoteh_b200.lowering import TreeSchedule
+    cfg = synth.config_c2(n_sites=1_000_000)
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    mjp = rt.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'])
+    obs = rt.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'])
+    s = torch.zeros(1, dtype=torch.float64, device='cuda')
+    r = mjp.log_likelihood(obs, loglik_sum=s)
+    ll = r['loglik']
+    assert bool((r['status'] == 0).all()) and bool(torch.isfinite(ll).all())
+    np.testing.assert_allclose(float(s[0]), float(ll.sum()), rtol=1e-12)
+    # identical columns give identical log-likelihoods; check against the oracle on a slice
+    sl = slice(123_456, 123_456 + 512)
+    P = np_oracle.expm_edges(cfg['Q'], cfg['length'])
+    ref, _ = np_oracle.log_likelihood(
+        cfg['parent'], P, np_oracle.Obs('codes', 4, 512, leaf_nodes=cfg['leaves'],
+                                         codes=cfg['codes'][:, sl]), cfg['pi'])
+    np.testing.assert_allclose(ll[sl].cpu().numpy(), ref, rtol=RTOL)
+    # expectations: total expected dwell = tree length * sites; transitions >= 0
+    e = mjp.expected_history_statistics(obs)
+    np.testing.assert_allclose(float(e['dwell'].sum()), cfg['length'].sum() * 1_000_000, rtol=1e-10)
+    np.testing.assert_allclose(float(e['root_post_sum'].sum()), 1_000_000, rtol=1e-12)
+    assert bool((e['trans'] >= 0).all())
