@@ -1,7 +1,293 @@
-// K5 for large state spaces -- placeholder until the DMMA downward kernel lands.
+// K4/K5 for large state spaces (9 <= S <= 64): downward pass, posterior node
+// marginals and per-edge sufficient statistics on the FP64 tensor pipe.
+//
+// Replaces, batched over sites, pyfelscore.mc0_esd_get_node_to_distn
+// (raoteh/sampler/_mc0_dense.py:381, spec :400-489), mc0_esd_get_joint_endpoint_distn
+// (_mcy_dense.py:205, spec _mc0_dense.py:217-270) and the `joint_prob/cond_prob`
+// accumulation of _mjp_dense.get_expected_history_statistics (:502-510,521-533).
+//
+// Edge-major, level-synchronous: grid = (site chunks) x (edges of the level).
+// A CTA stages P_b once and streams 128-site tiles; per tile three DMMA
+// contractions
+//     m   = P_b   L_b      (states x sites)      normalisers per parent state
+//     D_b = L_b o (P_b^T G),  G = D_a / m        child marginal
+//     W_b += G L_b^T       (states x states, K = sites)
+// run back to back; W_b (= sum_sites J_b / P_b) stays in registers for the whole
+// chunk and is flushed with one masked atomicAdd per entry.  The joint J_b is
+// never materialised (7.6 MB per site at S = 61).
 #include "rt_common.cuh"
-int rt_posterior_dmma_dispatch(int, int, int64_t, int64_t, const int32_t*, const int32_t*, int,
-                               const double*, const double*, const void*, const double*,
-                               const int8_t*, double*, double*, double*, cudaStream_t) {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kNT = 2;
+constexpr int kWarpSites = 8 * kNT;               // 16
+constexpr int kTileSites = kWarps * kWarpSites;   // 128
+constexpr int kLd = kWarpSites + 4;               // 20
+constexpr int kTilesPerCta = 8;                   // 1024 sites per CTA
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+root_distn_generic_kernel(int S, int64_t n_sites, int64_t stride,
+                          const double* __restrict__ root_distn,
+                          const double* __restrict__ partials, const int8_t* __restrict__ status,
+                          double* __restrict__ node_distn, double* __restrict__ root_post_sum) {
+  extern __shared__ double rsum[];   // [S]
+  for (int s = threadIdx.x; s < S; s += blockDim.x) rsum[s] = 0.0;
+  __syncthreads();
+  for (int64_t site = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; site < n_sites;
+       site += (int64_t)gridDim.x * blockDim.x) {
+    const bool ok = status[site] == RT_SITE_OK;
+    double tot = 0.0;
+    for (int s = 0; s < S; ++s)
+      tot += partials[(int64_t)s * stride + site] * (root_distn ? root_distn[s] : 1.0);
+    const double inv = (ok && tot > 0.0) ? 1.0 / tot : 0.0;
+    for (int s = 0; s < S; ++s) {
+      const double d = partials[(int64_t)s * stride + site] * (root_distn ? root_distn[s] : 1.0) * inv;
+      node_distn[(int64_t)s * stride + site] = d;
+      if (root_post_sum && d != 0.0) atomicAdd(&rsum[s], d);
+    }
+  }
+  __syncthreads();
+  if (root_post_sum)
+    for (int s = threadIdx.x; s < S; s += blockDim.x)
+      if (rsum[s] != 0.0) atomicAdd(&root_post_sum[s], rsum[s]);
+}
+
+template <int MT, int OBS>
+__global__ void __launch_bounds__(kThreads, 1)
+down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict__ edges,
+                 const double* __restrict__ P, const void* __restrict__ obs,
+                 const double* __restrict__ partials, const int8_t* __restrict__ status,
+                 double* __restrict__ node_distn, double* __restrict__ W) {
+  constexpr int SP = 8 * MT;
+  constexpr int LDP = SP + 4;
+  constexpr int KS = SP / 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Ps = reinterpret_cast<double*>(smem_raw);          // [SP][LDP]
+  double* Lall = Ps + SP * LDP;                              // [kWarps][SP][kLd]
+  double* Gall = Lall + (size_t)kWarps * SP * kLd;           // [kWarps][SP][kLd]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int4 e = edges[blockIdx.y];    // (child node, parent store, child store, child obs slot)
+  const int b = e.x;
+  for (int idx = tid; idx < SP * LDP; idx += kThreads) {
+    const int r = idx / LDP, c = idx % LDP;
+    Ps[idx] = (r < S && c < S) ? P[(size_t)b * S * S + r * S + c] : 0.0;
+  }
+  double* Lw = Lall + (size_t)warp * SP * kLd;
+  double* Gw = Gall + (size_t)warp * SP * kLd;
+  const double* Dp = node_distn + (int64_t)e.y * S * stride;
+  const double* Lc = e.z >= 0 ? partials + (int64_t)e.z * S * stride : nullptr;
+  double* Dc = e.z >= 0 ? node_distn + (int64_t)e.z * S * stride : nullptr;
+
+  // W rows [8*warp, 8*warp+8) x all columns, accumulated over the whole chunk
+  double Wacc[MT][2];
+#pragma unroll
+  for (int j = 0; j < MT; ++j) Wacc[j][0] = Wacc[j][1] = 0.0;
+  __syncthreads();
+
+  for (int tile = 0; tile < kTilesPerCta; ++tile) {
+    const int64_t tile0 = ((int64_t)blockIdx.x * kTilesPerCta + tile) * kTileSites;
+    if (tile0 >= n_sites) break;
+    const int64_t site0 = tile0 + warp * kWarpSites;
+
+    // ---- L_b^T tile of this warp: [SP][16 sites] --------------------------------
+    {
+      const int c = lane & 15;
+      const int64_t sg = site0 + c;
+      const bool live = sg < n_sites && status[sg] == RT_SITE_OK;
+      if (Lc) {
+        for (int r0 = 0; r0 < SP; r0 += 2) {
+          const int r = r0 + (lane >> 4);
+          Lw[r * kLd + c] = (r < S && live) ? Lc[(int64_t)r * stride + sg] : 0.0;
+        }
+      } else if (e.w < 0) {
+        for (int r0 = 0; r0 < SP; r0 += 2) {
+          const int r = r0 + (lane >> 4);
+          Lw[r * kLd + c] = (r < S && live) ? 1.0 : 0.0;
+        }
+      } else if (OBS == OBS_CODES) {
+        const int k = live ? reinterpret_cast<const uint8_t*>(obs)[(int64_t)e.w * stride + sg] : -1;
+        for (int r0 = 0; r0 < SP; r0 += 2) {
+          const int r = r0 + (lane >> 4);
+          Lw[r * kLd + c] = (r < S && live && (k == RT_MISSING || k == r)) ? 1.0 : 0.0;
+        }
+      } else if (OBS == OBS_MASK) {
+        const unsigned long long mk =
+            live ? reinterpret_cast<const unsigned long long*>(obs)[(int64_t)e.w * stride + sg] : 0ull;
+        for (int r0 = 0; r0 < SP; r0 += 2) {
+          const int r = r0 + (lane >> 4);
+          Lw[r * kLd + c] = (r < S && ((mk >> r) & 1ull)) ? 1.0 : 0.0;
+        }
+      } else {
+        const double* d = reinterpret_cast<const double*>(obs) + (int64_t)e.w * S * stride;
+        for (int r0 = 0; r0 < SP; r0 += 2) {
+          const int r = r0 + (lane >> 4);
+          Lw[r * kLd + c] = (r < S && live) ? d[(int64_t)r * stride + sg] : 0.0;
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- m = P L  (rows = parent states, cols = sites) -----------------------------
+    double m[MT][kNT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < kNT; ++j) m[i][j][0] = m[i][j][1] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      double bf[kNT];
+#pragma unroll
+      for (int j = 0; j < kNT; ++j) bf[j] = Lw[(4 * kk + t) * kLd + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const double a = Ps[(8 * i + g) * LDP + 4 * kk + t];
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) dmma884(m[i][j][0], m[i][j][1], a, bf[j]);
+      }
+    }
+    // ---- G = D_a / m (0 where D_a == 0), written to the warp's G tile ---------------
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < kNT; ++j) {
+        double gv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int s = 8 * i + g;
+          const int64_t sg = site0 + 8 * j + 2 * t + h;
+          double d = 0.0;
+          if (s < S && sg < n_sites) d = Dp[(int64_t)s * stride + sg];
+          gv[h] = (d > 0.0 && m[i][j][h] > 0.0) ? d / m[i][j][h] : 0.0;
+        }
+        *reinterpret_cast<double2*>(&Gw[(8 * i + g) * kLd + 8 * j + 2 * t]) = make_double2(gv[0], gv[1]);
+      }
+    __syncwarp();
+
+    // ---- D_b = L o (P^T G)  (rows = child states) ------------------------------------
+    if (Dc) {
+      double d2[MT][kNT][2];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) d2[i][j][0] = d2[i][j][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        double bf[kNT];
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) bf[j] = Gw[(4 * kk + t) * kLd + 8 * j + g];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const double a = Ps[(4 * kk + t) * LDP + 8 * i + g];   // P^T[8i+g][4kk+t]
+#pragma unroll
+          for (int j = 0; j < kNT; ++j) dmma884(d2[i][j][0], d2[i][j][1], a, bf[j]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < kNT; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int s = 8 * i + g;
+            const int64_t sg = site0 + 8 * j + 2 * t + h;
+            if (s < S && sg < n_sites)
+              Dc[(int64_t)s * stride + sg] = d2[i][j][h] * Lw[s * kLd + 8 * j + 2 * t + h];
+          }
+    }
+    __syncthreads();   // every warp's L and G tiles are complete
+
+    // ---- W[8*warp.., :] += G L^T over the 128 sites of the tile ------------------------
+    if (warp < MT) {
+#pragma unroll 4
+      for (int ks = 0; ks < kTileSites / 4; ++ks) {
+        const int wt = ks >> 2;            // warp tile owning these 4 sites
+        const int col = 4 * (ks & 3) + t;  // site column inside that tile
+        const double a = Gall[(size_t)wt * SP * kLd + (8 * warp + g) * kLd + col];
+        const double* Lt = Lall + (size_t)wt * SP * kLd;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const double bb = Lt[(8 * j + g) * kLd + col];
+          dmma884(Wacc[j][0], Wacc[j][1], a, bb);
+        }
+      }
+    }
+    __syncthreads();   // tiles may be overwritten
+  }
+
+  if (warp < MT) {
+#pragma unroll
+    for (int j = 0; j < MT; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = 8 * warp + g, c = 8 * j + 2 * t + h;
+        const double v = Wacc[j][h];
+        if (r < S && c < S && v != 0.0 && Ps[r * LDP + c] > 0.0)
+          atomicAdd(&W[(size_t)b * S * S + r * S + c], v);
+      }
+  }
+}
+
+template <int MT>
+int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edges_dev,
+        const int32_t* level_ptr_h, int n_levels, const double* P, const double* root_distn,
+        const void* obs, const double* partials, const int8_t* status, double* node_distn,
+        double* W, double* root_post_sum, cudaStream_t stream) {
+  constexpr int SP = 8 * MT;
+  constexpr int LDP = SP + 4;
+  int64_t gr = (n_sites + 255) / 256;
+  root_distn_generic_kernel<<<(int)(gr < 1184 ? gr : 1184), 256, sizeof(double) * S, stream>>>(
+      S, n_sites, stride, root_distn, partials, status, node_distn, root_post_sum);
+  const size_t smem = sizeof(double) * ((size_t)SP * LDP + 2 * (size_t)kWarps * SP * kLd);
+  const int4* edges = reinterpret_cast<const int4*>(edges_dev);
+  const unsigned gx = (unsigned)((n_sites + kTilesPerCta * kTileSites - 1) / (kTilesPerCta * kTileSites));
+#define RT_LAUNCH(OBSK)                                                                           \
+  {                                                                                               \
+    auto kern = down_dmma_kernel<MT, OBSK>;                                                       \
+    RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kThreads, smem, stream>>>(S, n_sites, stride, edges + e0, P, obs, partials,     \
+                                           status, node_distn, W);                                \
+  }
+  for (int l = 0; l < n_levels; ++l) {
+    const int e0 = level_ptr_h[l], e1 = level_ptr_h[l + 1];
+    if (e1 <= e0) continue;
+    dim3 grid(gx, (unsigned)(e1 - e0));
+    switch (obs_kind) {
+      case OBS_CODES: RT_LAUNCH(OBS_CODES) break;
+      case OBS_MASK: RT_LAUNCH(OBS_MASK) break;
+      case OBS_DENSE: RT_LAUNCH(OBS_DENSE) break;
+      default: return RT_ERR_ARG;
+    }
+  }
+#undef RT_LAUNCH
+  RT_CUDA_CHECK(cudaGetLastError());
+  return RT_OK;
+}
+
+}  // namespace
+
+int rt_posterior_dmma_dispatch(int S, int obs_kind, int64_t n_sites, int64_t stride,
+                               const int32_t* edges_dev, const int32_t* level_ptr_h, int n_levels,
+                               const double* P, const double* root_distn, const void* obs,
+                               const double* partials, const int8_t* status, double* node_distn,
+                               double* W, double* root_post_sum, cudaStream_t stream) {
+  const int MT = (S + 15) / 16 * 2;
+#define RT_ARGS S, obs_kind, n_sites, stride, edges_dev, level_ptr_h, n_levels, P, root_distn, obs, \
+                partials, status, node_distn, W, root_post_sum, stream
+  switch (MT) {
+    case 2: return run<2>(RT_ARGS);
+    case 4: return run<4>(RT_ARGS);
+    case 6: return run<6>(RT_ARGS);
+    case 8: return run<8>(RT_ARGS);
+  }
+#undef RT_ARGS
   return RT_ERR_UNSUPPORTED;
 }

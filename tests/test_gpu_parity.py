@@ -46,10 +46,10 @@ def test_expm_matches_scipy(rt, S):
     dev = torch.device('cuda')
     P = torch.empty((24, S, S), dtype=torch.float64, device=dev)
     from raoteh_b200 import _native
-    rc = _native.lib().rt_expm_batched(
-        torch.from_numpy(Q).to(dev).data_ptr(), torch.from_numpy(q_index).to(dev).data_ptr(),
-        torch.from_numpy(t).to(dev).data_ptr(), 24, S, P.data_ptr(),
-        torch.cuda.current_stream().cuda_stream)
+    Qd, qd, td = (torch.from_numpy(Q).to(dev), torch.from_numpy(q_index).to(dev),
+                  torch.from_numpy(t).to(dev))   # keep the device tensors alive
+    rc = _native.lib().rt_expm_batched(Qd.data_ptr(), qd.data_ptr(), td.data_ptr(), 24, S,
+                                       P.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _native.check(rc, 'rt_expm_batched')
     P = P.cpu().numpy()
     for m in range(24):
@@ -73,10 +73,10 @@ def test_frechet_contract_matches_scipy(rt, S):
     W[3] = 0.0
     dev = torch.device('cuda')
     M = torch.empty((n, S, S), dtype=torch.float64, device=dev)
-    rc = _native.lib().rt_frechet_contract(
-        torch.from_numpy(Q).to(dev).data_ptr(), None, torch.from_numpy(t).to(dev).data_ptr(),
-        torch.from_numpy(W).to(dev).data_ptr(), n, S, M.data_ptr(),
-        torch.cuda.current_stream().cuda_stream)
+    Qd, td, Wd = (torch.from_numpy(Q).to(dev), torch.from_numpy(t).to(dev),
+                  torch.from_numpy(W).to(dev))   # keep the device tensors alive
+    rc = _native.lib().rt_frechet_contract(Qd.data_ptr(), None, td.data_ptr(), Wd.data_ptr(), n, S,
+                                           M.data_ptr(), torch.cuda.current_stream().cuda_stream)
     _native.check(rc, 'rt_frechet_contract')
     M = M.cpu().numpy()
     for m in range(n):
