@@ -1,0 +1,489 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the raoteh_b200 hot path.
+
+Workload (BASELINE.json configs[1], "C2"): 4-state HKY MJP on a 32-leaf random
+binary tree, 1M synthetic sites per GPU: per-site log-likelihood + site-summed
+expected dwell times / transition counts.  One step = one full evaluation for
+one batch of sites: per-edge expm, upward pass (partials stored), downward
+pass + per-edge weights, Frechet contraction, (N > 1) one NCCL allreduce of
+[1 + S + S*S] doubles.  Metric: site.edge messages / s = n_sites * n_edges / t.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`value`   : inputs resident in HBM, CUDA-event time, max over ranks.
+`e2e`     : same step through the public API with HOST buffers: H2D of the leaf
+            codes from pinned memory and D2H of log-likelihoods, status and the
+            statistics inside the timed region.
+`roofline`: dominant kernel of the step (downward pass), algorithmic bytes /
+            CUDA-event duration against MEASURED_PEAKS.json hbm_gbs.
+`extra`   : C3 (61-state DMMA pruning) and C4 (Rao-Teh sweeps) figures.
+`--impl reference`: the oracle port of the reference's CPU path (numpy/scipy,
+            one process per host core) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+C2_SITES = 1_000_000
+C2_LEAVES = 32
+
+
+# ----------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), 'measured'
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), 'fallback'
+
+
+def fp64_peak():
+    """FP64 tensor (DMMA) peak measured on this pool's B200 with tools/fp64_peak.cu
+    (profiles/r1_fp64_peak.jsonl): 37.0 TFLOP/s; DFMA 33.5 TFLOP/s."""
+    path = os.path.join(ROOT, 'profiles', 'r1_fp64_peak.jsonl')
+    best = 37.0
+    if os.path.exists(path):
+        vals = []
+        for line in open(path):
+            try:
+                d = json.loads(line)
+            except ValueError:
+                continue
+            if d.get('probe') == 'dmma_m8n8k4':
+                vals.append(d['tflops'])
+        if vals:
+            best = max(vals)
+    return best
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=float(max(mx)) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def c2_workload(rank, n_sites=C2_SITES):
+    from raoteh_b200 import synth
+    return synth.config_c2(n_sites=n_sites, seed=20260201 + 1000 * rank, n_leaves=C2_LEAVES) \
+        if rank else synth.config_c2(n_sites=n_sites, n_leaves=C2_LEAVES)
+
+
+def c2_bytes_per_site(sched, S):
+    """Algorithmic HBM bytes per site."""
+    n_int = sched.n_store
+    n_leaf = len(sched.leaves)
+    up = n_leaf * 1 + n_int * S * 8 + 8 + 1
+    # down: every stored partial read once, every marginal written once and read once,
+    # leaf codes and status read once
+    down = n_int * S * 8 + 2 * n_int * S * 8 + n_leaf * 1 + 1
+    return up, down
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle port on host cores
+# ----------------------------------------------------------------------------
+def _cpu_chunk(args):
+    from oracle import np_oracle
+    cfg, lo, hi = args
+    S = cfg['S']
+    P = np_oracle.expm_edges(cfg['Q'], cfg['length'])
+    obs = np_oracle.Obs('codes', S, hi - lo, leaf_nodes=cfg['leaves'], codes=cfg['codes'][:, lo:hi])
+    r = np_oracle.expected_history_statistics(cfg['parent'], cfg['length'], cfg['Q'], P, obs, cfg['pi'])
+    return float(r['loglik'].sum()), r['dwell'], r['trans']
+
+
+def cpu_reference_step(cfg, n_sample, pool, cores):
+    """One step of the oracle port (log-lik + expectations) on n_sample sites."""
+    per = (n_sample + cores - 1) // cores
+    jobs = [(cfg, lo, min(n_sample, lo + per)) for lo in range(0, n_sample, per)]
+    t0 = time.perf_counter()
+    out = pool.map(_cpu_chunk, jobs)
+    dt = time.perf_counter() - t0
+    return dt, sum(o[0] for o in out)
+
+
+def cpu_per_site_reference_style(cfg, n_sites=3):
+    """The reference's own structure: expm of every edge redone for every site
+    (raoteh/sampler/_mjp_dense.py:352-358), one site per call."""
+    from oracle import np_oracle
+    S = cfg['S']
+    t0 = time.perf_counter()
+    for i in range(n_sites):
+        P = np_oracle.expm_edges(cfg['Q'], cfg['length'])
+        obs = np_oracle.Obs('codes', S, 1, leaf_nodes=cfg['leaves'], codes=cfg['codes'][:, i:i + 1])
+        np_oracle.log_likelihood(cfg['parent'], P, obs, cfg['pi'])
+    return (time.perf_counter() - t0) / n_sites
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_sample = 200_000
+    cfg = c2_workload(0, n_sample)
+    n_edges = len(cfg['parent']) - 1
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_reference_step(cfg, n_sample, pool, cores)
+        times = [cpu_reference_step(cfg, n_sample, pool, cores)[0] for _ in range(args.steps)]
+    dt = float(np.mean(times))
+    value = n_sample * n_edges / dt
+    line = dict(
+        impl='reference', metric='site_edge_messages_per_sec', value=value, unit='messages/s',
+        n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt * 1e3,
+        higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+        config=dict(workload='C2: 4-state HKY, 32-leaf tree, log-lik + expected dwell/transition '
+                             'counts; CPU arm on a %d-site sample per step' % n_sample,
+                    sites_per_step=n_sample, n_edges=n_edges),
+        cpu_baseline=dict(value=value, unit='messages/s', cores=cores, kind='port',
+                          sample='%d of 1e6 C2 sites per step, oracle/np_oracle.py (numpy/scipy '
+                                 'restatement, expm hoisted out of the site loop), one process '
+                                 'per core' % n_sample),
+        e2e=dict(value=value, unit='messages/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    cfg = c2_workload(rank)
+    S = cfg['S']
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    n_edges = sched.n_edges
+    N = cfg['codes'].shape[1]
+    codes_pinned = torch.from_numpy(cfg['codes']).pin_memory()
+    codes_dev = codes_pinned.to(dev)
+    obs_slot = np.full(sched.n, -1, dtype=np.int32)
+    obs_slot[cfg['leaves']] = np.arange(len(cfg['leaves']), dtype=np.int32)
+    obs = engine.Observations(engine.OBS_CODES, codes_dev, obs_slot, N)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out_ll = torch.empty(N, dtype=torch.float64).pin_memory()
+    out_st = torch.empty(N, dtype=torch.int8).pin_memory()
+    out_stats = torch.empty(1 + S + S * S + S, dtype=torch.float64).pin_memory()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    mjp = engine.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'], device=dev)
+    state = {}
+
+    def step(record=False):
+        """New rate matrix -> expm + up + down + Frechet contraction (+ allreduce);
+        observations resident in HBM."""
+        mjp.events = sub if record else None
+        mjp.set_rate_matrix(cfg['Q'])
+        r = mjp.expected_history_statistics(obs)
+        stats = torch.cat([r['loglik'].sum().reshape(1), r['dwell'], r['trans'].reshape(-1),
+                           r['root_post_sum']])
+        if world > 1:
+            dist.all_reduce(stats)
+        state['n_levels'] = r['n_levels']
+        return r, stats
+    sub = {}
+
+    def step_e2e():
+        """Same step from HOST buffers: H2D codes, D2H log-lik, status, statistics."""
+        codes_dev.copy_(codes_pinned, non_blocking=True)
+        up, stats = step()
+        out_ll.copy_(up['loglik'], non_blocking=True)
+        out_st.copy_(up['status'], non_blocking=True)
+        out_stats.copy_(stats, non_blocking=True)
+
+    def timed(fn, steps, warmup, record=False):
+        for _ in range(warmup):
+            flush.fill_(1)
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = 0.0
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)            # evict L2 between timed iterations
+            a, b = ev(), ev()
+            a.record()
+            fn(record) if record else fn()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]) / steps
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step, args.steps, args.warmup, record=True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+    total_sites = N * world
+    value = total_sites * n_edges / (ms * 1e-3)
+    e2e_value = total_sites * n_edges / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel (down pass: root + one launch per level)
+    peaks, peak_kind = measured_peaks()
+    torch.cuda.synchronize()
+    pair = lambda L: [(L[i], L[i + 1]) for i in range(0, len(L) - 1, 2)]
+    up_ms = float(np.mean([a.elapsed_time(b) for a, b in pair(sub['up'])]))
+    down_ms = float(np.mean([a.elapsed_time(b) for a, b in pair(sub['down'])]))
+    up_b, down_b = c2_bytes_per_site(sched, S)
+    down_gbs = N * down_b / (down_ms * 1e-3) / 1e9
+    up_gbs = N * up_b / (up_ms * 1e-3) / 1e9
+    roofline = dict(bound='hbm', kernel='down_level_kernel<4,codes> (%d launches/step) + root_distn_kernel'
+                    % state['n_levels'], achieved=down_gbs, peak=peaks['hbm_gbs'], unit='GB/s',
+                    frac=down_gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
+                    traffic=None, algorithmic_bytes_per_launch_set=N * down_b, ms=down_ms,
+                    also=dict(kernel='prune_small_kernel<4,codes,store>', achieved=up_gbs,
+                              frac=up_gbs / peaks['hbm_gbs'], ms=up_ms,
+                              algorithmic_bytes_per_launch=N * up_b))
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        try:
+            extra['c3_61state_pruning'] = bench_c3(dev, args)
+        except Exception as e:   # keep the headline line even if an extra fails
+            extra['c3_61state_pruning'] = dict(error=repr(e))
+        try:
+            extra['c2_loglik_only'] = bench_c2_loglik(dev, cfg, sched, obs, args, peaks)
+        except Exception as e:
+            extra['c2_loglik_only'] = dict(error=repr(e))
+        try:
+            from raoteh_b200 import raoteh_bench
+            extra['c4_raoteh_sweeps'] = raoteh_bench.bench_c4(dev, args)
+        except Exception as e:
+            extra['c4_raoteh_sweeps'] = dict(error=repr(e))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        n_sample = 200_000
+        small = c2_workload(0, n_sample)
+        with mp.get_context('fork').Pool(cores) as pool:
+            cpu_reference_step(small, n_sample, pool, cores)
+            dt, _ = cpu_reference_step(small, n_sample, pool, cores)
+        per_site = cpu_per_site_reference_style(small, 3)
+        cpu_baseline = dict(value=n_sample * n_edges / dt, unit='messages/s', cores=cores, kind='port',
+                            sample='%d of 1e6 C2 sites, oracle/np_oracle.py (numpy/scipy), one '
+                                   'process per core; reference-style per-site loop with expm per '
+                                   'edge per site: %.4f s/site = %.0f messages/s on 1 core'
+                                   % (n_sample, per_site, n_edges / per_site))
+
+    if rank == 0:
+        launches_per_step = 2 + 1 + 1 + state['n_levels'] + 3
+        line = dict(
+            metric='site_edge_messages_per_sec', value=value, unit='messages/s', n_gpus=world,
+            steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+            scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+            config=dict(workload='C2: 4-state HKY MJP, 32-leaf random binary tree, 1e6 synthetic '
+                                 'sites per GPU (uint8 leaf codes, 1% missing): per-site log-lik + '
+                                 'site-summed expected dwell/transition counts',
+                        sites_per_gpu=N, n_edges=n_edges, n_states=S,
+                        parallelism='site-sharded x%d, one allreduce of %d doubles' % (world, 1 + 2 * S + S * S),
+                        l2='256 MiB flush buffer written between timed iterations'),
+            e2e=dict(value=e2e_value, unit='messages/s', ms_per_step=ms_e2e,
+                     h2d_bytes_per_step=int(codes_pinned.numel()),
+                     d2h_bytes_per_step=int(out_ll.numel() * 8 + out_st.numel() + out_stats.numel() * 8)),
+            gpu_launches=launches_per_step * args.steps,
+            roofline=roofline, cpu_baseline=cpu_baseline, clocks=clocks, extra=extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_c2_loglik(dev, cfg, sched, obs, args, peaks):
+    """K2 alone: log-likelihood only (no stored partials), codes and dense-emission input."""
+    import torch
+    from raoteh_b200 import engine
+    S = cfg['S']
+    N = obs.n_sites
+    mjp = engine.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'], device=dev)
+    mjp.transition_matrices()
+    res = {}
+    ll = torch.empty(N, dtype=torch.float64, device=dev)
+    st = torch.empty(N, dtype=torch.int8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def time_it(o):
+        for _ in range(3):
+            mjp.log_likelihood(o, out=(ll, st))
+        ts = []
+        for _ in range(max(5, args.steps)):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            mjp.log_likelihood(o, out=(ll, st))
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+    ms = time_it(obs)
+    b_site = len(sched.leaves) + 9
+    res['codes'] = dict(ms=ms, messages_per_sec=N * sched.n_edges / (ms * 1e-3), bytes_per_site=b_site,
+                        hbm_gbs=N * b_site / (ms * 1e-3) / 1e9, hbm_frac=N * b_site / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'])
+    # dense emission likelihoods (obs type z): [n_leaves, S, N] fp64 = 1 KiB / site
+    codes = obs.data.long()
+    lik = torch.zeros((len(sched.leaves), S, N), dtype=torch.float64, device=dev)
+    miss = codes == 255
+    lik.scatter_(1, codes.clamp(max=S - 1).unsqueeze(1), 1.0)
+    lik[miss.unsqueeze(1).expand(-1, S, -1)] = 1.0
+    dobs = engine.Observations(engine.OBS_DENSE, lik, obs.obs_slot, N)
+    ms = time_it(dobs)
+    b_site = len(sched.leaves) * S * 8 + 9
+    res['dense_emissions'] = dict(ms=ms, messages_per_sec=N * sched.n_edges / (ms * 1e-3), bytes_per_site=b_site,
+                                  hbm_gbs=N * b_site / (ms * 1e-3) / 1e9,
+                                  hbm_frac=N * b_site / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'])
+    return res
+
+
+def bench_c3(dev, args):
+    """C3: 61-state codon model, 128-leaf tree, 1e5 sites, log-likelihood (DMMA)."""
+    import torch
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    cfg = synth.config_c3(n_sites=100_000)
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    mjp = engine.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'], device=dev)
+    obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'], device=dev)
+    N = obs.n_sites
+    ll = torch.empty(N, dtype=torch.float64, device=dev)
+    st = torch.empty(N, dtype=torch.int8, device=dev)
+    mjp.transition_matrices()
+    for _ in range(3):
+        mjp.log_likelihood(obs, out=(ll, st))
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(max(5, args.steps)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        mjp.log_likelihood(obs, out=(ll, st))
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    E = sched.n_edges
+    n_int_edges = int((~sched.is_leaf[1:]).sum())
+    flops_nominal = N * E * 7503.0
+    flops_dmma = N * n_int_edges * 2.0 * 64 * 64
+    peak = fp64_peak()
+    # expm alone
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mjp._P = None
+    a.record()
+    mjp.transition_matrices()
+    b.record()
+    torch.cuda.synchronize()
+    return dict(workload='C3: 61-state MG94 codon MJP, 128-leaf tree, 1e5 sites, log-lik',
+                ms=ms, messages_per_sec=N * E / (ms * 1e-3),
+                tflops_nominal=flops_nominal / (ms * 1e-3) / 1e12,
+                tflops_executed_on_tensor_pipe=flops_dmma / (ms * 1e-3) / 1e12,
+                fp64_tensor_peak_tflops=peak,
+                frac_nominal=flops_nominal / (ms * 1e-3) / 1e12 / peak,
+                frac_executed=flops_dmma / (ms * 1e-3) / 1e12 / peak,
+                expm_ms=a.elapsed_time(b), finite=bool(torch.isfinite(ll).all()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-extra', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

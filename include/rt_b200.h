@@ -128,6 +128,43 @@ int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
                        const double* partials, const int8_t* status,
                        double* node_distn, double* W, double* root_post_sum, void* stream);
 
+/*
+ * Rao-Teh uniformization sweeps for n_traj independent trajectories
+ * (trajectory t = chain * n_sites + site; observations are per site:
+ * site = (traj0 + t) % n_sites), n_sweeps sweeps per call, Philox4x32-10
+ * keyed by (seed; traj0 + t, sweep0 + i) so results do not depend on how
+ * trajectories are split over launches or GPUs.  S in {2,3,4,5,6,8}.
+ *
+ * Trajectory state (caller-owned device arrays, trajectory-minor):
+ *   node_state uint8 [n_nodes][traj_stride]  state at every tree node
+ *   ev_count   uint8 [n_nodes][traj_stride]  real jumps on the edge above node b
+ *   ev_total   int32 [traj_stride]           total real jumps
+ *   ev_time    float [cap][traj_stride]      jump times from the PARENT end of the
+ *   ev_sb      uint8 [cap][traj_stride]      edge / state on the parent side; the
+ *              jumps occupy rows [cap - ev_total, cap) in upward-program order
+ *              (edges in program order, child end first).
+ * B = I + Q/omega, rate[s] = omega - q_s (raoteh/sampler/_sampler.py:346-355).
+ * init_k >= 0: build an initial history with init_k equally spaced events on
+ * every edge (one round of _sampler.get_restricted_feasible_history,
+ * raoteh/sampler/_sampler.py:612-643); status 1 where infeasible.
+ * init_k < 0: n_sweeps Rao-Teh sweeps (raoteh/sampler/_sampler.py:366-390 =
+ * _sample_mjp.resample_poisson :19 + _sample_mcy.resample_edge_states :86 +
+ * _graph_transform.remove_redundant_nodes :144); dwell_sum[S] / trans_sum[S*S]
+ * (nullable) += the sufficient statistics of every sampled history
+ * (_mjp.get_history_statistics, raoteh/sampler/_mjp.py:150).
+ * Trajectories whose status != 0 are skipped; status 3 = more than `cap`
+ * candidate events in one sweep (trajectory left at its last completed sweep).
+ */
+int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, int64_t n_sites,
+                     int64_t traj0, const int32_t* program, int n_ops, int n_slots,
+                     const int32_t* parent, const double* length, const double* B,
+                     const double* rate, const double* root_distn,
+                     int obs_kind, const void* obs, int64_t obs_stride,
+                     uint8_t* node_state, float* ev_time, uint8_t* ev_sb, uint8_t* ev_count,
+                     int32_t* ev_total, int cap, uint64_t seed, int64_t sweep0, int n_sweeps,
+                     int init_k, double* dwell_sum, double* trans_sum, int8_t* status,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,8 +30,10 @@ EXPORTS = {
     'rt_posterior_stats': ([c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p,
                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p], c_int),
-    'rt_raoteh_init': None,      # filled in below when present
-    'rt_raoteh_sweeps': None,
+    'rt_raoteh_sweeps': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_uint64,
+                          c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
 }
 
 

@@ -8,6 +8,21 @@ static thread_local char g_err[512] = "";
 void rt_set_last_error(cudaError_t e, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
 }
+// Workspaces come from the device's default stream-ordered pool (cudaMallocAsync).
+// Keep freed blocks cached in the pool instead of returning them to the OS at
+// every synchronisation (default threshold 0), once per device.
+static void ensure_pool_cached() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_for = dev;
+}
+
 static int arg_error(const char* msg) {
   snprintf(g_err, sizeof(g_err), "argument error: %s", msg);
   return RT_ERR_ARG;
@@ -35,6 +50,11 @@ int rt_posterior_dmma_dispatch(int, int, int64_t, int64_t, const int32_t*, const
                                const double*, const double*, const void*, const double*,
                                const int8_t*, double*, double*, double*, cudaStream_t);
 
+int rt_raoteh_dispatch(int, int, int, int64_t, int64_t, int64_t, int64_t, const int32_t*, int, int,
+                       const int32_t*, const double*, const double*, const double*, const double*,
+                       const void*, int64_t, uint8_t*, float*, uint8_t*, uint8_t*, int32_t*, int,
+                       uint64_t, int64_t, int, int, double*, double*, int8_t*, cudaStream_t);
+
 extern "C" {
 
 int rt_version(void) { return 100; }
@@ -44,6 +64,7 @@ int rt_expm_batched(const double* Q, const int32_t* q_index, const double* t, in
                     double* P, void* stream) {
   if (!Q || !t || !P) return arg_error("null pointer");
   if (S < 1 || S > 128) return unsupported("rt_expm_batched needs 1 <= S <= 128");
+  ensure_pool_cached();
   return rt_expm_batched_impl(Q, q_index, t, n_mat, S, P, (cudaStream_t)stream);
 }
 
@@ -51,6 +72,7 @@ int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t
                         int n_mat, int S, double* M, void* stream) {
   if (!Q || !t || !W || !M) return arg_error("null pointer");
   if (S < 1 || S > 64) return unsupported("rt_frechet_contract needs 1 <= S <= 64");
+  ensure_pool_cached();
   return rt_frechet_contract_impl(Q, q_index, t, W, n_mat, S, M, (cudaStream_t)stream);
 }
 
@@ -58,6 +80,7 @@ int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride, co
                     const double* P, uint64_t* mask, void* stream) {
   if (!parent || !P || !mask) return arg_error("null pointer");
   if (site_stride < n_sites) return arg_error("site_stride < n_sites");
+  ensure_pool_cached();
   return rt_support_sets_impl(S, n_nodes, n_sites, site_stride, parent, P, mask, (cudaStream_t)stream);
 }
 
@@ -72,6 +95,7 @@ int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
   if (n_sites <= 0) return RT_OK;
   if (n_ops <= 0 || n_slots <= 0 || n_nodes <= 1) return arg_error("empty program");
   const bool store = partials != nullptr;
+  ensure_pool_cached();
   int rc;
   if (S >= 2 && S <= 8)
     rc = rt_prune_small_dispatch(S, obs_kind, store, n_sites, site_stride, program, n_ops, n_slots,
@@ -107,6 +131,29 @@ int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
                                       n_levels, P, root_distn, obs, partials, status, node_distn, W,
                                       root_post_sum, (cudaStream_t)stream);
   return unsupported("rt_posterior_stats needs 1 <= S <= 64");
+}
+
+int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, int64_t n_sites,
+                     int64_t traj0, const int32_t* program, int n_ops, int n_slots,
+                     const int32_t* parent, const double* length, const double* B,
+                     const double* rate, const double* root_distn, int obs_kind, const void* obs,
+                     int64_t obs_stride, uint8_t* node_state, float* ev_time, uint8_t* ev_sb,
+                     uint8_t* ev_count, int32_t* ev_total, int cap, uint64_t seed, int64_t sweep0,
+                     int n_sweeps, int init_k, double* dwell_sum, double* trans_sum, int8_t* status,
+                     void* stream) {
+  if (!program || !parent || !length || !B || !rate || !obs || !node_state || !ev_time || !ev_sb ||
+      !ev_count || !ev_total || !status)
+    return arg_error("null pointer");
+  if (obs_kind != 0 && obs_kind != 1) return arg_error("rt_raoteh_sweeps takes codes or masks");
+  if (traj_stride < n_traj || n_sites <= 0 || cap <= 0) return arg_error("sizes");
+  if (n_traj <= 0) return RT_OK;
+  ensure_pool_cached();
+  int rc = rt_raoteh_dispatch(S, obs_kind, n_nodes, n_traj, traj_stride, n_sites, traj0, program,
+                              n_ops, n_slots, parent, length, B, rate, root_distn, obs, obs_stride,
+                              node_state, ev_time, ev_sb, ev_count, ev_total, cap, seed, sweep0,
+                              n_sweeps, init_k, dwell_sum, trans_sum, status, (cudaStream_t)stream);
+  if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: S or shared-memory budget");
+  return rc;
 }
 
 }  // extern "C"

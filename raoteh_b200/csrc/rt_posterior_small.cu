@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kSitesPerCta = 4096;
+constexpr int kSitesPerCta = 2048;
 
 template <int S>
 __global__ void __launch_bounds__(kBlock)
@@ -71,7 +71,7 @@ root_distn_kernel(int64_t n_sites, int64_t stride, const double* __restrict__ ro
 }
 
 template <int S, int OBS>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, (S <= 4 ? 2 : 1))
 down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edges,
                   const double* __restrict__ P, const void* __restrict__ obs,
                   const double* __restrict__ partials, const int8_t* __restrict__ status,
@@ -96,18 +96,19 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
 
   const int64_t lo = (int64_t)blockIdx.x * kSitesPerCta;
   const int64_t hi = (n_sites < lo + kSitesPerCta) ? n_sites : lo + kSitesPerCta;
-  for (int64_t site = lo + tid; site < hi; site += kBlock) {
-    if (status[site] != RT_SITE_OK) {
-      if (Dc) {
+
+  // loads of one site (software-pipelined: the next site's loads are in flight
+  // while the current one is computed)
+  auto load_site = [&](int64_t site, double (&L)[S], double (&D)[S], bool& ok) {
+    ok = site < hi && status[site] == RT_SITE_OK;
+    if (!ok) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) Dc[(int64_t)s * stride + site] = 0.0;
-      }
-      continue;
+      for (int s = 0; s < S; ++s) { L[s] = 0.0; D[s] = 0.0; }
+      return;
     }
-    double L[S], D[S];
     if (Lc) {
 #pragma unroll
-      for (int s = 0; s < S; ++s) L[s] = Lc[(int64_t)s * stride + site];
+      for (int s = 0; s < S; ++s) L[s] = __ldcs(&Lc[(int64_t)s * stride + site]);
     } else if (e.w < 0) {
 #pragma unroll
       for (int s = 0; s < S; ++s) L[s] = 1.0;
@@ -127,6 +128,24 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
     }
 #pragma unroll
     for (int s = 0; s < S; ++s) D[s] = Dp[(int64_t)s * stride + site];
+  };
+
+  double Ln[S], Dn[S];
+  bool okn;
+  load_site(lo + tid, Ln, Dn, okn);
+  for (int64_t site = lo + tid; site < hi; site += kBlock) {
+    double L[S], D[S];
+    const bool ok = okn;
+#pragma unroll
+    for (int s = 0; s < S; ++s) { L[s] = Ln[s]; D[s] = Dn[s]; }
+    load_site(site + kBlock, Ln, Dn, okn);
+    if (!ok) {
+      if (Dc) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) Dc[(int64_t)s * stride + site] = 0.0;
+      }
+      continue;
+    }
     double G[S];
 #pragma unroll
     for (int a = 0; a < S; ++a) {

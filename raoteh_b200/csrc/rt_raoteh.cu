@@ -1,0 +1,455 @@
+// K6: Rao-Teh uniformization sweeps on trees, one thread per (chain, site)
+// trajectory, counter-based Philox4x32-10 RNG.
+//
+// Replaces the reference's per-trajectory Python/networkx sweep
+//   _sampler.gen_restricted_histories loop      raoteh/sampler/_sampler.py:366-390
+//   _sample_mjp.resample_poisson                 raoteh/sampler/_sample_mjp.py:19-69
+//   _graph_transform.get_chunk_tree_type_b       raoteh/sampler/_graph_transform.py:298
+//   _sample_mcy.resample_edge_states -> FFBS     raoteh/sampler/_sample_mcy.py:86-187,
+//                                                _sample_mc0.py:20-93
+//   _graph_transform.remove_redundant_nodes      raoteh/sampler/_graph_transform.py:144
+//   _mjp.get_history_statistics                  raoteh/sampler/_mjp.py:150 (dwell :74, transitions :97)
+//   _sampler.get_restricted_feasible_history     raoteh/sampler/_sampler.py:563-643 (init mode)
+//
+// A trajectory is stored implicitly: a state per tree node plus, per edge, the
+// list of real jumps (time from the parent end, state on the parent side).  The
+// chunk tree of the reference is never built: an edge with k events is a chain
+// of k steps of the uniformized matrix B = I + Q/omega between its end points,
+// and an edge without events forces equal end states.
+//
+// One sweep = two passes over the host-built upward program (the same program
+// the pruning kernels walk):
+//   UP   (child -> parent along every edge): thin a Poisson process of rate
+//        omega - q_s onto every constant-state segment, and at each event
+//        (virtual or old jump) push the backward message through B.  Instead of
+//        keeping every message for the backward-sampling pass, the thread draws
+//        the next state for EVERY possible parent-side state right away (one
+//        uniform, S inverse-CDF look-ups that share the mat-vec's partial sums)
+//        and stores that S-entry table (4 bits per entry).  Partials then live
+//        only in a small per-thread stack in shared memory.
+//   DOWN (program reversed): sample the root from pi * L_root, then resolve the
+//        tables by look-up, drop self-transitions, accumulate dwell times and
+//        transition counts, and rewrite the jump lists.
+// The law is exactly that of FFBS: a table row is used only for the realised
+// parent state, and rows use independent randomness from everything upstream.
+#include "rt_common.cuh"
+
+namespace {
+
+constexpr int kBlock = 128;
+
+// ---------------- Philox4x32-10 (Salmon et al. 2011), counter based ----------------
+struct Philox {
+  uint32_t key0, key1;
+  uint32_t c0, c1, c2, c3;
+  uint32_t out[4];
+  int have;
+  __device__ __forceinline__ void init(uint64_t seed, uint64_t traj, uint32_t sweep) {
+    key0 = (uint32_t)seed; key1 = (uint32_t)(seed >> 32);
+    c0 = 0; c1 = sweep; c2 = (uint32_t)traj; c3 = (uint32_t)(traj >> 32);
+    have = 0;
+  }
+  __device__ __forceinline__ void round(uint32_t k0, uint32_t k1, uint32_t (&c)[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ __forceinline__ void refill() {
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round(k0, k1, c);
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    ++c0;
+    have = 4;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    if (have == 0) refill();
+    --have;
+    return out[have];
+  }
+  // uniform in (0, 1]
+  __device__ __forceinline__ float uniform() { return ((float)next() + 1.0f) * 2.3283064365386963e-10f; }
+  __device__ __forceinline__ double uniform_d() { return ((double)next() + 0.5) * 2.3283064365386963e-10; }
+};
+
+template <int S, int OBS>
+__device__ __forceinline__ void load_obs_vec(const void* obs, int slot, int64_t obs_stride,
+                                             int64_t site, double (&v)[S]) {
+  if (OBS == OBS_CODES) {
+    const int k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)slot * obs_stride + site];
+#pragma unroll
+    for (int s = 0; s < S; ++s) v[s] = (k == RT_MISSING || k == s) ? 1.0 : 0.0;
+  } else {
+    const unsigned long long mk =
+        reinterpret_cast<const unsigned long long*>(obs)[(int64_t)slot * obs_stride + site];
+#pragma unroll
+    for (int s = 0; s < S; ++s) v[s] = ((mk >> s) & 1ull) ? 1.0 : 0.0;
+  }
+}
+
+struct SweepArgs {
+  int n_nodes, n_ops, n_slots, cap, scr_cap;
+  int64_t n_traj, stride, n_sites, obs_stride, traj0;
+  const int4* program;
+  const int32_t* parent;
+  const double* length;
+  const double* B;
+  const double* rate;
+  const double* root_distn;
+  const void* obs;
+  uint8_t* node_state;   // [n_nodes][stride]
+  float* ev_time;        // [cap][stride]   jumps in up order, occupying [cap - total, cap)
+  uint8_t* ev_sb;        // [cap][stride]   state on the parent side of the jump
+  uint8_t* ev_count;     // [n_nodes][stride]
+  int32_t* ev_total;     // [stride]
+  float* scr_time;       // [scr_cap][stride]
+  uint32_t* scr_tab;     // [scr_cap][stride]
+  uint8_t* scr_count;    // [n_nodes][stride]
+  unsigned long long seed;
+  long long sweep0;
+  int n_sweeps;
+  int init_k;            // >= 0: initial-history mode with init_k equally spaced events per edge
+  double* dwell_sum;     // [S]   += over trajectories and sweeps
+  double* trans_sum;     // [S*S] +=
+  int8_t* status;        // [stride]
+};
+
+// One event on the way up: table[a] = draw from B[a,:] * beta, beta <- B beta.
+template <int S>
+__device__ __forceinline__ uint32_t event_up(const double* __restrict__ Bs, double (&beta)[S], double u) {
+  double nb[S];
+  uint32_t tab = 0;
+#pragma unroll
+  for (int a = 0; a < S; ++a) {
+    double w[S];
+    double tot = 0.0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) { w[s] = Bs[a * S + s] * beta[s]; tot += w[s]; }
+    nb[a] = tot;
+    const double x = u * tot;
+    double cum = 0.0;
+    int pick = S - 1;
+    bool found = false;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      cum += w[s];
+      if (!found && w[s] > 0.0 && x <= cum) { pick = s; found = true; }
+    }
+    if (!found) {   // rounding at the top end: last state with positive weight
+#pragma unroll
+      for (int s = 0; s < S; ++s) if (w[s] > 0.0) pick = s;
+    }
+    tab |= (uint32_t)pick << (4 * a);
+  }
+#pragma unroll
+  for (int a = 0; a < S; ++a) beta[a] = nb[a];
+  return tab;
+}
+
+template <int S, int OBS, bool STATS>
+__global__ void __launch_bounds__(kBlock)
+raoteh_kernel(SweepArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int4* prog_s = reinterpret_cast<int4*>(smem_raw);
+  double* B_s = reinterpret_cast<double*>(prog_s + A.n_ops);
+  double* rate_s = B_s + S * S;
+  double* pi_s = rate_s + S;
+  float* len_s = reinterpret_cast<float*>(pi_s + S);
+  int* par_s = reinterpret_cast<int*>(len_s + A.n_nodes);
+  double* stk = reinterpret_cast<double*>(par_s + A.n_nodes);   // 8*n_nodes bytes so far: aligned
+  __shared__ double red[kBlock / 32][S * S + S];
+
+  const int tid = threadIdx.x;
+  for (int i = tid; i < A.n_ops; i += kBlock) prog_s[i] = A.program[i];
+  for (int i = tid; i < S * S; i += kBlock) B_s[i] = A.B[i];
+  if (tid < S) { rate_s[tid] = A.rate[tid]; pi_s[tid] = A.root_distn ? A.root_distn[tid] : 1.0; }
+  for (int i = tid; i < A.n_nodes; i += kBlock) { len_s[i] = (float)A.length[i]; par_s[i] = A.parent[i]; }
+  __syncthreads();
+
+  const int64_t traj = (int64_t)blockIdx.x * kBlock + tid;
+  const bool active = traj < A.n_traj && A.status[traj] == RT_SITE_OK;
+  const int64_t site = active ? (A.traj0 + traj) % A.n_sites : 0;
+  const int64_t st = A.stride;
+
+  double dwell[S], trans[S * S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) dwell[s] = 0.0;
+#pragma unroll
+  for (int s = 0; s < S * S; ++s) trans[s] = 0.0;
+
+  if (active) {
+    Philox rng;
+    for (int sw = 0; sw < A.n_sweeps; ++sw) {
+      rng.init(A.seed, (uint64_t)(A.traj0 + traj), (uint32_t)(A.sweep0 + sw));
+      // =============================== UP ===============================
+      int nA = 0;                                   // entries pushed to the scratch list
+      int rd = A.cap - A.ev_total[traj];            // read cursor in the old jump list
+      bool overflow = false;
+      double acc[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = 1.0;
+      int root_state = 0;
+      bool infeasible = false;
+
+      for (int ip = 0; ip < A.n_ops; ++ip) {
+        const int4 op = prog_s[ip];
+        const int code = op.x & 0xff;
+        if (code <= OP_MSG_ONES) {
+          const int c = op.y;
+          double beta[S];
+          if (code == OP_MSG_SLOT) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) beta[s] = stk[(op.z * S + s) * kBlock + tid];
+          } else if (code == OP_MSG_OBS) {
+            load_obs_vec<S, OBS>(A.obs, op.z, A.obs_stride, site, beta);
+          } else {
+#pragma unroll
+            for (int s = 0; s < S; ++s) beta[s] = 1.0;
+          }
+          const float tc = len_s[c];
+          int kA = 0;
+          if (A.init_k >= 0) {
+            // initial history: init_k equally spaced events (_sampler.py:612-631)
+            for (int j = A.init_k; j >= 1; --j) {
+              const uint32_t tab = event_up<S>(B_s, beta, rng.uniform_d());
+              if (nA < A.scr_cap) {
+                A.scr_time[(int64_t)nA * st + traj] = tc * (float)j / (float)(A.init_k + 1);
+                A.scr_tab[(int64_t)nA * st + traj] = tab;
+              } else overflow = true;
+              ++nA; ++kA;
+            }
+          } else {
+            int cur = A.node_state[(int64_t)c * st + traj];
+            const int k_old = A.ev_count[(int64_t)c * st + traj];
+            float seg_end = tc;
+            for (int j = 0; j <= k_old; ++j) {
+              float seg_start = 0.0f;
+              int sb = 0;
+              if (j < k_old) {
+                seg_start = A.ev_time[(int64_t)rd * st + traj];
+                sb = A.ev_sb[(int64_t)rd * st + traj];
+                ++rd;
+              }
+              // virtual events on (seg_start, seg_end), state `cur`, rate omega - q_cur
+              const float r = (float)rate_s[cur];
+              if (r > 0.0f) {
+                float pos = seg_end;
+                while (true) {
+                  pos -= -__logf(rng.uniform()) / r;
+                  if (!(pos > seg_start)) break;
+                  const uint32_t tab = event_up<S>(B_s, beta, rng.uniform_d());
+                  if (nA < A.scr_cap) {
+                    A.scr_time[(int64_t)nA * st + traj] = pos;
+                    A.scr_tab[(int64_t)nA * st + traj] = tab;
+                  } else overflow = true;
+                  ++nA; ++kA;
+                }
+              }
+              if (j < k_old) {   // the old jump itself stays a candidate event
+                const uint32_t tab = event_up<S>(B_s, beta, rng.uniform_d());
+                if (nA < A.scr_cap) {
+                  A.scr_time[(int64_t)nA * st + traj] = seg_start;
+                  A.scr_tab[(int64_t)nA * st + traj] = tab;
+                } else overflow = true;
+                ++nA; ++kA;
+                cur = sb;
+                seg_end = seg_start;
+              }
+            }
+          }
+          if (kA > 255) overflow = true;
+          A.scr_count[(int64_t)c * st + traj] = (uint8_t)(kA > 255 ? 255 : kA);
+          if (kA > 0) {   // keep the chain of B-steps in range
+            double mx = beta[0];
+#pragma unroll
+            for (int s = 1; s < S; ++s) mx = fmax(mx, beta[s]);
+            if (mx > 0.0) {
+              const double sc = rt_pow2_neg(rt_exponent(mx));
+#pragma unroll
+              for (int s = 0; s < S; ++s) beta[s] *= sc;
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < S; ++s) acc[s] *= beta[s];
+        } else if (code == OP_APPLY_OBS) {
+          double v[S];
+          load_obs_vec<S, OBS>(A.obs, op.z, A.obs_stride, site, v);
+#pragma unroll
+          for (int s = 0; s < S; ++s) acc[s] *= v[s];
+        } else {   // OP_STORE / OP_ROOT
+          double mx = acc[0];
+#pragma unroll
+          for (int s = 1; s < S; ++s) mx = fmax(mx, acc[s]);
+          if (mx > 0.0) {
+            const double sc = rt_pow2_neg(rt_exponent(mx));
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc[s] *= sc;
+          }
+          if (code == OP_STORE) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) { stk[(op.z * S + s) * kBlock + tid] = acc[s]; acc[s] = 1.0; }
+          } else {
+            // root ~ pi * L_root  (_sample_mc0.py:41-90)
+            double w[S], tot = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) { w[s] = pi_s[s] * acc[s]; tot += w[s]; }
+            if (!(tot > 0.0)) infeasible = true;
+            const double x = rng.uniform_d() * tot;
+            double cum = 0.0;
+            bool found = false;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              cum += w[s];
+              if (!found && w[s] > 0.0 && x <= cum) { root_state = s; found = true; }
+            }
+            if (!found) {
+#pragma unroll
+              for (int s = 0; s < S; ++s) if (w[s] > 0.0) root_state = s;
+            }
+          }
+        }
+      }
+      if (infeasible) { A.status[traj] = RT_SITE_STRUCTURAL_ZERO; break; }
+      if (overflow) { A.status[traj] = 3; break; }
+
+      // ============================== DOWN ==============================
+      A.node_state[traj] = (uint8_t)root_state;
+      int rdA = nA;          // scratch is consumed backwards
+      int wr = A.cap;        // new jump list grows backwards from the end
+      bool pool_overflow = false;
+      for (int ip = A.n_ops - 1; ip >= 0; --ip) {
+        const int4 op = prog_s[ip];
+        if ((op.x & 0xff) > OP_MSG_ONES) continue;
+        const int c = op.y;
+        int cur = A.node_state[(int64_t)par_s[c] * st + traj];
+        const int kA = A.scr_count[(int64_t)c * st + traj];
+        const float tc = len_s[c];
+        float prev = 0.0f;
+        int kept = 0;
+        for (int j = 0; j < kA; ++j) {
+          --rdA;
+          const float tau = A.scr_time[(int64_t)rdA * st + traj];
+          const uint32_t tab = A.scr_tab[(int64_t)rdA * st + traj];
+          const int nxt = (tab >> (4 * cur)) & 15;
+          if (STATS) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) dwell[s] += (s == cur) ? (double)(tau - prev) : 0.0;
+          }
+          prev = tau;
+          if (nxt != cur) {
+            if (STATS) {
+#pragma unroll
+              for (int q = 0; q < S * S; ++q) trans[q] += (q == cur * S + nxt) ? 1.0 : 0.0;
+            }
+            --wr;
+            if (wr >= 0) {
+              A.ev_time[(int64_t)wr * st + traj] = tau;
+              A.ev_sb[(int64_t)wr * st + traj] = (uint8_t)cur;
+            } else pool_overflow = true;
+            ++kept;
+            cur = nxt;
+          }
+        }
+        if (STATS) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) dwell[s] += (s == cur) ? (double)(tc - prev) : 0.0;
+        }
+        A.node_state[(int64_t)c * st + traj] = (uint8_t)cur;
+        A.ev_count[(int64_t)c * st + traj] = (uint8_t)kept;
+      }
+      // jumps were written in down order from the end backwards == up order forwards
+      if (pool_overflow) { A.status[traj] = 4; A.ev_total[traj] = 0; break; }
+      A.ev_total[traj] = A.cap - wr;
+    }
+  }
+
+  if (STATS && A.dwell_sum) {
+#pragma unroll
+    for (int q = 0; q < S + S * S; ++q) {
+      const double v = rt_warp_sum(q < S ? dwell[q < S ? q : 0] : trans[q >= S ? q - S : 0]);
+      if ((tid & 31) == 0) red[tid >> 5][q] = v;
+    }
+    __syncthreads();
+    if (tid < S + S * S) {
+      double t = 0.0;
+      for (int i = 0; i < kBlock / 32; ++i) t += red[i][tid];
+      if (t != 0.0) atomicAdd(tid < S ? &A.dwell_sum[tid] : &A.trans_sum[tid - S], t);
+    }
+  }
+}
+
+template <int S, int OBS>
+int launch(const SweepArgs& A, bool stats, cudaStream_t stream) {
+  size_t smem = sizeof(int4) * A.n_ops + sizeof(double) * (S * S + 2 * S) +
+                sizeof(float) * A.n_nodes + sizeof(int) * A.n_nodes +
+                sizeof(double) * (size_t)A.n_slots * S * kBlock + 16;
+  if (smem > 200 * 1024) return RT_ERR_UNSUPPORTED;
+  const unsigned grid = (unsigned)((A.n_traj + kBlock - 1) / kBlock);
+  if (stats) {
+    auto kern = raoteh_kernel<S, OBS, true>;
+    RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kBlock, smem, stream>>>(A);
+  } else {
+    auto kern = raoteh_kernel<S, OBS, false>;
+    RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kBlock, smem, stream>>>(A);
+  }
+  RT_CUDA_CHECK(cudaGetLastError());
+  return RT_OK;
+}
+
+template <int S>
+int launch_s(int obs_kind, const SweepArgs& A, bool stats, cudaStream_t stream) {
+  if (obs_kind == OBS_CODES) return launch<S, OBS_CODES>(A, stats, stream);
+  if (obs_kind == OBS_MASK) return launch<S, OBS_MASK>(A, stats, stream);
+  return RT_ERR_ARG;
+}
+
+}  // namespace
+
+int rt_raoteh_dispatch(int S, int obs_kind, int n_nodes, int64_t n_traj, int64_t stride,
+                       int64_t n_sites, int64_t traj0, const int32_t* program, int n_ops, int n_slots,
+                       const int32_t* parent, const double* length, const double* B,
+                       const double* rate, const double* root_distn, const void* obs,
+                       int64_t obs_stride, uint8_t* node_state, float* ev_time, uint8_t* ev_sb,
+                       uint8_t* ev_count, int32_t* ev_total, int cap, uint64_t seed, int64_t sweep0,
+                       int n_sweeps, int init_k, double* dwell_sum, double* trans_sum,
+                       int8_t* status, cudaStream_t stream) {
+  SweepArgs A;
+  A.n_nodes = n_nodes; A.n_ops = n_ops; A.n_slots = n_slots; A.cap = cap;
+  A.scr_cap = cap;   // kept jumps <= scratch entries <= cap: the jump list can never overflow
+  A.n_traj = n_traj; A.stride = stride; A.n_sites = n_sites; A.obs_stride = obs_stride; A.traj0 = traj0;
+  A.program = reinterpret_cast<const int4*>(program);
+  A.parent = parent; A.length = length; A.B = B; A.rate = rate; A.root_distn = root_distn;
+  A.obs = obs; A.node_state = node_state; A.ev_time = ev_time; A.ev_sb = ev_sb;
+  A.ev_count = ev_count; A.ev_total = ev_total;
+  A.seed = seed; A.sweep0 = sweep0; A.n_sweeps = n_sweeps; A.init_k = init_k;
+  A.dwell_sum = dwell_sum; A.trans_sum = trans_sum; A.status = status;
+  // scratch: full event list (time + table) and per-edge counts
+  unsigned char* ws = nullptr;
+  const size_t n_scr = (size_t)A.scr_cap * (size_t)stride;
+  const size_t bytes = n_scr * (sizeof(float) + sizeof(uint32_t)) + (size_t)n_nodes * (size_t)stride;
+  RT_CUDA_CHECK(cudaMallocAsync(&ws, bytes, stream));
+  A.scr_time = reinterpret_cast<float*>(ws);
+  A.scr_tab = reinterpret_cast<uint32_t*>(ws + n_scr * sizeof(float));
+  A.scr_count = ws + n_scr * (sizeof(float) + sizeof(uint32_t));
+  const bool stats = dwell_sum != nullptr && trans_sum != nullptr && init_k < 0;
+  int rc;
+  switch (S) {
+    case 2: rc = launch_s<2>(obs_kind, A, stats, stream); break;
+    case 3: rc = launch_s<3>(obs_kind, A, stats, stream); break;
+    case 4: rc = launch_s<4>(obs_kind, A, stats, stream); break;
+    case 5: rc = launch_s<5>(obs_kind, A, stats, stream); break;
+    case 6: rc = launch_s<6>(obs_kind, A, stats, stream); break;
+    case 8: rc = launch_s<8>(obs_kind, A, stats, stream); break;
+    default: rc = RT_ERR_UNSUPPORTED;
+  }
+  cudaFreeAsync(ws, stream);
+  return rc;
+}

@@ -104,20 +104,59 @@ class TreeMJP(object):
                            else torch.from_numpy(self.root_distn_host.copy()).to(self.device))
         self.parent = torch.from_numpy(sched.parent.copy()).to(self.device)
         self._P = None
+        self._P_valid = False
         if P is not None:   # caller-supplied per-edge transition matrices [n,S,S]
             self._P = torch.from_numpy(np.ascontiguousarray(P, dtype=np.float64)).to(self.device)
+            self._P_valid = True
         self._prog_cache = {}
+        self._ws = {}
+        self._Q_stage = None
+        self.events = None     # optional dict: name -> [(start, end) CUDA events]
+
+    def _buf(self, name, shape, dtype, zero=False):
+        """Reusable device workspace (avoids per-call allocation)."""
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self._ws[key] = t
+        if zero:
+            t.zero_()
+        return t
+
+    def _mark(self, name):
+        if self.events is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.events.setdefault(name, []).append(e)
+        return e
+
+    def set_rate_matrix(self, Q):
+        """New rate matrix/matrices for the same tree (e.g. inside an optimiser
+        loop): one small pinned, non-blocking H2D copy; P is recomputed lazily."""
+        Q = np.asarray(Q, dtype=np.float64)
+        Q = Q if Q.ndim == 3 else Q[None]
+        if Q.shape != tuple(self.Q.shape):
+            raise ValueError('rate matrix shape changed')
+        if self._Q_stage is None:
+            self._Q_stage = torch.empty(self.Q.shape, dtype=torch.float64).pin_memory()
+        self._Q_stage.copy_(torch.from_numpy(Q))
+        self.Q.copy_(self._Q_stage, non_blocking=True)
+        self.Q_host = Q
+        self._P_valid = False
 
     # ---- K1 ---------------------------------------------------------------
     def transition_matrices(self):
         """P[b] = expm(Q_b t_b) for every node b (slot 0 = identity); cached."""
-        if self._P is None:
+        if not self._P_valid:
             n, S = self.sched.n, self.S
-            P = torch.empty((n, S, S), dtype=torch.float64, device=self.device)
+            if self._P is None:
+                self._P = torch.empty((n, S, S), dtype=torch.float64, device=self.device)
             rc = _native.lib().rt_expm_batched(_ptr(self.Q), _ptr(self.q_index), _ptr(self.length),
-                                               n, S, _ptr(P), _stream())
+                                               n, S, _ptr(self._P), _stream())
             _native.check(rc, 'rt_expm_batched')
-            self._P = P
+            self._P_valid = True
         return self._P
 
     def _programs(self, obs):
@@ -157,14 +196,16 @@ class TreeMJP(object):
             loglik, status = out
         partials = exponents = None
         if keep_partials:
-            partials = torch.empty((self.sched.n_store, self.S, stride), dtype=torch.float64, device=dev)
+            partials = self._buf('partials', (self.sched.n_store, self.S, stride), torch.float64)
             if want_exponents:
-                exponents = torch.empty((self.sched.n_store, stride), dtype=torch.int32, device=dev)
+                exponents = self._buf('exponents', (self.sched.n_store, stride), torch.int32)
+        self._mark('up')
         rc = _native.lib().rt_prune_loglik(
             self.S, self.sched.n, N, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
             _ptr(P), _ptr(self.root_distn), obs.kind, _ptr(obs.data), _ptr(partials),
             _ptr(exponents), _ptr(loglik), _ptr(status), _ptr(loglik_sum), _stream())
         _native.check(rc, 'rt_prune_loglik')
+        self._mark('up')
         res = dict(loglik=loglik, status=status)
         if keep_partials:
             res['partials'] = partials
@@ -180,22 +221,24 @@ class TreeMJP(object):
         N, stride = obs.n_sites, obs.stride
         dev = self.device
         P = self.transition_matrices()
-        node_distn = torch.empty((self.sched.n_store, self.S, stride), dtype=torch.float64, device=dev)
-        W = torch.zeros((self.sched.n, self.S, self.S), dtype=torch.float64, device=dev)
-        root_post_sum = torch.zeros(self.S, dtype=torch.float64, device=dev)
+        node_distn = self._buf('node_distn', (self.sched.n_store, self.S, stride), torch.float64)
+        W = self._buf('W', (self.sched.n, self.S, self.S), torch.float64, zero=True)
+        root_post_sum = self._buf('root_post_sum', (self.S,), torch.float64, zero=True)
         lp = prog['level_ptr']
+        self._mark('down')
         rc = _native.lib().rt_posterior_stats(
             self.S, self.sched.n, N, stride, _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
             _ptr(P), _ptr(self.root_distn), obs.kind, _ptr(obs.data), _ptr(up['partials']),
             _ptr(up['status']), _ptr(node_distn), _ptr(W), _ptr(root_post_sum), _stream())
         _native.check(rc, 'rt_posterior_stats')
-        up.update(node_distn=node_distn, W=W, root_post_sum=root_post_sum)
+        self._mark('down')
+        up.update(node_distn=node_distn, W=W, root_post_sum=root_post_sum, n_levels=len(lp) - 1)
         return up
 
     def frechet_contract(self, W):
         """M[b] = L(t_b Q_b^T, t_b W[b]) for every node b (slot 0 -> 0)."""
         n, S = self.sched.n, self.S
-        M = torch.empty((n, S, S), dtype=torch.float64, device=self.device)
+        M = self._buf('M', (n, S, S), torch.float64)
         rc = _native.lib().rt_frechet_contract(_ptr(self.Q), _ptr(self.q_index), _ptr(self.length),
                                                _ptr(W), n, S, _ptr(M), _stream())
         _native.check(rc, 'rt_frechet_contract')
@@ -216,8 +259,9 @@ class TreeMJP(object):
             Qe = self.Q[0].expand(self.sched.n, S, S)
         else:
             Qe = self.Q[self.q_index.long()]
-        eye = torch.eye(S, dtype=torch.bool, device=self.device)
+        if getattr(self, '_offdiag', None) is None:
+            self._offdiag = 1.0 - torch.eye(S, dtype=torch.float64, device=self.device)
         dwell = torch.diagonal(M, dim1=1, dim2=2).sum(dim=0)
-        trans = (Qe.masked_fill(eye, 0.0) * M).sum(dim=0)
+        trans = (Qe * self._offdiag * M).sum(dim=0)
         post.update(dwell=dwell, trans=trans, M_edges=M, Q_edges=Qe)
         return post

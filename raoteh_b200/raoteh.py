@@ -1,0 +1,152 @@
+"""
+Batched Rao-Teh sampler: many independent (chain, site) trajectories on device.
+
+Host side of K6 (csrc/rt_raoteh.cu).  Mirrors the generator loop of the
+reference, raoteh/sampler/_sampler.py:300-390 (gen_restricted_histories):
+uniformization constants (:346-355), initial feasible history (:362 -> :563),
+then sweeps (:366-390); statistics as _mjp.get_history_statistics
+(raoteh/sampler/_mjp.py:150).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native
+from .engine import OBS_CODES, OBS_MASK, _ptr, _stream
+
+
+class RaoTehChains(object):
+    """n_chains x n_sites trajectories of one MJP on one tree.
+
+    trajectory t = chain * n_sites + site; observations are per site.
+    """
+
+    def __init__(self, sched, Q, obs, n_chains=1, root_distn=None, uniformization_factor=2.0,
+                 cap=96, seed=0, device='cuda', traj0=0, n_traj=None):
+        if not torch.cuda.is_available():
+            raise _native.NativeError('raoteh_b200 needs a CUDA device; there is no CPU fallback')
+        if uniformization_factor <= 1:
+            raise ValueError('the uniformization factor must be greater than 1')
+        Q = np.asarray(Q, dtype=np.float64)
+        self.S = S = Q.shape[0]
+        if S not in (2, 3, 4, 5, 6, 8):
+            raise ValueError('the Rao-Teh kernel supports 2, 3, 4, 5, 6 or 8 states')
+        if obs.kind not in (OBS_CODES, OBS_MASK):
+            raise ValueError('Rao-Teh sampling takes hard codes or allowed-state masks')
+        self.sched = sched
+        self.obs = obs
+        self.device = dev = torch.device(device)
+        self.n_sites = obs.n_sites
+        self.n_chains = int(n_chains)
+        # this object may own a contiguous shard [traj0, traj0 + n_traj) of the global
+        # (chain, site) index space (site sharding across GPUs)
+        self.traj0 = int(traj0)
+        self.n_traj = int(n_chains) * self.n_sites if n_traj is None else int(n_traj)
+        self.cap = int(cap)
+        self.seed = int(seed)
+        # uniformization: omega = f * max_s q_s; B = I + Q/omega; rates omega - q_s
+        q = -np.diag(Q)
+        self.omega = float(uniformization_factor * q.max())
+        if not self.omega > 0:
+            raise ValueError('the rate matrix is empty')
+        B = np.eye(S) + Q / self.omega
+        self.Q_host = Q
+        self.B = torch.from_numpy(B).to(dev)
+        self.rate = torch.from_numpy(self.omega - q).to(dev)
+        self.root_distn = None if root_distn is None else torch.from_numpy(
+            np.asarray(root_distn, dtype=np.float64).copy()).to(dev)
+        ops, n_slots = sched.up_program(obs.obs_slot)
+        self.ops = torch.from_numpy(ops).to(dev)
+        self.n_ops, self.n_slots = len(ops), n_slots
+        self.parent = torch.from_numpy(sched.parent.copy()).to(dev)
+        self.length = torch.from_numpy(sched.length.copy()).to(dev)
+        T, n = self.n_traj, sched.n
+        self.stride = T
+        self.node_state = torch.zeros((n, T), dtype=torch.uint8, device=dev)
+        self.ev_count = torch.zeros((n, T), dtype=torch.uint8, device=dev)
+        self.ev_total = torch.zeros(T, dtype=torch.int32, device=dev)
+        self.ev_time = torch.zeros((self.cap, T), dtype=torch.float32, device=dev)
+        self.ev_sb = torch.zeros((self.cap, T), dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(T, dtype=torch.int8, device=dev)
+        self.dwell_sum = torch.zeros(S, dtype=torch.float64, device=dev)
+        self.trans_sum = torch.zeros((S, S), dtype=torch.float64, device=dev)
+        self.sweeps_done = 0
+        self.initialized = False
+
+    def _call(self, n_sweeps, init_k, stats):
+        rc = _native.lib().rt_raoteh_sweeps(
+            self.S, self.sched.n, self.n_traj, self.stride, self.n_sites, self.traj0,
+            _ptr(self.ops), self.n_ops, self.n_slots, _ptr(self.parent), _ptr(self.length),
+            _ptr(self.B), _ptr(self.rate), _ptr(self.root_distn), self.obs.kind,
+            _ptr(self.obs.data), self.obs.stride, _ptr(self.node_state), _ptr(self.ev_time),
+            _ptr(self.ev_sb), _ptr(self.ev_count), _ptr(self.ev_total), self.cap, self.seed,
+            self.sweeps_done, n_sweeps, init_k,
+            _ptr(self.dwell_sum) if stats else None, _ptr(self.trans_sum) if stats else None,
+            _ptr(self.status), _stream())
+        _native.check(rc, 'rt_raoteh_sweeps')
+
+    def initialize(self):
+        """Initial feasible history: 0, 1, 3, 7, ... equally spaced events per edge
+        until FFBS under B succeeds (raoteh/sampler/_sampler.py:612-643)."""
+        DONE = 5
+        k, j = 0, 0
+        self.status.zero_()
+        while True:
+            if k > self.S:
+                raise RuntimeError('failed to find a feasible history')
+            self._call(1, k, False)
+            failed = self.status == 1
+            self.status[self.status == 0] = DONE
+            if not bool(failed.any()):
+                break
+            self.status[failed] = 0
+            k += 2 ** j
+            j += 1
+        self.status[self.status == DONE] = 0
+        self.sweeps_done = 1      # sweep index 0 was the initial history
+        self.initialized = True
+        return k
+
+    def sweep(self, n_sweeps=1, stats=True):
+        """n_sweeps Rao-Teh sweeps of every trajectory; raises if any trajectory needed
+        more than `cap` candidate events in one sweep."""
+        if not self.initialized:
+            self.initialize()
+        self._call(int(n_sweeps), -1, stats)
+        self.sweeps_done += int(n_sweeps)
+
+    def check(self):
+        bad = int((self.status != 0).sum())
+        if bad:
+            raise _native.NativeError(
+                '%d trajectories exceeded the event capacity cap=%d in one sweep '
+                '(status 3); re-create the sampler with a larger cap' % (bad, self.cap))
+
+    def reset_statistics(self):
+        self.dwell_sum.zero_()
+        self.trans_sum.zero_()
+
+    # -- host-side views --------------------------------------------------------
+    def trajectory(self, t):
+        """Trajectory t as per-edge arrays: dict child node -> (times from the parent
+        end, ascending; states of the k+1 segments, parent side first)."""
+        n = self.sched.n
+        cnt = self.ev_count[:, t].cpu().numpy().astype(int)
+        tot = int(self.ev_total[t])
+        times = self.ev_time[self.cap - tot:, t].cpu().numpy()
+        sbs = self.ev_sb[self.cap - tot:, t].cpu().numpy().astype(int)
+        ns = self.node_state[:, t].cpu().numpy().astype(int)
+        out = {}
+        pos = 0
+        ops = self.ops.cpu().numpy()
+        for code, c, a, b in ops:
+            if (code & 0xff) > 2:
+                continue
+            k = cnt[c]
+            tt = times[pos:pos + k][::-1]          # stored child end first
+            sb = sbs[pos:pos + k][::-1]
+            pos += k
+            states = np.concatenate([sb, [ns[c]]]) if k else np.array([ns[c]])
+            out[int(c)] = (tt.astype(float), states)
+        return ns, out

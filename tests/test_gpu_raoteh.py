@@ -1,0 +1,152 @@
+"""Rao-Teh sweeps (K6) on the GPU: structural invariants of every sampled history
+(the assertions of raoteh/sampler/tests/test_sampler.py:398-438) and distributional
+agreement with the closed-form posterior expectations
+(_mjp.get_expected_history_statistics), which the reference only prints
+(tests/test_sampler.py:251-393).  z-score bound stated per test."""
+import numpy as np
+import pytest
+
+from oracle import np_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(S, n_leaves, n_sites, seed, missing=0.0):
+    from raoteh_b200 import synth, engine
+    from raoteh_b200.lowering import TreeSchedule
+    rng = np.random.default_rng(seed)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.25, rng)
+    if S == 4:
+        Q, pi = synth.hky85()
+    else:
+        Q = rng.exponential(1.0, size=(S, S))
+        np.fill_diagonal(Q, 0)
+        Q -= np.diag(Q.sum(axis=1))
+        Q /= np.abs(np.diag(Q)).mean()
+        pi = rng.dirichlet(np.ones(S) * 3)
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, missing)
+    sched = TreeSchedule(parent, length)
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaves)
+    return parent, length, leaves, Q, pi, codes, sched, obs
+
+
+def test_histories_respect_structure():
+    from raoteh_b200.raoteh import RaoTehChains
+    parent, length, leaves, Q, pi, codes, sched, obs = _setup(4, 12, 5, 11, missing=0.1)
+    ch = RaoTehChains(sched, Q, obs, n_chains=7, root_distn=pi, seed=3)
+    ch.initialize()
+    ch.sweep(25)
+    ch.check()
+    for t in range(ch.n_traj):
+        site = t % 5
+        ns, edges = ch.trajectory(t)
+        assert len(edges) == sched.n - 1
+        for c, (times, states) in edges.items():
+            assert states[0] == ns[parent[c]]            # consistent state around original nodes
+            assert states[-1] == ns[c]
+            assert len(states) == len(times) + 1
+            assert np.all(np.diff(times) > 0) or len(times) < 2
+            assert np.all(times > 0) and np.all(times < length[c])
+            assert np.all(states[1:] != states[:-1])      # self-transitions were dropped
+        for i, leaf in enumerate(leaves):                 # observed leaf states are respected
+            if codes[i, site] != 255:
+                assert ns[leaf] == codes[i, site]
+
+
+def test_philox_is_counter_based():
+    """Same (seed, global trajectory index, sweep) -> same history, however the
+    trajectories are split over launches / ranks."""
+    import torch
+    from raoteh_b200.raoteh import RaoTehChains
+    parent, length, leaves, Q, pi, codes, sched, obs = _setup(4, 10, 6, 5)
+    full = RaoTehChains(sched, Q, obs, n_chains=4, root_distn=pi, seed=9)
+    full.sweep(5)
+    full.sweep(3)
+    lo = RaoTehChains(sched, Q, obs, n_chains=4, root_distn=pi, seed=9, traj0=0, n_traj=10)
+    hi = RaoTehChains(sched, Q, obs, n_chains=4, root_distn=pi, seed=9, traj0=10, n_traj=14)
+    for part in (lo, hi):
+        part.sweep(8)
+    ns = torch.cat([lo.node_state, hi.node_state], dim=1)
+    assert bool((ns == full.node_state).all())
+    tot = torch.cat([lo.ev_total, hi.ev_total])
+    assert bool((tot == full.ev_total).all())
+    np.testing.assert_allclose((lo.dwell_sum + hi.dwell_sum).cpu().numpy(),
+                               full.dwell_sum.cpu().numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize('S,n_leaves', [(4, 8), (3, 5), (6, 6)])
+def test_sweep_statistics_match_closed_form(S, n_leaves):
+    """Mean dwell times / transition counts over many chains and sweeps vs the
+    closed-form posterior expectations; |z| < 5 per statistic with the standard
+    error estimated from 16 independent groups of chains."""
+    from raoteh_b200.raoteh import RaoTehChains
+    n_sites = 3
+    parent, length, leaves, Q, pi, codes, sched, obs = _setup(S, n_leaves, n_sites, 100 + S)
+    P = np_oracle.expm_edges(Q, length)
+    o = np_oracle.expected_history_statistics(
+        parent, length, Q, P, np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes), pi)
+    groups, n_chains, burn, n_sweeps = 16, 512, 60, 120
+    dwell = np.zeros((groups, S))
+    trans = np.zeros((groups, S, S))
+    for gidx in range(groups):
+        ch = RaoTehChains(sched, Q, obs, n_chains=n_chains, root_distn=pi, seed=1000 + gidx)
+        ch.sweep(burn, stats=False)
+        ch.sweep(n_sweeps)
+        ch.check()
+        dwell[gidx] = ch.dwell_sum.cpu().numpy() / (n_chains * n_sweeps)
+        trans[gidx] = ch.trans_sum.cpu().numpy() / (n_chains * n_sweeps)
+    # total dwell per sweep is exactly the tree length (float32 event times)
+    np.testing.assert_allclose(dwell.sum(axis=1), length.sum() * n_sites, rtol=1e-5)
+    for got, want in ((dwell, o['dwell']), (trans.reshape(groups, -1), o['trans'].reshape(-1))):
+        mean = got.mean(axis=0)
+        se = got.std(axis=0, ddof=1) / np.sqrt(groups)
+        for m, s, w in zip(mean, se, want):
+            if w == 0:
+                assert m == 0
+            else:
+                assert abs(m - w) < 5 * s + 1e-9, (m, w, s)
+
+
+def test_jukes_cantor_path_dwell():
+    """raoteh/sampler/tests/test_sampler.py:86-122: one branch with known end states."""
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
+    n, t = 4, 0.5
+    Q = (np.ones((n, n)) - np.eye(n)) / (n - 1)
+    Q -= np.diag(Q.sum(axis=1))
+    sched = TreeSchedule(np.array([-1, 0], dtype=np.int32), np.array([0.0, t]))
+    a, b = 0, 2
+    mask = np.array([[1 << a], [1 << b]], dtype=np.uint64)
+    obs = engine.Observations.from_masks(sched, mask)
+    ch = RaoTehChains(sched, Q, obs, n_chains=20000, seed=4)
+    ch.sweep(30, stats=False)
+    ch.sweep(50)
+    ch.check()
+    p = np.exp(-(n * t) / (n - 1))
+    pm1 = np.expm1(-(n * t) / (n - 1))
+    pab = (1 - p) / n
+
+    def interaction(c):   # _conditional_expectation.py:35-46 with d = c
+        if a != c and c != b:
+            x = t * p + pm1 * 2 * (n - 1) / n
+        else:
+            x = -(n - 1) * t * p - pm1 * (n - 2) * (n - 1) / n
+        return (t + x) / (n * n)
+    want = np.array([interaction(c) / pab for c in range(n)])
+    got = ch.dwell_sum.cpu().numpy() / (20000 * 50)
+    np.testing.assert_allclose(got, want, rtol=0.02)
+
+
+def test_infeasible_data_is_reported():
+    """raoteh/sampler/tests/test_sample_mcx.py:79-99 analogue: no feasible history."""
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
+    Q = np.array([[-1.0, 1.0, 0.0], [0.0, -1.0, 1.0], [0.0, 0.0, 0.0]])   # 0 -> 1 -> 2, absorbing
+    sched = TreeSchedule(np.array([-1, 0], dtype=np.int32), np.array([0.0, 1.0]))
+    mask = np.array([[1 << 2], [1 << 0]], dtype=np.uint64)                # root in 2, leaf in 0
+    obs = engine.Observations.from_masks(sched, mask)
+    ch = RaoTehChains(sched, Q, obs, n_chains=3, seed=1)
+    with pytest.raises(RuntimeError):
+        ch.initialize()
