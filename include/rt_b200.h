@@ -72,6 +72,7 @@ int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t
  * Structural support of every node for every site (integer work):
  * backward pass (state kept iff every child has a reachable kept state) then
  * forward pass (state kept iff reachable from a kept parent state).
+ * passes: 1 = backward only (the reference's "pset"), 3 = backward then forward ("set").
  * mask: uint64 [n_nodes][site_stride] in/out; parent: int32 [n_nodes];
  * P: [n_nodes][S][S] (only the > 0 pattern is used).  S <= 64.
  * Replaces pyfelscore.mcy_esd_get_node_to_pset + esd_get_node_to_set
@@ -79,7 +80,7 @@ int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t
  * specs _mcy.py:397-470 and _mc0.py:89-138) and the shared-pattern variants
  * mcy_get_node_to_pset / get_node_to_set (_mcy.py:158-174).
  */
-int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride, int passes,
                     const int32_t* parent, const double* P, uint64_t* mask, void* stream);
 
 /*
@@ -127,6 +128,23 @@ int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
                        int obs_kind, const void* obs,
                        const double* partials, const int8_t* status,
                        double* node_distn, double* W, double* root_post_sum, void* stream);
+
+/*
+ * Materialised per-edge joints and all-node marginals for small batches
+ * (n_sites <= 65535):  J[b][site][a][c] = D[parent(b)][a] * norm(P_b[a,:] L_b)[c],
+ * D_all[b][site][c] = sum_a J[b][site][a][c].  edges: all rows of the downward
+ * program; partials / node_distn as produced by rt_prune_loglik /
+ * rt_posterior_stats.  J: [n_nodes][n_sites][S][S], D_all: [n_nodes][n_sites][S]
+ * (rows of the root are not written).
+ * Replaces pyfelscore.mc0_esd_get_joint_endpoint_distn (raoteh/sampler/
+ * _mcy_dense.py:205; spec _mc0_dense.py:217-270) where the caller wants J itself
+ * (_mc0_dense.get_joint_endpoint_distn, _mcy_dense.kitchen_sink :57).
+ */
+int rt_joint_distn(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                   const int32_t* edges, int n_edges, const double* P,
+                   int obs_kind, const void* obs, const double* partials,
+                   const double* node_distn, const int8_t* status,
+                   double* J, double* D_all, void* stream);
 
 /*
  * Rao-Teh uniformization sweeps for n_traj independent trajectories

@@ -188,8 +188,84 @@ def gen_jukes_cantor():
     print('jukes_cantor: %d rows' % len(rows))
 
 
+def gen_sparse():
+    """Sparse (networkx / dict) API: _mjp, _mcy, _mc0, _mcz on random cases with
+    non-contiguous state labels."""
+    ref_shim.load_reference()
+    import networkx as nx
+    mjp = ref_shim.ref_module('_mjp')
+    mcy = ref_shim.ref_module('_mcy')
+    mc0 = ref_shim.ref_module('_mc0')
+    mcz = ref_shim.ref_module('_mcz')
+    util = ref_shim.ref_module('_util')
+    rng = np.random.default_rng(4321)
+    cases = []
+    for S, n, density in [(3, 4, 1.0), (4, 6, 0.6), (5, 7, 0.5), (4, 8, 1.0), (6, 6, 0.4)]:
+        for rep in range(4):
+            labels = [10 * (i + 1) + (i % 3) for i in range(S)]
+            T = random_tree(rng, n)
+            root = int(rng.integers(0, n))
+            Q = nx.DiGraph()
+            for i in range(S):
+                for j in range(S):
+                    if i != j and (rng.random() < density or j == (i + 1) % S):
+                        Q.add_edge(labels[i], labels[j], weight=float(rng.exponential(1.0)))
+            w = rng.dirichlet(np.ones(S))
+            distn = dict((labels[i], float(w[i])) for i in range(S) if rep % 2 == 0 or i != 0)
+            allowed = {}
+            deg = dict(T.degree())
+            for v in T:
+                r = rng.random()
+                if deg[v] == 1 and r < 0.7:
+                    allowed[v] = {labels[int(rng.integers(0, S))]}
+                elif r < 0.3:
+                    k = int(rng.integers(1, S + 1))
+                    allowed[v] = set(labels[int(x)] for x in rng.choice(S, size=k, replace=False))
+                else:
+                    allowed[v] = set(labels)
+            case = dict(tree=tree_to_json(T, root), labels=labels,
+                        Q=[[a, b, d['weight']] for a, b, d in Q.edges(data=True)],
+                        root_distn=dict((str(k), v) for k, v in distn.items()),
+                        allowed=allowed_to_json(allowed))
+            try:
+                case['likelihood'] = float(mjp.get_likelihood(T, allowed, root, root_distn=distn, Q_default=Q))
+                dwell, rootp, trans = mjp.get_expected_history_statistics(
+                    T, allowed, root, root_distn=distn, Q_default=Q)
+                case['dwell'] = dict((str(k), float(v)) for k, v in dwell.items())
+                case['root_post'] = dict((str(k), float(v)) for k, v in rootp.items())
+                case['trans'] = [[a, b, float(d['weight'])] for a, b, d in trans.edges(data=True)]
+                T_aug = mjp.get_expm_augmented_tree(T, root, Q_default=Q)
+                case['P'] = [[int(a), int(b), [[x, y, float(d['weight'])] for x, y, d in
+                                               T_aug[a][b]['P'].edges(data=True)]]
+                             for a, b in nx.bfs_edges(T, root)]
+                case['node_to_pset'] = dict((str(v), sorted(s)) for v, s in mcy.get_node_to_pset(
+                    T_aug, root, node_to_allowed_states=allowed).items())
+                case['node_to_set'] = dict((str(v), sorted(s)) for v, s in mcy.get_node_to_set(
+                    T_aug, root, node_to_allowed_states=allowed).items())
+                pmap = mcy.get_node_to_pmap(T_aug, root, node_to_allowed_states=allowed)
+                case['pmap'] = dict((str(v), dict((str(k), float(x)) for k, x in d.items()))
+                                    for v, d in pmap.items())
+                nd = mc0.get_node_to_distn(T_aug, root, pmap, root_distn=distn)
+                case['node_distn'] = dict((str(v), dict((str(k), float(x)) for k, x in d.items()))
+                                          for v, d in nd.items())
+                # z-type emissions on the same tree
+                emis = dict((v, dict((s, float(rng.random() + 0.05)) for s in allowed[v])) for v in T)
+                zp = mcz.get_node_to_pmap(T_aug, root, node_to_state_to_likelihood=emis)
+                case['emissions'] = dict((str(v), dict((str(k), x) for k, x in d.items()))
+                                         for v, d in emis.items())
+                case['z_pmap'] = dict((str(v), dict((str(k), float(x)) for k, x in d.items()))
+                                      for v, d in zp.items())
+            except util.ZeroProbError as e:
+                case['raises'] = type(e).__name__
+            cases.append(case)
+    with open(os.path.join(OUT, 'mjp_sparse.json'), 'w') as f:
+        json.dump(dict(source='oracle/gen_golden.py gen_sparse, seed 4321', cases=cases), f)
+    print('mjp_sparse: %d cases (%d raise)' % (len(cases), sum('raises' in c for c in cases)))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    gen_sparse()
     gen_code2x3()
     gen_mjp_random()
     gen_jukes_cantor()

@@ -36,7 +36,9 @@ static int unsupported(const char* msg) {
 int rt_expm_batched_impl(const double*, const int32_t*, const double*, int, int, double*, cudaStream_t);
 int rt_frechet_contract_impl(const double*, const int32_t*, const double*, const double*, int, int,
                              double*, cudaStream_t);
-int rt_support_sets_impl(int, int, int64_t, int64_t, const int32_t*, const double*, uint64_t*, cudaStream_t);
+int rt_support_sets_impl(int, int, int64_t, int64_t, int, const int32_t*, const double*, uint64_t*, cudaStream_t);
+int rt_joint_distn_impl(int, int, int64_t, int64_t, const int32_t*, int, const double*, const void*,
+                        const double*, const double*, const int8_t*, double*, double*, cudaStream_t);
 int rt_prune_small_dispatch(int, int, bool, int64_t, int64_t, const int32_t*, int, int, int,
                             const double*, const double*, const void*, double*, int32_t*, double*,
                             int8_t*, double*, cudaStream_t);
@@ -76,12 +78,26 @@ int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t
   return rt_frechet_contract_impl(Q, q_index, t, W, n_mat, S, M, (cudaStream_t)stream);
 }
 
-int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride, const int32_t* parent,
-                    const double* P, uint64_t* mask, void* stream) {
+int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride, int passes,
+                    const int32_t* parent, const double* P, uint64_t* mask, void* stream) {
   if (!parent || !P || !mask) return arg_error("null pointer");
   if (site_stride < n_sites) return arg_error("site_stride < n_sites");
+  if (passes < 1 || passes > 3) return arg_error("passes must be 1 (backward), 2 (forward) or 3");
   ensure_pool_cached();
-  return rt_support_sets_impl(S, n_nodes, n_sites, site_stride, parent, P, mask, (cudaStream_t)stream);
+  return rt_support_sets_impl(S, n_nodes, n_sites, site_stride, passes, parent, P, mask,
+                              (cudaStream_t)stream);
+}
+
+int rt_joint_distn(int S, int n_nodes, int64_t n_sites, int64_t site_stride, const int32_t* edges,
+                   int n_edges, const double* P, int obs_kind, const void* obs,
+                   const double* partials, const double* node_distn, const int8_t* status,
+                   double* J, double* D_all, void* stream) {
+  if (!edges || !P || !partials || !node_distn || !status || !J || !D_all)
+    return arg_error("null pointer");
+  if (obs_kind < 0 || obs_kind > 2) return arg_error("obs_kind");
+  (void)n_nodes;
+  return rt_joint_distn_impl(S, obs_kind, n_sites, site_stride, edges, n_edges, P, obs, partials,
+                             node_distn, status, J, D_all, (cudaStream_t)stream);
 }
 
 int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,

@@ -423,7 +423,11 @@ int rt_raoteh_dispatch(int S, int obs_kind, int n_nodes, int64_t n_traj, int64_t
                        int8_t* status, cudaStream_t stream) {
   SweepArgs A;
   A.n_nodes = n_nodes; A.n_ops = n_ops; A.n_slots = n_slots; A.cap = cap;
-  A.scr_cap = cap;   // kept jumps <= scratch entries <= cap: the jump list can never overflow
+  // sweeps: kept jumps <= scratch entries <= cap, so the jump list cannot overflow.
+  // init mode: init_k events on every edge are candidates (status 4 if more than
+  // `cap` of them turn out to be real jumps).
+  A.scr_cap = cap;
+  if (init_k > 0 && (n_nodes - 1) * init_k > cap) A.scr_cap = (n_nodes - 1) * init_k;
   A.n_traj = n_traj; A.stride = stride; A.n_sites = n_sites; A.obs_stride = obs_stride; A.traj0 = traj0;
   A.program = reinterpret_cast<const int4*>(program);
   A.parent = parent; A.length = length; A.B = B; A.rate = rate; A.root_distn = root_distn;

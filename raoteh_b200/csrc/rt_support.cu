@@ -21,14 +21,14 @@ __global__ void pack_pattern_kernel(const double* __restrict__ P, int S, int n_n
 }
 
 __global__ void __launch_bounds__(128)
-support_kernel(int S, int n_nodes, int64_t n_sites, int64_t stride,
+support_kernel(int S, int n_nodes, int64_t n_sites, int64_t stride, int passes,
                const int32_t* __restrict__ parent,
                const unsigned long long* __restrict__ rowbits,
                unsigned long long* __restrict__ mask) {
   const int64_t site = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (site >= n_sites) return;
   // backward: state s of a kept iff every child b has some kept s' with P_b[s,s'] > 0
-  for (int b = n_nodes - 1; b >= 1; --b) {
+  for (int b = n_nodes - 1; b >= 1 && (passes & 1); --b) {
     const int a = parent[b];
     const unsigned long long Mb = mask[(int64_t)b * stride + site];
     unsigned long long keep = 0ull;
@@ -38,7 +38,7 @@ support_kernel(int S, int n_nodes, int64_t n_sites, int64_t stride,
     mask[(int64_t)a * stride + site] &= keep;
   }
   // forward: state s' of b kept iff reachable from a kept state of its parent
-  for (int b = 1; b < n_nodes; ++b) {
+  for (int b = 1; b < n_nodes && (passes & 2); ++b) {
     const int a = parent[b];
     unsigned long long Ma = mask[(int64_t)a * stride + site];
     unsigned long long reach = 0ull;
@@ -54,7 +54,7 @@ support_kernel(int S, int n_nodes, int64_t n_sites, int64_t stride,
 
 }  // namespace
 
-int rt_support_sets_impl(int S, int n_nodes, int64_t n_sites, int64_t stride, const int32_t* parent,
+int rt_support_sets_impl(int S, int n_nodes, int64_t n_sites, int64_t stride, int passes, const int32_t* parent,
                          const double* P, uint64_t* mask, cudaStream_t stream) {
   if (S < 1 || S > 64) return RT_ERR_UNSUPPORTED;
   if (n_nodes <= 0 || n_sites <= 0) return RT_OK;
@@ -63,7 +63,7 @@ int rt_support_sets_impl(int S, int n_nodes, int64_t n_sites, int64_t stride, co
   const int tot = n_nodes * S;
   pack_pattern_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(P, S, n_nodes, rowbits);
   support_kernel<<<(unsigned)((n_sites + 127) / 128), 128, 0, stream>>>(
-      S, n_nodes, n_sites, stride, parent, rowbits,
+      S, n_nodes, n_sites, stride, passes, parent, rowbits,
       reinterpret_cast<unsigned long long*>(mask));
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(rowbits, stream);

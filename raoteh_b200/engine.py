@@ -172,11 +172,12 @@ class TreeMJP(object):
         return hit
 
     # ---- A4 ---------------------------------------------------------------
-    def support_sets(self, mask):
-        """In-place structural-support pruning of int64 bitmasks [n_nodes, stride]."""
+    def support_sets(self, mask, passes=3):
+        """In-place structural-support pruning of int64 bitmasks [n_nodes, stride];
+        passes=1 backward only ("pset"), 3 backward + forward ("set")."""
         P = self.transition_matrices()
         n_sites = mask.shape[1]
-        rc = _native.lib().rt_support_sets(self.S, self.sched.n, n_sites, mask.shape[1],
+        rc = _native.lib().rt_support_sets(self.S, self.sched.n, n_sites, mask.shape[1], passes,
                                            _ptr(self.parent), _ptr(P), _ptr(mask), _stream())
         _native.check(rc, 'rt_support_sets')
         return mask
@@ -234,6 +235,42 @@ class TreeMJP(object):
         self._mark('down')
         up.update(node_distn=node_distn, W=W, root_post_sum=root_post_sum, n_levels=len(lp) - 1)
         return up
+
+    def posterior_given_partials(self, obs, partials, status=None):
+        """Downward pass for caller-supplied partials of the internal nodes
+        ([n_store, S, stride]; leaves come from `obs`): the batched form of
+        _mc0_dense.get_node_to_distn (raoteh/sampler/_mc0_dense.py:400), whose input
+        is a node_to_pmap rather than observations."""
+        prog = self._programs(obs)
+        N, stride = obs.n_sites, obs.stride
+        if status is None:
+            status = torch.zeros(N, dtype=torch.int8, device=self.device)
+        node_distn = self._buf('node_distn', (self.sched.n_store, self.S, stride), torch.float64)
+        W = self._buf('W', (self.sched.n, self.S, self.S), torch.float64, zero=True)
+        root_post_sum = self._buf('root_post_sum', (self.S,), torch.float64, zero=True)
+        lp = prog['level_ptr']
+        rc = _native.lib().rt_posterior_stats(
+            self.S, self.sched.n, N, stride, _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
+            _ptr(self.transition_matrices()), _ptr(self.root_distn), obs.kind, _ptr(obs.data),
+            _ptr(partials), _ptr(status), _ptr(node_distn), _ptr(W), _ptr(root_post_sum), _stream())
+        _native.check(rc, 'rt_posterior_stats')
+        return dict(partials=partials, status=status, node_distn=node_distn, W=W,
+                    root_post_sum=root_post_sum)
+
+    def joint_distn(self, obs, post):
+        """Materialised joints J[n, N, S, S] and marginals of every node D[n, N, S]
+        (row 0 of D = root posterior) from the result of `posterior`."""
+        prog = self._programs(obs)
+        n, S, N = self.sched.n, self.S, obs.n_sites
+        J = torch.zeros((n, N, S, S), dtype=torch.float64, device=self.device)
+        D = torch.zeros((n, N, S), dtype=torch.float64, device=self.device)
+        rc = _native.lib().rt_joint_distn(
+            S, n, N, obs.stride, _ptr(prog['edges']), n - 1, _ptr(self.transition_matrices()),
+            obs.kind, _ptr(obs.data), _ptr(post['partials']), _ptr(post['node_distn']),
+            _ptr(post['status']), _ptr(J), _ptr(D), _stream())
+        _native.check(rc, 'rt_joint_distn')
+        D[0] = post['node_distn'][0, :, :N].T
+        return J, D
 
     def frechet_contract(self, W):
         """M[b] = L(t_b Q_b^T, t_b W[b]) for every node b (slot 0 -> 0)."""

@@ -104,6 +104,7 @@ class RaoTehChains(object):
             k += 2 ** j
             j += 1
         self.status[self.status == DONE] = 0
+        self.check()
         self.sweeps_done = 1      # sweep index 0 was the initial history
         self.initialized = True
         return k
@@ -118,6 +119,8 @@ class RaoTehChains(object):
 
     def check(self):
         bad = int((self.status != 0).sum())
+        if bad and int((self.status == 4).sum()):
+            raise _native.NativeError('initial history has more than cap=%d real jumps' % self.cap)
         if bad:
             raise _native.NativeError(
                 '%d trajectories exceeded the event capacity cap=%d in one sweep '

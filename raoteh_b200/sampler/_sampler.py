@@ -1,0 +1,137 @@
+"""
+Rao-Teh history generators with the reference's signatures
+(raoteh/sampler/_sampler.py:238-390).  Each generator owns one device-resident
+trajectory (a batch of one chain x one site of raoteh_b200.raoteh.RaoTehChains);
+every `next()` runs one sweep of the CUDA kernel and converts the trajectory to
+the reference's output type: an undirected nx.Graph whose edges carry `weight`
+(segment length) and `state`, original node ids preserved, new degree-2 node ids
+> max(T), total weight preserved.
+
+Randomness comes from the counter-based Philox generator of the kernel, seeded
+from numpy's global RNG at generator creation (the reference draws from the
+global `np.random` / `random` state and is never seeded by the library).
+"""
+from __future__ import division, print_function, absolute_import
+
+import itertools
+
+import networkx as nx
+import numpy as np
+
+from . import _mjp, _sparse
+from ._util import get_first_element
+from .. import engine
+from ..lowering import TreeSchedule
+from ..raoteh import RaoTehChains
+
+__all__ = []
+
+
+def _trajectory_to_graph(sched, states, ns, edges, next_node):
+    T_out = nx.Graph()
+    for i in range(1, sched.n):
+        a, b = sched.nodes[sched.parent[i]], sched.nodes[i]
+        times, seg_states = edges[i]
+        prev_node, prev_t = a, 0.0
+        for j, tau in enumerate(times):
+            mid = next_node
+            next_node += 1
+            T_out.add_edge(prev_node, mid, weight=float(tau - prev_t), state=states[seg_states[j]])
+            prev_node, prev_t = mid, float(tau)
+        T_out.add_edge(prev_node, b, weight=float(sched.length[i] - prev_t),
+                       state=states[seg_states[-1]])
+    return T_out
+
+
+def gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=None,
+                             uniformization_factor=2, nhistories=None, seed=None, cap=None):
+    """raoteh/sampler/_sampler.py:300-390 (generator of nx.Graph histories)."""
+    bad = set(node_to_allowed_states) - set(T)
+    if bad:
+        raise ValueError('some of the nodes which have been annotated with state restrictions '
+                         'are not even in the tree: ' + str(sorted(bad)))
+    if uniformization_factor <= 1:
+        raise ValueError('the uniformization factor must be greater than 1')
+    if not Q:
+        raise ValueError('the rate matrix is empty')
+    for a, b in Q.edges():
+        if a == b:
+            raise ValueError('the rate matrix should have no loops')
+    if root not in T:
+        raise ValueError('the root must be a node in the tree')
+    states = sorted(set(Q) | (set(root_distn) if root_distn is not None else set()))
+    index = dict((s, i) for i, s in enumerate(states))
+    S = len(states)
+    Qd = _sparse.dense_matrix(Q, states, index)
+    Qd -= np.diag(Qd.sum(axis=1))
+    sched = TreeSchedule.from_nx(T, root)
+    full = (1 << S) - 1
+    mask = np.full((sched.n, 1), full, dtype=np.uint64)
+    for v, allowed in node_to_allowed_states.items():
+        m = 0
+        for s in allowed:
+            if s in index:
+                m |= 1 << index[s]
+        mask[sched.node_index[v], 0] = m
+    prior = None
+    if root_distn is not None:
+        prior = np.array([root_distn.get(s, 0.0) for s in states], dtype=float)
+    obs = engine.Observations.from_masks(sched, mask)
+    if seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+    if cap is None:
+        omega = uniformization_factor * np.max(-np.diag(Qd))
+        mean = omega * sched.length.sum()
+        cap = int(max(256, (sched.n - 1) * (S + 1), 4 * mean + 64))
+    chain = RaoTehChains(sched, Qd, obs, n_chains=1, root_distn=prior,
+                         uniformization_factor=uniformization_factor, cap=cap, seed=seed)
+    try:
+        chain.initialize()
+    except RuntimeError:
+        raise Exception('failed to find a feasible history')
+    next_node = max(T) + 1
+    for i in itertools.count():
+        ns, edges = chain.trajectory(0)
+        yield _trajectory_to_graph(sched, states, ns, edges, next_node)
+        if nhistories is not None and i + 1 >= nhistories:
+            return
+        chain.sweep(1, stats=False)
+        chain.check()
+
+
+def gen_histories(T, Q, node_to_state, root=None, root_distn=None, uniformization_factor=2,
+                  nhistories=None, seed=None):
+    """raoteh/sampler/_sampler.py:238-297"""
+    if root is None:
+        root = get_first_element(node_to_state) if node_to_state else get_first_element(T)
+    all_states = set(Q)
+    if root_distn is not None:
+        all_states.update(set(root_distn))
+    node_to_allowed_states = {}
+    for node in T:
+        if node in node_to_state:
+            node_to_allowed_states[node] = {node_to_state[node]}
+        else:
+            node_to_allowed_states[node] = all_states
+    for history in gen_restricted_histories(T, Q, node_to_allowed_states, root,
+                                            root_distn=root_distn,
+                                            uniformization_factor=uniformization_factor,
+                                            nhistories=nhistories, seed=seed):
+        yield history
+
+
+def get_restricted_feasible_history(T, P, node_to_allowed_states, root, root_distn=None):
+    """raoteh/sampler/_sampler.py:563-643: an arbitrary feasible history under the
+    uniformized matrix P (weighted DiGraph with self-loops); the law is not meaningful."""
+    states = sorted(P)
+    index = dict((s, i) for i, s in enumerate(states))
+    B = _sparse.dense_matrix(P, states, index)
+    Q = nx.DiGraph()
+    for a, b in P.edges():
+        if a != b and P[a][b]['weight'] > 0:
+            Q.add_edge(a, b, weight=P[a][b]['weight'])
+    if not Q:
+        raise Exception('failed to find a feasible history')
+    gen = gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=root_distn,
+                                   nhistories=1)
+    return next(gen)

@@ -1,0 +1,280 @@
+"""The reference-shaped API (raoteh_b200.sampler) against golden fixtures produced
+by the unmodified reference, plus ports of the reference's own tests
+(raoteh/sampler/tests/test_mjp.py, test_sampler.py:398-438)."""
+from itertools import product
+
+import networkx as nx
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_equal
+
+from helpers import load_golden, case_tree, case_allowed
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def S():
+    from raoteh_b200 import sampler  # noqa: F401
+    from raoteh_b200.sampler import (_util, _density, _mjp, _mjp_dense, _mcy, _mcy_dense, _mcz,
+                                      _mc0, _mc0_dense, _sampler, _sample_mjp,
+                                      _conditional_expectation)
+
+    class NS(object):
+        pass
+    ns = NS()
+    for m in (_util, _density, _mjp, _mjp_dense, _mcy, _mcy_dense, _mcz, _mc0, _mc0_dense,
+              _sampler, _sample_mjp, _conditional_expectation):
+        setattr(ns, m.__name__.split('.')[-1], m)
+    return ns
+
+
+def test_dense_api_matches_reference_fixtures(S):
+    g = load_golden('mjp_random.json')
+    for case in g['cases']:
+        T, root = case_tree(case)
+        allowed = case_allowed(case)
+        n = case['nstates']
+        Q = np.array(case['Q'])
+        pi = np.array(case['root_distn'])
+        if 'raises' in case:
+            with pytest.raises(getattr(S._util, case['raises'])):
+                S._mjp_dense.get_likelihood(T, allowed, root, n, root_distn=pi, Q_default=Q)
+            continue
+        lk = S._mjp_dense.get_likelihood(T, allowed, root, n, root_distn=pi, Q_default=Q)
+        assert_allclose(lk, case['likelihood'], rtol=1e-10)
+        dwell, rootp, trans = S._mjp_dense.get_expected_history_statistics(
+            T, allowed, root, n, root_distn=pi, Q_default=Q)
+        assert isinstance(dwell, dict) and isinstance(trans, nx.DiGraph)
+        assert_allclose([dwell.get(s, 0.0) for s in range(n)], case['dwell'], rtol=1e-9, atol=1e-12)
+        assert_allclose(rootp, case['root_post'], rtol=1e-10, atol=1e-14)
+        tr = np.zeros((n, n))
+        for a, b, d in trans.edges(data=True):
+            tr[a, b] = d['weight']
+        assert_allclose(tr, np.array(case['trans']), rtol=1e-9, atol=1e-12)
+        T_aug = S._mjp_dense.get_expm_augmented_tree(T, root, Q_default=Q)
+        for a, b, P in case['P']:
+            assert_allclose(T_aug[a][b]['P'], np.array(P), rtol=0, atol=1e-13)
+        pmap = S._mcy_dense.get_node_to_pmap(T_aug, root, n, node_to_allowed_states=allowed)
+        for v, p in case['pmap'].items():
+            assert_allclose(pmap[int(v)], p, rtol=1e-10, atol=1e-300)
+        distn = S._mc0_dense.get_node_to_distn(T_aug, root, pmap, n, root_distn=pi)
+        for v, d in case['node_distn'].items():
+            assert_allclose(distn[int(v)], d, rtol=1e-10, atol=1e-14)
+        TJ = S._mc0_dense.get_joint_endpoint_distn(T_aug, root, pmap, distn, n)
+        for a, b, J in case['joint']:
+            assert_allclose(TJ[a][b]['J'], np.array(J), rtol=1e-10, atol=1e-14)
+        pm2, dn2, ej2 = S._mcy_dense.kitchen_sink(T_aug, root, n, node_to_allowed_states=allowed,
+                                                  root_distn=pi)
+        for a, b, J in case['joint']:
+            assert_allclose(ej2[(a, b)], np.array(J), rtol=1e-10, atol=1e-14)
+
+
+def test_sparse_api_matches_reference_fixtures(S):
+    g = load_golden('mjp_sparse.json')
+    for case in g['cases']:
+        T, root = case_tree(case)
+        Q = nx.DiGraph()
+        for a, b, w in case['Q']:
+            Q.add_edge(a, b, weight=w)
+        distn = dict((int(k), v) for k, v in case['root_distn'].items())
+        allowed = case_allowed(case)
+        if 'raises' in case:
+            with pytest.raises(getattr(S._util, case['raises'])):
+                S._mjp.get_likelihood(T, allowed, root, root_distn=distn, Q_default=Q)
+            continue
+        lk = S._mjp.get_likelihood(T, allowed, root, root_distn=distn, Q_default=Q)
+        assert_allclose(lk, case['likelihood'], rtol=1e-10)
+        dwell, rootp, trans = S._mjp.get_expected_history_statistics(
+            T, allowed, root, root_distn=distn, Q_default=Q)
+        for k, v in case['dwell'].items():
+            assert_allclose(dwell[int(k)], v, rtol=1e-9, atol=1e-12)
+        assert_equal(set(rootp), set(int(k) for k in case['root_post']))
+        for k, v in case['root_post'].items():
+            assert_allclose(rootp[int(k)], v, rtol=1e-10)
+        assert_equal(set(trans.edges()), set((a, b) for a, b, w in case['trans']))
+        for a, b, w in case['trans']:
+            assert_allclose(trans[a][b]['weight'], w, rtol=1e-9, atol=1e-12)
+        T_aug = S._mjp.get_expm_augmented_tree(T, root, Q_default=Q)
+        for a, b, entries in case['P']:
+            P = T_aug[a][b]['P']
+            assert_equal(set(P.edges()), set((x, y) for x, y, w in entries))
+            for x, y, w in entries:
+                assert_allclose(P[x][y]['weight'], w, rtol=0, atol=1e-13)
+        pset = S._mcy.get_node_to_pset(T_aug, root, node_to_allowed_states=allowed)
+        nset = S._mcy.get_node_to_set(T_aug, root, node_to_allowed_states=allowed)
+        for v, s in case['node_to_pset'].items():
+            assert_equal(pset[int(v)], set(s))
+        for v, s in case['node_to_set'].items():
+            assert_equal(nset[int(v)], set(s))
+        pmap = S._mcy.get_node_to_pmap(T_aug, root, node_to_allowed_states=allowed)
+        for v, d in case['pmap'].items():
+            assert_equal(set(pmap[int(v)]), set(int(k) for k in d))
+            for k, x in d.items():
+                assert_allclose(pmap[int(v)][int(k)], x, rtol=1e-10)
+        nd = S._mc0.get_node_to_distn(T_aug, root, pmap, root_distn=distn)
+        for v, d in case['node_distn'].items():
+            for k, x in d.items():
+                assert_allclose(nd[int(v)].get(int(k), 0.0), x, rtol=1e-10, atol=1e-14)
+        emis = dict((int(v), dict((int(k), x) for k, x in d.items()))
+                    for v, d in case['emissions'].items())
+        zp = S._mcz.get_node_to_pmap(T_aug, root, node_to_state_to_likelihood=emis)
+        for v, d in case['z_pmap'].items():
+            for k, x in d.items():
+                assert_allclose(zp[int(v)][int(k)], x, rtol=1e-10)
+
+
+def test_get_total_rates(S):
+    # raoteh/sampler/tests/test_mjp.py:30-50
+    Q = nx.DiGraph()
+    Q.add_weighted_edges_from([(0, 1, 1), (1, 0, 1), (1, 2, 1), (2, 1, 1)])
+    assert_equal(S._mjp.get_total_rates(Q), {0: 1, 1: 2, 2: 1})
+    Q_dense = S._density.rate_matrix_to_numpy_array(Q, nodelist=range(3))
+    assert_allclose(S._mjp_dense.get_total_rates(Q_dense), [1, 2, 1])
+
+
+def test_likelihoods_sum_to_one(S):
+    # raoteh/sampler/tests/test_mjp.py:52-89
+    rng = np.random.RandomState(0)
+    T = nx.Graph()
+    T.add_weighted_edges_from([(0, 1, 2.0), (0, 2, 3.0), (0, 3, 4.0)])
+    nnodes, root, nstates = len(T), 0, 3
+    distn = S._util.get_normalized_dict_distn(dict((i, rng.exponential()) for i in range(3)))
+    Q = nx.DiGraph()
+    for i in range(nstates):
+        for j in range(nstates):
+            if i != j:
+                Q.add_edge(i, j, weight=rng.exponential())
+    distn_dense = S._density.dict_to_numpy_array(distn, nodelist=range(nstates))
+    Q_dense = S._density.rate_matrix_to_numpy_array(Q, nodelist=range(nstates))
+    total = 0
+    for assignment in product(range(nstates), repeat=nnodes):
+        allowed = dict((n, {s}) for n, s in zip(range(nnodes), assignment))
+        lk = S._mjp.get_likelihood(T, allowed, root, root_distn=distn, Q_default=Q)
+        lk_dense = S._mjp_dense.get_likelihood(T, allowed, root, nstates,
+                                               root_distn=distn_dense, Q_default=Q_dense)
+        assert_allclose(lk, lk_dense)
+        total += lk
+    assert_allclose(total, 1)
+
+
+def test_get_likelihood_root_invariance_and_marginalisation(S):
+    # raoteh/sampler/tests/test_mjp.py:91-164
+    T = nx.Graph()
+    T.add_weighted_edges_from([(0, 1, 2.0), (0, 2, 3.0), (0, 3, 4.0), (1, 4, 5.0), (1, 5, 6.0)])
+    nstates = 4
+    distn = {0: 0.1, 1: 0.2, 2: 0.3, 3: 0.4}
+    Q = nx.DiGraph()
+    Q.add_weighted_edges_from([
+        (0, 1, 1.0 * distn[1]), (1, 0, 1.0 * distn[0]), (1, 2, 2.0 * distn[2]),
+        (2, 1, 2.0 * distn[1]), (2, 3, 1.0 * distn[3]), (3, 2, 1.0 * distn[2]),
+        (3, 0, 2.0 * distn[0]), (0, 3, 2.0 * distn[3])])
+    allowed = {0: set(range(4)), 1: set(range(4)), 2: {0}, 3: {1}, 4: {2}, 5: {3}}
+    distn_dense = S._density.dict_to_numpy_array(distn, nodelist=range(nstates))
+    Q_dense = S._density.rate_matrix_to_numpy_array(Q, nodelist=range(nstates))
+    lks = []
+    for root in range(6):
+        lk = S._mjp.get_likelihood(T, allowed, root, root_distn=distn, Q_default=Q)
+        lk_dense = S._mjp_dense.get_likelihood(T, allowed, root, nstates,
+                                               root_distn=distn_dense, Q_default=Q_dense)
+        assert_allclose(lk, lk_dense)
+        lks.append(lk)
+    assert_allclose(lks, lks[0])     # reversible Q with its stationary prior: root-invariant
+    lk_m = 0
+    for s0 in range(4):
+        for s1 in range(4):
+            nodemap = dict(allowed)
+            nodemap[0] = {s0}
+            nodemap[1] = {s1}
+            lk_m += S._mjp.get_likelihood(T, nodemap, 3, root_distn=distn, Q_default=Q)
+    assert_allclose(lks[0], lk_m)
+
+
+def test_jukes_cantor_conditional_expectation(S):
+    # raoteh/sampler/tests/test_mjp.py:166-240 (3 of the 16 end-state pairs, all roots)
+    ce = S._conditional_expectation
+    t = 0.5
+    T = nx.Graph()
+    for i, w in enumerate([0.1, 0.2, 0.3, 0.4]):
+        T.add_edge(i, i + 1, weight=w * t)
+    nstates = 4
+    for a, b in ((0, 0), (0, 1), (2, 3)):
+        allowed = {0: {a}, 1: set(range(4)), 2: set(range(4)), 3: set(range(4)), 4: {b}}
+        Q = ce.get_jukes_cantor_rate_matrix(nstates)
+        expected = [ce.get_jukes_cantor_interaction(a, b, i, i, t, nstates) /
+                    ce.get_jukes_cantor_probability(a, b, t, nstates) for i in range(nstates)]
+        Q_dense = S._density.rate_matrix_to_numpy_array(Q, nodelist=range(nstates))
+        for root in T:
+            dwell, init, trans = S._mjp.get_expected_history_statistics(T, allowed, root, Q_default=Q)
+            assert_allclose([dwell[i] for i in range(nstates)], expected)
+            dwell, init, trans = S._mjp_dense.get_expected_history_statistics(
+                T, allowed, root, nstates, Q_default=Q_dense)
+            assert_allclose([dwell[i] for i in range(nstates)], expected)
+
+
+def test_code2x3_through_the_dense_api(S):
+    """examples/code2x3/run.py main(): every likelihood and per-branch expectation."""
+    g = load_golden('code2x3.json')
+    for call in g['calls'][:14]:
+        T, root = case_tree(call)
+        allowed = case_allowed(call)
+        n = call['nstates']
+        Q, pi = np.array(call['Q']), np.array(call['root_distn'])
+        if call['kind'] == 'likelihood':
+            lk = S._mjp_dense.get_likelihood(T, allowed, root, n, root_distn=pi, Q_default=Q)
+            assert_allclose(lk, call['out'], rtol=1e-10)
+        else:
+            E = None if call['E'] is None else np.array(call['E'])
+            out = S._mjp_dense.get_expected_ntransitions(T, allowed, root, n, root_distn=pi,
+                                                         Q_default=Q, E=E)
+            for a, b, v in call['out']:
+                assert_allclose(out[a, b], v, rtol=1e-9, atol=1e-12)
+
+
+def test_gen_histories_invariants(S):
+    # raoteh/sampler/tests/test_sampler.py:398-438
+    T = nx.Graph()
+    T.add_weighted_edges_from([(0, 12, 1.0), (0, 23, 2.0), (0, 33, 1.0), (23, 4, 0.5), (23, 5, 1.5)])
+    Q = nx.DiGraph()
+    Q.add_weighted_edges_from([(0, 1, 4), (0, 2, 2), (1, 0, 1), (1, 2, 2), (2, 1, 1), (2, 0, 2)])
+    node_to_state = {12: 1, 33: 2, 4: 0, 5: 1}
+    root_distn = {0: 0.25, 1: 0.5, 2: 0.25}
+    total = T.size(weight='weight')
+    n = 0
+    for T_aug in S._sampler.gen_histories(T, Q, node_to_state, root=0, root_distn=root_distn,
+                                          nhistories=12, seed=5):
+        n += 1
+        assert_allclose(T_aug.size(weight='weight'), total, rtol=1e-6)   # float32 event times
+        for node, state in node_to_state.items():
+            for nb in T_aug[node]:
+                assert_equal(T_aug[node][nb]['state'], state)
+        for node in T:
+            assert len(set(T_aug[node][nb]['state'] for nb in T_aug[node])) == 1
+        for node in set(T_aug) - set(T):
+            assert node > max(T) and T_aug.degree(node) == 2
+            s = [T_aug[node][nb]['state'] for nb in T_aug[node]]
+            assert s[0] != s[1]
+        dwell, root_state, trans = S._mjp.get_history_statistics(T_aug, root=0)
+        assert_allclose(sum(dwell.values()), total, rtol=1e-6)
+    assert n == 12
+
+
+def test_gen_restricted_histories_input_validation(S):
+    # raoteh/sampler/_sampler.py:329-343
+    T = nx.Graph()
+    T.add_edge(0, 1, weight=1.0)
+    Q = nx.DiGraph()
+    Q.add_weighted_edges_from([(0, 1, 1.0), (1, 0, 1.0)])
+    ok = {0: {0}, 1: {1}}
+    with pytest.raises(ValueError):
+        next(S._sampler.gen_restricted_histories(T, Q, ok, 0, uniformization_factor=1))
+    with pytest.raises(ValueError):
+        next(S._sampler.gen_restricted_histories(T, nx.DiGraph(), ok, 0))
+    Ql = Q.copy()
+    Ql.add_edge(0, 0, weight=1.0)
+    with pytest.raises(ValueError):
+        next(S._sampler.gen_restricted_histories(T, Ql, ok, 0))
+    with pytest.raises(ValueError):
+        next(S._sampler.gen_restricted_histories(T, Q, {0: {0}, 7: {1}}, 0))
+    with pytest.raises(ValueError):
+        S._mjp_dense.get_likelihood(T, ok, 9, 2, Q_default=np.array([[-1., 1.], [1., -1.]]))
