@@ -217,11 +217,17 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from raoteh_b200 import engine
+    from raoteh_b200 import dist as rdist
     from raoteh_b200.lowering import TreeSchedule
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly ONE JSON line: library chatter (e.g. NCCL's version
+    # banner) is diverted to stderr while the benchmark runs
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
@@ -252,10 +258,8 @@ def run_gpu(args):
         mjp.events = sub if record else None
         mjp.set_rate_matrix(cfg['Q'])
         r = mjp.expected_history_statistics(obs)
-        stats = torch.cat([r['loglik'].sum().reshape(1), r['dwell'], r['trans'].reshape(-1),
-                           r['root_post_sum']])
-        if world > 1:
-            dist.all_reduce(stats)
+        stats = rdist.pack_stats(r['loglik'].sum(), r['dwell'], r['trans'], r['root_post_sum'])
+        rdist.allreduce_stats(stats)      # the path's only collective (NCCL, 1+S+S*S+S doubles)
         state['n_levels'] = r['n_levels']
         return r, stats
     sub = {}
@@ -372,7 +376,8 @@ def run_gpu(args):
                      d2h_bytes_per_step=int(out_ll.numel() * 8 + out_st.numel() + out_stats.numel() * 8)),
             gpu_launches=launches_per_step * args.steps,
             roofline=roofline, cpu_baseline=cpu_baseline, clocks=clocks, extra=extra)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -455,7 +460,7 @@ def bench_c3(dev, args):
     peak = fp64_peak()
     # expm alone
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    mjp._P = None
+    mjp._P_valid = False
     a.record()
     mjp.transition_matrices()
     b.record()

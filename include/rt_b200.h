@@ -113,6 +113,9 @@ int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
  * idx, child store idx or -1, child obs slot), sorted by depth of the child;
  * level_ptr_h: HOST int32 [n_levels+1], rows level_ptr_h[l]..level_ptr_h[l+1]
  * form level l (one launch per level: parents before children).
+ * program / n_ops / n_slots: the upward program (as for rt_prune_loglik); for
+ * S <= 8 the kernel walks it backwards per site (no level launches, marginals
+ * stay on chip) and node_distn may then be NULL when only statistics are wanted.
  * partials: from rt_prune_loglik; node_distn: [n_store][S][site_stride] out
  * (posterior marginals of the internal nodes); W: [n_nodes][S][S], += ;
  * root_post_sum (nullable): [S], += sum_sites D[root].
@@ -123,6 +126,7 @@ int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
  * _mc0_dense.py:217-270); the joint J is consumed on chip (never stored).
  */
 int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                       const int32_t* program, int n_ops, int n_slots,
                        const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
                        const double* P, const double* root_distn,
                        int obs_kind, const void* obs,

@@ -29,7 +29,8 @@ EXPORTS = {
     'rt_prune_loglik': ([c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p,
                          c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p], c_int),
-    'rt_posterior_stats': ([c_int, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p,
+    'rt_posterior_stats': ([c_int, c_int, c_int64, c_int64, c_void_p, c_int, c_int,
+                            c_void_p, c_void_p, c_int, c_void_p,
                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_void_p, c_void_p], c_int),
     'rt_raoteh_sweeps': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int,

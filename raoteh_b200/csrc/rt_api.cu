@@ -45,7 +45,8 @@ int rt_prune_small_dispatch(int, int, bool, int64_t, int64_t, const int32_t*, in
 int rt_prune_dmma_dispatch(int, int, bool, int64_t, int64_t, const int32_t*, int, int, int,
                            const double*, const double*, const void*, double*, int32_t*, double*,
                            int8_t*, double*, cudaStream_t);
-int rt_posterior_small_dispatch(int, int, int64_t, int64_t, const int32_t*, const int32_t*, int,
+int rt_posterior_small_dispatch(int, int, int64_t, int64_t, const int32_t*, int, int, int,
+                                const int32_t*, const int32_t*, int,
                                 const double*, const double*, const void*, const double*,
                                 const int8_t*, double*, double*, double*, cudaStream_t);
 int rt_posterior_dmma_dispatch(int, int, int64_t, int64_t, const int32_t*, const int32_t*, int,
@@ -128,20 +129,24 @@ int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
 }
 
 int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                       const int32_t* program, int n_ops, int n_slots,
                        const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
                        const double* P, const double* root_distn, int obs_kind, const void* obs,
                        const double* partials, const int8_t* status, double* node_distn, double* W,
                        double* root_post_sum, void* stream) {
-  if (!edges || !level_ptr_h || !P || !partials || !status || !node_distn || !W)
+  if (!edges || !level_ptr_h || !P || !partials || !status || !W)
     return arg_error("null pointer");
+  if (!node_distn && !(S >= 2 && S <= 8 && program))
+    return arg_error("node_distn may be NULL only for S <= 8 with the upward program given");
   if (obs_kind < 0 || obs_kind > 2) return arg_error("obs_kind");
   if (site_stride < n_sites) return arg_error("site_stride < n_sites");
   if (n_sites <= 0) return RT_OK;
   (void)n_nodes;
   if (S >= 2 && S <= 8)
-    return rt_posterior_small_dispatch(S, obs_kind, n_sites, site_stride, edges, level_ptr_h,
-                                       n_levels, P, root_distn, obs, partials, status, node_distn,
-                                       W, root_post_sum, (cudaStream_t)stream);
+    return rt_posterior_small_dispatch(S, obs_kind, n_sites, site_stride, program, n_ops, n_slots,
+                                       n_nodes, edges, level_ptr_h, n_levels, P, root_distn, obs,
+                                       partials, status, node_distn, W, root_post_sum,
+                                       (cudaStream_t)stream);
   if (S >= 1 && S <= 64)
     return rt_posterior_dmma_dispatch(S, obs_kind, n_sites, site_stride, edges, level_ptr_h,
                                       n_levels, P, root_distn, obs, partials, status, node_distn, W,

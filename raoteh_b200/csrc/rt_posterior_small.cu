@@ -184,11 +184,215 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fused downward WALK: one thread per site runs the whole downward pass by walking the
+// upward program backwards (same slot assignment, liveness reversed), with the current
+// node marginal in registers and parked marginals in a per-thread shared-memory stack.
+// Nothing but the stored partials is read from HBM and node marginals are written only on
+// request.  The per-edge weights W_b += G (x) L are reduced across the warp with a
+// transpose (reduce-scatter) butterfly -- V = S*S values over 32 lanes in
+// V/2 + V/4 + ... exchanges instead of V full reductions -- and then added to a per-CTA
+// accumulator in shared memory; one masked global atomicAdd per entry per CTA at the end.
+// ---------------------------------------------------------------------------------------
+constexpr int kWalkBlock = 128;
+
+template <int V>
+__device__ __forceinline__ void reduce_scatter_warp(double (&v)[V], int lane) {
+  // after the call: V==16 -> lane holds value (lane>>1) in v[0]; V==32 -> value `lane`;
+  // V==64 -> values 2*lane, 2*lane+1 in v[0], v[1]   (all fully summed over the warp)
+  int len = V;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    if (len > 1) {
+      const bool up = (lane & m) != 0;
+      const int half = len / 2;
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        if (i < half) {
+          const double send = up ? v[i] : v[i + half];
+          const double keep = up ? v[i + half] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      len = half;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], m);
+    }
+  }
+}
+
+template <int S> struct WalkV { static constexpr int value = (S <= 4) ? 16 : (S == 5 ? 32 : 64); };
+
+template <int S, int OBS>
+__global__ void __launch_bounds__(kWalkBlock)
+down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ program, int n_ops,
+                 int n_slots, int n_nodes, const double* __restrict__ P,
+                 const double* __restrict__ root_distn, const void* __restrict__ obs,
+                 const double* __restrict__ partials, const int8_t* __restrict__ status,
+                 double* __restrict__ node_distn, double* __restrict__ W,
+                 double* __restrict__ root_post_sum) {
+  constexpr int V = WalkV<S>::value;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int4* prog_s = reinterpret_cast<int4*>(smem_raw);
+  double* pi_s = reinterpret_cast<double*>(prog_s + n_ops);
+  double* P_s = pi_s + S;                              // [n_nodes][S][S]
+  double* W_s = P_s + (size_t)n_nodes * S * S;         // [n_nodes][S*S] per-CTA accumulator
+  double* rp_s = W_s + (size_t)n_nodes * S * S;        // [S]
+  double* stk = rp_s + S;                              // [n_slots][S][kWalkBlock]
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < n_ops; i += kWalkBlock) prog_s[i] = program[i];
+  if (tid < S) { pi_s[tid] = root_distn ? root_distn[tid] : 1.0; rp_s[tid] = 0.0; }
+  for (int i = tid; i < n_nodes * S * S; i += kWalkBlock) { P_s[i] = P[i]; W_s[i] = 0.0; }
+  __syncthreads();
+
+  const int64_t tiles = (n_sites + kWalkBlock - 1) / kWalkBlock;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t site = tile * kWalkBlock + tid;
+    const bool live = site < n_sites && status[site] == RT_SITE_OK;
+    double cur[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) cur[s] = 0.0;
+
+    for (int ip = n_ops - 1; ip >= 0; --ip) {
+      const int4 op = prog_s[ip];
+      const int code = op.x & 0xff;
+      if (code == OP_ROOT) {
+        double tot = 0.0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          cur[s] = live ? partials[((int64_t)op.w * S + s) * stride + site] * pi_s[s] : 0.0;
+          tot += cur[s];
+        }
+        const double inv = tot > 0.0 ? 1.0 / tot : 0.0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          cur[s] *= inv;
+          if (node_distn && site < n_sites) node_distn[((int64_t)op.w * S + s) * stride + site] = cur[s];
+          const double t = rt_warp_sum(cur[s]);
+          if (lane == 0 && root_post_sum && t != 0.0) atomicAdd(&rp_s[s], t);
+        }
+      } else if (code == OP_STORE) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) cur[s] = stk[(op.z * S + s) * kWalkBlock + tid];
+      } else if (code <= OP_MSG_ONES) {
+        const int c = op.y;
+        const double* Pc = P_s + (size_t)c * S * S;
+        double L[S];
+        if (code == OP_MSG_SLOT) {
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            L[s] = live ? __ldcs(&partials[((int64_t)op.w * S + s) * stride + site]) : 0.0;
+        } else if (code == OP_MSG_ONES) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) L[s] = live ? 1.0 : 0.0;
+        } else if (OBS == OBS_CODES) {
+          const int k = live ? reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site] : -1;
+#pragma unroll
+          for (int s = 0; s < S; ++s) L[s] = (k == RT_MISSING || k == s) ? 1.0 : 0.0;
+        } else if (OBS == OBS_MASK) {
+          const unsigned long long mk =
+              live ? reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site] : 0ull;
+#pragma unroll
+          for (int s = 0; s < S; ++s) L[s] = ((mk >> s) & 1ull) ? 1.0 : 0.0;
+        } else {
+          const double* d = reinterpret_cast<const double*>(obs);
+#pragma unroll
+          for (int s = 0; s < S; ++s) L[s] = live ? d[((int64_t)op.z * S + s) * stride + site] : 0.0;
+        }
+        double G[S];
+#pragma unroll
+        for (int a = 0; a < S; ++a) {
+          double m = 0.0;
+#pragma unroll
+          for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], L[b], m);
+          G[a] = (cur[a] > 0.0 && m > 0.0) ? cur[a] / m : 0.0;
+        }
+        if (code == OP_MSG_SLOT) {   // the child is internal: park its marginal
+#pragma unroll
+          for (int b = 0; b < S; ++b) {
+            double t = 0.0;
+#pragma unroll
+            for (int a = 0; a < S; ++a) t = fma(G[a], Pc[a * S + b], t);
+            t *= L[b];
+            stk[(op.z * S + b) * kWalkBlock + tid] = t;
+            if (node_distn && site < n_sites) node_distn[((int64_t)op.w * S + b) * stride + site] = t;
+          }
+        }
+        // W_c += G (x) L over the 32 sites of the warp
+        double w[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) w[i] = (i < S * S) ? G[i / S] * L[i % S] : 0.0;
+        reduce_scatter_warp<V>(w, lane);
+        if (V == 16) {
+          if ((lane & 1) == 0 && (lane >> 1) < S * S && w[0] != 0.0)
+            atomicAdd(&W_s[(size_t)c * S * S + (lane >> 1)], w[0]);
+        } else if (V == 32) {
+          if (lane < S * S && w[0] != 0.0) atomicAdd(&W_s[(size_t)c * S * S + lane], w[0]);
+        } else {
+          if (2 * lane < S * S && w[0] != 0.0) atomicAdd(&W_s[(size_t)c * S * S + 2 * lane], w[0]);
+          if (2 * lane + 1 < S * S && w[1] != 0.0) atomicAdd(&W_s[(size_t)c * S * S + 2 * lane + 1], w[1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n_nodes * S * S; i += kWalkBlock) {
+    const double v = W_s[i];
+    if (v != 0.0 && P_s[i] > 0.0) atomicAdd(&W[i], v);
+  }
+  if (root_post_sum && tid < S && rp_s[tid] != 0.0) atomicAdd(&root_post_sum[tid], rp_s[tid]);
+}
+
+template <int S, int OBS>
+int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops, int n_slots,
+                int n_nodes, const double* P, const double* root_distn, const void* obs,
+                const double* partials, const int8_t* status, double* node_distn, double* W,
+                double* root_post_sum, cudaStream_t stream, bool* handled) {
+  auto kern = down_walk_kernel<S, OBS>;
+  const size_t smem = sizeof(int4) * n_ops + sizeof(double) * (2 * S + 2 * (size_t)n_nodes * S * S) +
+                      sizeof(double) * (size_t)n_slots * S * kWalkBlock;
+  *handled = false;
+  if (smem > 100 * 1024) return RT_OK;        // fall back to the level-synchronous kernel
+  RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  RT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWalkBlock, smem));
+  if (per_sm < 1) per_sm = 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t tiles = (n_sites + kWalkBlock - 1) / kWalkBlock;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > tiles) grid = tiles;
+  kern<<<(unsigned)grid, kWalkBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots,
+                                                     n_nodes, P, root_distn, obs, partials, status,
+                                                     node_distn, W, root_post_sum);
+  RT_CUDA_CHECK(cudaGetLastError());
+  *handled = true;
+  return RT_OK;
+}
+
 template <int S>
-int run(int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edges_dev,
+int run(int obs_kind, int64_t n_sites, int64_t stride, const int32_t* program, int n_ops,
+        int n_slots, int n_nodes, const int32_t* edges_dev,
         const int32_t* level_ptr_h, int n_levels, const double* P, const double* root_distn,
         const void* obs, const double* partials, const int8_t* status, double* node_distn,
         double* W, double* root_post_sum, cudaStream_t stream) {
+  if (program && n_ops > 0) {
+    bool handled = false;
+    const int4* prog = reinterpret_cast<const int4*>(program);
+    int rc = RT_ERR_ARG;
+#define RT_WALK(OBSK) rc = launch_walk<S, OBSK>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P, \
+                                                root_distn, obs, partials, status, node_distn, W,   \
+                                                root_post_sum, stream, &handled)
+    if (obs_kind == OBS_CODES) RT_WALK(OBS_CODES);
+    else if (obs_kind == OBS_MASK) RT_WALK(OBS_MASK);
+    else if (obs_kind == OBS_DENSE) RT_WALK(OBS_DENSE);
+#undef RT_WALK
+    if (rc != RT_OK || handled) return rc;
+  }
+  if (!node_distn) return RT_ERR_ARG;   // the level-synchronous kernel needs the marginals buffer
   int64_t gr = (n_sites + kBlock - 1) / kBlock;
   int grid_root = (int)(gr < 148 * 8 ? gr : 148 * 8);
   root_distn_kernel<S><<<grid_root, kBlock, 0, stream>>>(n_sites, stride, root_distn, partials,
@@ -222,12 +426,13 @@ int run(int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edges_dev,
 }  // namespace
 
 int rt_posterior_small_dispatch(int S, int obs_kind, int64_t n_sites, int64_t stride,
+                                const int32_t* program, int n_ops, int n_slots, int n_nodes,
                                 const int32_t* edges_dev, const int32_t* level_ptr_h, int n_levels,
                                 const double* P, const double* root_distn, const void* obs,
                                 const double* partials, const int8_t* status, double* node_distn,
                                 double* W, double* root_post_sum, cudaStream_t stream) {
-#define RT_ARGS obs_kind, n_sites, stride, edges_dev, level_ptr_h, n_levels, P, root_distn, obs, \
-                partials, status, node_distn, W, root_post_sum, stream
+#define RT_ARGS obs_kind, n_sites, stride, program, n_ops, n_slots, n_nodes, edges_dev, level_ptr_h, \
+                n_levels, P, root_distn, obs, partials, status, node_distn, W, root_post_sum, stream
   switch (S) {
     case 2: return run<2>(RT_ARGS);
     case 3: return run<3>(RT_ARGS);

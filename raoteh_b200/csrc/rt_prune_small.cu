@@ -20,35 +20,72 @@ namespace {
 
 constexpr int kBlock = 128;
 
-template <int S>
-struct ObsCodes {
-  const uint8_t* p; int64_t stride;
-  __device__ __forceinline__ int code(int slot, int64_t site) const {
-    return p[(int64_t)slot * stride + site];
+// One observation row of one site, fetched one obs-consuming op ahead of its use.
+template <int S, int OBS>
+struct ObsVal {
+  int k;                    // OBS_CODES
+  unsigned long long mk;    // OBS_MASK
+  double d[S];              // OBS_DENSE
+  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride,
+                                        int64_t site) {
+    if (row < 0) return;
+    if (OBS == OBS_CODES) {
+      k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * stride + site];
+    } else if (OBS == OBS_MASK) {
+      mk = reinterpret_cast<const unsigned long long*>(obs)[(int64_t)row * stride + site];
+    } else {
+      const double* p = reinterpret_cast<const double*>(obs) + (int64_t)row * S * stride + site;
+#pragma unroll
+      for (int s = 0; s < S; ++s) d[s] = __ldcs(p + (int64_t)s * stride);
+    }
   }
 };
 
-template <int S, int OBS, bool STORE>
+// decoded op in shared memory: x = opcode, y = P offset in doubles (node*S*S),
+// z = stack offset in doubles (slot*S*kBlock) or unused, w = store index;
+// pre_s[ip] = observation row to prefetch when op ip is reached (-1 none)
+template <int S, int OBS, bool STORE, bool P_SMEM>
 __global__ void __launch_bounds__(kBlock)
 prune_small_kernel(int64_t n_sites, int64_t stride,
                    const int4* __restrict__ program, int n_ops, int n_slots, int n_nodes,
-                   const double* __restrict__ P, int p_in_smem,
+                   const double* __restrict__ P,
                    const double* __restrict__ root_distn,
                    const void* __restrict__ obs,
                    double* __restrict__ partials, int32_t* __restrict__ exponents,
                    double* __restrict__ loglik, int8_t* __restrict__ status,
                    double* __restrict__ loglik_sum) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // carve: program | pi | rowsum | P (optional) | stack doubles | stack exponents
+  // carve: decoded program | prefetch rows | pi | rowsum | P (optional) | stack | stack exponents
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
-  double* pi_s = reinterpret_cast<double*>(prog_s + n_ops);
+  int* pre_s = reinterpret_cast<int*>(prog_s + n_ops);
+  double* pi_s = reinterpret_cast<double*>(pre_s + ((n_ops + 4) & ~3));
   double* rowsum_s = pi_s + S;
-  double* P_s = rowsum_s + (size_t)n_nodes * S;
-  double* stk = P_s + (p_in_smem ? (size_t)n_nodes * S * S : 0);
-  int* estk = reinterpret_cast<int*>(stk + (size_t)n_slots * S * kBlock);
+  double* P_s = rowsum_s + n_nodes * S;
+  double* stk = P_s + (P_SMEM ? n_nodes * S * S : 0);
+  int* estk = reinterpret_cast<int*>(stk + n_slots * S * kBlock);
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < n_ops; i += kBlock) prog_s[i] = program[i];
+  for (int i = tid; i < n_ops; i += kBlock) {
+    int4 op = program[i];
+    const int code = op.x & 0xff;
+    int4 d;
+    d.x = code;
+    d.y = op.y * S * S;
+    d.z = (code == OP_MSG_SLOT || code == OP_STORE) ? op.z * S * kBlock : op.z;
+    d.w = op.w;
+    prog_s[i] = d;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // pre_s[ip]: row consumed by the next obs-consuming op after ip; pre_s[n_ops] unused.
+    int nxt = -1;
+    for (int i = n_ops - 1; i >= 0; --i) {
+      pre_s[i] = nxt;
+      const int code = prog_s[i].x;
+      if (code == OP_MSG_OBS || code == OP_APPLY_OBS) nxt = prog_s[i].z;
+    }
+    pre_s[n_ops] = nxt;     // first row of the program (slot n_ops is inside the padding)
+  }
   if (tid < S) pi_s[tid] = root_distn ? root_distn[tid] : 1.0;
   for (int i = tid; i < n_nodes * S; i += kBlock) {
     double r = 0.0;
@@ -56,10 +93,9 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
     for (int b = 0; b < S; ++b) r += P[(size_t)i * S + b];
     rowsum_s[i] = r;
   }
-  if (p_in_smem)
+  if (P_SMEM)
     for (int i = tid; i < n_nodes * S * S; i += kBlock) P_s[i] = P[i];
   __syncthreads();
-  const double* Pm = p_in_smem ? P_s : P;
 
   const int64_t site = (int64_t)blockIdx.x * kBlock + tid;
   const bool active = site < n_sites;
@@ -70,16 +106,26 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
 #pragma unroll
     for (int a = 0; a < S; ++a) acc[a] = 1.0;
     int esum = 0;
+    ObsVal<S, OBS> cur, nxt;
+    nxt.k = RT_MISSING; nxt.mk = ~0ull;
+#pragma unroll
+    for (int s = 0; s < S; ++s) nxt.d[s] = 1.0;
+    nxt.fetch(obs, pre_s[n_ops], stride, site);
 
     for (int ip = 0; ip < n_ops; ++ip) {
       const int4 op = prog_s[ip];
-      const double* Pc = Pm + (size_t)op.y * S * S;
-      switch (op.x & 0xff) {
+      const double* Pc = P_SMEM ? (P_s + op.y) : (P + op.y);
+      if (op.x == OP_MSG_OBS || op.x == OP_APPLY_OBS) {
+        cur = nxt;
+        nxt.fetch(obs, pre_s[ip], stride, site);
+      }
+      switch (op.x) {
         case OP_MSG_SLOT: {
           double v[S];
+          const double* sp = stk + op.z + tid;
 #pragma unroll
-          for (int b = 0; b < S; ++b) v[b] = stk[(op.z * S + b) * kBlock + tid];
-          esum += estk[op.z * kBlock + tid];
+          for (int b = 0; b < S; ++b) v[b] = sp[b * kBlock];
+          esum += estk[op.z / S + tid];
 #pragma unroll
           for (int a = 0; a < S; ++a) {
             double m = 0.0;
@@ -90,10 +136,10 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
         } break;
         case OP_MSG_OBS: {
           if (OBS == OBS_CODES) {
-            const int k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site];
+            const int k = cur.k;
             if (k == RT_MISSING) {
 #pragma unroll
-              for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y * S + a];
+              for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y / S + a];
             } else if (k < S) {
 #pragma unroll
               for (int a = 0; a < S; ++a) acc[a] *= Pc[a * S + k];
@@ -104,14 +150,11 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
           } else {
             double v[S];
             if (OBS == OBS_MASK) {
-              const unsigned long long mk =
-                  reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site];
 #pragma unroll
-              for (int b = 0; b < S; ++b) v[b] = ((mk >> b) & 1ull) ? 1.0 : 0.0;
+              for (int b = 0; b < S; ++b) v[b] = ((cur.mk >> b) & 1ull) ? 1.0 : 0.0;
             } else {
-              const double* d = reinterpret_cast<const double*>(obs);
 #pragma unroll
-              for (int b = 0; b < S; ++b) v[b] = d[((int64_t)op.z * S + b) * stride + site];
+              for (int b = 0; b < S; ++b) v[b] = cur.d[b];
             }
 #pragma unroll
             for (int a = 0; a < S; ++a) {
@@ -124,24 +167,20 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
         } break;
         case OP_MSG_ONES: {
 #pragma unroll
-          for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y * S + a];
+          for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y / S + a];
         } break;
         case OP_APPLY_OBS: {
           if (OBS == OBS_CODES) {
-            const int k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site];
-            if (k != RT_MISSING) {
+            if (cur.k != RT_MISSING) {
 #pragma unroll
-              for (int a = 0; a < S; ++a) acc[a] = (a == k) ? acc[a] : 0.0;
+              for (int a = 0; a < S; ++a) acc[a] = (a == cur.k) ? acc[a] : 0.0;
             }
           } else if (OBS == OBS_MASK) {
-            const unsigned long long mk =
-                reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site];
 #pragma unroll
-            for (int a = 0; a < S; ++a) acc[a] = ((mk >> a) & 1ull) ? acc[a] : 0.0;
+            for (int a = 0; a < S; ++a) acc[a] = ((cur.mk >> a) & 1ull) ? acc[a] : 0.0;
           } else {
-            const double* d = reinterpret_cast<const double*>(obs);
 #pragma unroll
-            for (int a = 0; a < S; ++a) acc[a] *= d[((int64_t)op.z * S + a) * stride + site];
+            for (int a = 0; a < S; ++a) acc[a] *= cur.d[a];
           }
         } break;
         case OP_STORE:
@@ -157,15 +196,16 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
             esum += e;
           }
           if (STORE && op.w >= 0) {
+            double* pp = partials + (int64_t)op.w * S * stride + site;
 #pragma unroll
-            for (int a = 0; a < S; ++a)
-              partials[((int64_t)op.w * S + a) * stride + site] = acc[a];
+            for (int a = 0; a < S; ++a) __stcs(pp + (int64_t)a * stride, acc[a]);
             if (exponents) exponents[(int64_t)op.w * stride + site] = esum;
           }
-          if ((op.x & 0xff) == OP_STORE) {
+          if (op.x == OP_STORE) {
+            double* sp = stk + op.z + tid;
 #pragma unroll
-            for (int a = 0; a < S; ++a) stk[(op.z * S + a) * kBlock + tid] = acc[a];
-            estk[op.z * kBlock + tid] = esum;
+            for (int a = 0; a < S; ++a) sp[a * kBlock] = acc[a];
+            estk[op.z / S + tid] = esum;
 #pragma unroll
             for (int a = 0; a < S; ++a) acc[a] = 1.0;
             esum = 0;
@@ -207,19 +247,28 @@ int launch_t(int64_t n_sites, int64_t stride, const int4* program, int n_ops, in
              int n_nodes, const double* P, const double* root_distn, const void* obs,
              double* partials, int32_t* exponents, double* loglik, int8_t* status,
              double* loglik_sum, cudaStream_t stream) {
-  auto kern = prune_small_kernel<S, OBS, STORE>;
-  size_t base = (size_t)n_ops * sizeof(int4) + sizeof(double) * (S + (size_t)n_nodes * S);
+  size_t base = (size_t)n_ops * sizeof(int4) + sizeof(int) * (((size_t)n_ops + 4) & ~(size_t)3) +
+                sizeof(double) * (S + (size_t)n_nodes * S);
   size_t stack = (size_t)n_slots * S * kBlock * sizeof(double) + (size_t)n_slots * kBlock * sizeof(int);
   size_t pbytes = (size_t)n_nodes * S * S * sizeof(double);
   const size_t limit = 200 * 1024;
-  int p_in_smem = (base + stack + pbytes <= 96 * 1024) ? 1 : 0;
+  const bool p_in_smem = base + stack + pbytes <= 96 * 1024;
   size_t smem = base + stack + (p_in_smem ? pbytes : 0);
   if (smem > limit) return RT_ERR_UNSUPPORTED;
-  RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t grid = (n_sites + kBlock - 1) / kBlock;
-  kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
-                                                P, p_in_smem, root_distn, obs, partials, exponents,
-                                                loglik, status, loglik_sum);
+  if (p_in_smem) {
+    auto kern = prune_small_kernel<S, OBS, STORE, true>;
+    RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
+                                                  P, root_distn, obs, partials, exponents, loglik,
+                                                  status, loglik_sum);
+  } else {
+    auto kern = prune_small_kernel<S, OBS, STORE, false>;
+    RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
+                                                  P, root_distn, obs, partials, exponents, loglik,
+                                                  status, loglik_sum);
+  }
   RT_CUDA_CHECK(cudaGetLastError());
   return RT_OK;
 }

@@ -214,7 +214,7 @@ class TreeMJP(object):
         return res
 
     # ---- K4 / K5 ------------------------------------------------------------
-    def posterior(self, obs, want_exponents=False):
+    def posterior(self, obs, want_exponents=False, want_node_distn=True):
         """Up + down pass.  Returns loglik, status, partials, node_distn (internal
         nodes, by store index), W[n,S,S] (site-summed J/P weights), root_post_sum[S]."""
         up = self.log_likelihood(obs, keep_partials=True, want_exponents=want_exponents)
@@ -222,13 +222,16 @@ class TreeMJP(object):
         N, stride = obs.n_sites, obs.stride
         dev = self.device
         P = self.transition_matrices()
-        node_distn = self._buf('node_distn', (self.sched.n_store, self.S, stride), torch.float64)
+        node_distn = None
+        if want_node_distn or self.S > 8:
+            node_distn = self._buf('node_distn', (self.sched.n_store, self.S, stride), torch.float64)
         W = self._buf('W', (self.sched.n, self.S, self.S), torch.float64, zero=True)
         root_post_sum = self._buf('root_post_sum', (self.S,), torch.float64, zero=True)
         lp = prog['level_ptr']
         self._mark('down')
         rc = _native.lib().rt_posterior_stats(
-            self.S, self.sched.n, N, stride, _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
+            self.S, self.sched.n, N, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
+            _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
             _ptr(P), _ptr(self.root_distn), obs.kind, _ptr(obs.data), _ptr(up['partials']),
             _ptr(up['status']), _ptr(node_distn), _ptr(W), _ptr(root_post_sum), _stream())
         _native.check(rc, 'rt_posterior_stats')
@@ -250,7 +253,8 @@ class TreeMJP(object):
         root_post_sum = self._buf('root_post_sum', (self.S,), torch.float64, zero=True)
         lp = prog['level_ptr']
         rc = _native.lib().rt_posterior_stats(
-            self.S, self.sched.n, N, stride, _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
+            self.S, self.sched.n, N, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
+            _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
             _ptr(self.transition_matrices()), _ptr(self.root_distn), obs.kind, _ptr(obs.data),
             _ptr(partials), _ptr(status), _ptr(node_distn), _ptr(W), _ptr(root_post_sum), _stream())
         _native.check(rc, 'rt_posterior_stats')
@@ -281,14 +285,14 @@ class TreeMJP(object):
         _native.check(rc, 'rt_frechet_contract')
         return M
 
-    def expected_history_statistics(self, obs):
+    def expected_history_statistics(self, obs, want_node_distn=False):
         """Site-summed expected dwell[S], transition counts[S,S], root posterior sum[S],
         per-site loglik, per-edge contraction matrices M_edges[n,S,S].
 
         dwell[c] = sum_b M_b[c,c]; trans[c,d] = Q_b[c,d] * M_b[c,d] summed over
         edges (raoteh/sampler/_mjp_dense.py:497-533 with one Frechet derivative per
         edge, the form of examples/code2x3/extras.py:108-129)."""
-        post = self.posterior(obs)
+        post = self.posterior(obs, want_node_distn=want_node_distn)
         M = self.frechet_contract(post['W'])
         M[0].zero_()
         S = self.S

@@ -1,0 +1,106 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header
+declares; host lowering (tree programs) is consistent."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from raoteh_b200 import _native, lowering, synth
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_native.LIB_PATH):
+        from raoteh_b200 import _build
+        _build.build()
+    L = ctypes.CDLL(_native.LIB_PATH)
+    declared = _native.declared_symbols()
+    assert len(declared) >= 9
+    for name in declared:
+        assert hasattr(L, name), name
+    for name in declared:
+        assert name in _native.EXPORTS, 'binding missing for ' + name
+    assert _native.lib().rt_version() >= 100
+
+
+def test_product_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from raoteh_b200 import engine
+    parent, length, leaves = synth.random_binary_tree(4, 0.1, np.random.default_rng(0))
+    with pytest.raises(_native.NativeError):
+        engine.TreeMJP(lowering.TreeSchedule(parent, length), synth.hky85()[0])
+
+
+def test_product_never_imports_the_oracle():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, 'raoteh_b200')
+    offenders = []
+    for dp, dn, fn in os.walk(pkg):
+        for f in fn:
+            if f.endswith('.py') and f != 'raoteh_bench.py':
+                text = open(os.path.join(dp, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M):
+                    offenders.append(f)
+    assert offenders == []
+
+
+@pytest.mark.parametrize('n_leaves', [2, 3, 8, 33, 128])
+def test_up_program_is_a_valid_postorder_schedule(n_leaves):
+    rng = np.random.default_rng(n_leaves)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.1, rng)
+    sched = lowering.TreeSchedule(parent, length)
+    obs_slot = np.full(sched.n, -1, dtype=np.int32)
+    obs_slot[leaves] = np.arange(len(leaves))
+    ops, n_slots = sched.up_program(obs_slot)
+    live = {}
+    stored = set()
+    msgs = set()
+    last_store = None
+    for code, node, a, b in ops:
+        fresh = bool(code & lowering.OP_FLAG_FRESH)
+        code &= 0xff
+        if code == lowering.OP_MSG_SLOT:
+            assert live.get(a) == node            # the slot still holds this child
+            assert b == sched.store_index[node]
+            if fresh:
+                assert last_store == node
+            msgs.add(node)
+        elif code in (lowering.OP_MSG_OBS, lowering.OP_MSG_ONES):
+            assert sched.is_leaf[node]
+            msgs.add(node)
+        elif code == lowering.OP_STORE:
+            for c in sched.children[node]:
+                assert c in msgs
+                if not sched.is_leaf[c]:
+                    slot = [k for k, v in live.items() if v == c]
+                    for k in slot:
+                        del live[k]
+            assert a not in live and a < n_slots
+            live[a] = node
+            stored.add(node)
+            last_store = node
+        elif code == lowering.OP_ROOT:
+            assert node == 0
+    assert msgs == set(range(1, sched.n))
+    assert stored == set(sched.internal) - {0}
+    assert n_slots <= max(1, int(np.ceil(np.log2(n_leaves))) + 1)
+    edges, level_ptr = sched.down_program(obs_slot)
+    assert len(edges) == sched.n - 1 and level_ptr[-1] == sched.n - 1
+    seen = {0}
+    for row in edges:
+        assert sched.parent[row[0]] in seen
+        seen.add(int(row[0]))
+
+
+def test_from_nx_matches_reference_preorder_convention():
+    import networkx as nx
+    T = nx.Graph()
+    T.add_weighted_edges_from([(0, 1, 0.5), (1, 2, 0.5), (2, 3, 0.5), (2, 4, 0.5), (1, 5, 0.5)])
+    sched = lowering.TreeSchedule.from_nx(T, 0)
+    assert sched.nodes == list(nx.dfs_preorder_nodes(T, 0))
+    assert all(sched.parent[i] < i for i in range(1, sched.n))
+    with pytest.raises(ValueError):
+        lowering.TreeSchedule.from_nx(T, 99)

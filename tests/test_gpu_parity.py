@@ -106,7 +106,7 @@ def test_golden_random_cases(rt):
     for case in g['cases']:
         sched, Q, pi, mjp, obs, mask = _engine_case(rt, case)
         S = case['nstates']
-        r = mjp.expected_history_statistics(obs)
+        r = mjp.expected_history_statistics(obs, want_node_distn=True)
         if 'raises' in case:
             assert int(r['status'][0]) == 1
             continue
