@@ -5,8 +5,8 @@
 // (raoteh/sampler/_mcy_dense.py:286-291, spec _mcy.py:611-682, emissions
 // _mcz.py:138-163) + _mc0_dense.get_likelihood (_mc0_dense.py:147-212).
 //
-// One CTA = 8 warps owns a tile of 8*16 = 128 sites and walks the whole upward
-// program.  A message is the dense contraction
+// One CTA = 4 warps owns a tile of 4*16 = 64 sites and walks the whole upward
+// program; two CTAs share an SM.  A message is the dense contraction
 //     M^T[s, site] = sum_s' P_c[s, s'] * L_c^T[s', site]
 // i.e. A = P_c (states x states), B = L_c^T (states x sites), C = messages.
 // Every warp owns 16 site columns, so a warp's B operand is always its own
@@ -16,12 +16,14 @@
 // observation mask, the exact power-of-two rescale and the root combine run on
 // the C fragments in registers; a finished partial goes to the warp's private
 // shared tile (the next B operand) and, coalesced, to HBM.
-// Leaf messages with hard codes are column gathers from P^T (no flops).
+// Leaf messages with hard codes are column gathers from the staged P_c (no flops).
+// P_c is stored XOR-swizzled (column ^ 4*(row&3)) so fragment loads are bank-conflict
+// free without padding.
 #include "rt_common.cuh"
 
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;                // 2 CTAs per SM run out of phase: one's bookkeeping hides behind the other's DMMAs
 constexpr int kThreads = kWarps * 32;
 constexpr int kNT = 2;                 // n-tiles (8 sites each) per warp
 constexpr int kWarpSites = 8 * kNT;    // 16
@@ -64,11 +66,10 @@ __global__ void pack_kernel(const double* __restrict__ P, int S, int SP, int n_n
                             double* __restrict__ Ppad, double* __restrict__ PT,
                             double* __restrict__ rowsum) {
   const int b = blockIdx.x;
-  const int ld = SP + 4;
   const double* Pb = P + (size_t)b * S * S;
-  for (int idx = threadIdx.x; idx < SP * ld; idx += blockDim.x) {
-    const int r = idx / ld, c = idx % ld;
-    Ppad[(size_t)b * SP * ld + idx] = (r < S && c < S) ? Pb[r * S + c] : 0.0;
+  for (int idx = threadIdx.x; idx < SP * SP; idx += blockDim.x) {
+    const int r = idx / SP, c = idx % SP;
+    Ppad[(size_t)b * SP * SP + r * SP + (c ^ (4 * (r & 3)))] = (r < S && c < S) ? Pb[r * S + c] : 0.0;
   }
   for (int idx = threadIdx.x; idx < SP * SP; idx += blockDim.x) {
     const int r = idx / SP, c = idx % SP;   // PT[r][c] = P[c][r]
@@ -91,7 +92,7 @@ struct Smem {
 
 // MT = number of 8-row m-tiles (padded states SP = 8*MT)
 template <int MT, int OBS, bool STORE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict__ program,
                   int n_ops, int n_slots, const double* __restrict__ Ppad,
                   const double* __restrict__ PT, const double* __restrict__ rowsum,
@@ -100,7 +101,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
                   int32_t* __restrict__ exponents, double* __restrict__ loglik,
                   int8_t* __restrict__ status, double* __restrict__ loglik_sum) {
   constexpr int SP = 8 * MT;
-  constexpr int LDP = SP + 4;
+  constexpr int LDP = SP;       // swizzled, no padding
   constexpr int KS = SP / 4;   // k-steps
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* Pbuf0 = reinterpret_cast<double*>(smem_raw);
@@ -128,7 +129,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
 
   auto needs_stage = [&](const int4& op) -> bool {
     const int code = op.x & 0xff;
-    return code == OP_MSG_SLOT || (code == OP_MSG_OBS && OBS != OBS_CODES);
+    return code == OP_MSG_SLOT || code == OP_MSG_OBS;   // every edge's P goes through the TMA ring
   };
   // producer state (thread 0 only)
   int scan_ip = 0;
@@ -177,19 +178,58 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
     const bool fresh = (op.x >> 8) & 1;
 
     if (needs_stage(op)) {
+      const int buf = consumed & 1;
+      const double* Ps = buf ? Pbuf1 : Pbuf0;
+      if (code == OP_MSG_OBS && OBS == OBS_CODES) {
+        // ---- leaf with hard codes: column gather from the staged P_c (no flops) ----------
+        const uint8_t* codes = reinterpret_cast<const uint8_t*>(obs);
+        int kk[kNT][2];
+#pragma unroll
+        for (int j = 0; j < kNT; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            kk[j][h] = cvalid[j][h] ? codes[(int64_t)op.z * stride + csite[j][h]] : RT_MISSING;
+        const double* rs = rowsum + (size_t)op.y * SP;
+        mbar_wait(&full_bar[buf], (uint32_t)((consumed >> 1) & 1));
+#pragma unroll
+        for (int j = 0; j < kNT; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = kk[j][h];
+            if (k == RT_MISSING) {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] *= rs[8 * i + g];
+            } else if (k < S) {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] *= Ps[(8 * i + g) * LDP + (k ^ (4 * (g & 3)))];
+            } else {
+#pragma unroll
+              for (int i = 0; i < MT; ++i) acc[i][j][h] = 0.0;
+            }
+          }
+        __syncthreads();
+        ++consumed;
+        if (tid == 0) issue_next();
+        continue;
+      }
       // ---- fill the warp's B tile (L_c^T, [SP][16 sites]) --------------------
       if (code == OP_MSG_SLOT) {
         if (!fresh) {
           const double* src = STORE ? partials + (int64_t)op.w * S * stride
                                     : slots_ws + (int64_t)op.z * S * stride;
           __syncwarp();
-#pragma unroll 4
-          for (int r0 = 0; r0 < SP; r0 += 2) {
-            const int r = r0 + (lane >> 4), c = lane & 15;
-            const int64_t sg = site0 + c;
-            double v = 0.0;
-            if (r < S && sg < n_sites) v = src[(int64_t)r * stride + sg];
-            Bw[r * kLdB + c] = v;
+          {
+            const int c = lane & 15, rh = lane >> 4;
+            const bool okc = site0 + c < n_sites;
+            const double* sp = src + (int64_t)rh * stride + site0 + c;
+            double* bp = Bw + rh * kLdB + c;
+#pragma unroll 8
+            for (int r0 = 0; r0 < SP; r0 += 2) {
+              const double v = (r0 + rh < S && okc) ? __ldcs(sp) : 0.0;
+              *bp = v;
+              sp += 2 * stride;
+              bp += 2 * kLdB;
+            }
           }
         }
 #pragma unroll
@@ -221,9 +261,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
       __syncwarp();
 
       // ---- wait for P_c, contract on the tensor pipe --------------------------
-      const int buf = consumed & 1;
       mbar_wait(&full_bar[buf], (uint32_t)((consumed >> 1) & 1));
-      const double* Ps = buf ? Pbuf1 : Pbuf0;
       double msg[MT][kNT][2];
 #pragma unroll
       for (int i = 0; i < MT; ++i)
@@ -236,7 +274,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
         for (int j = 0; j < kNT; ++j) bfrag[j] = Bw[(4 * kk + t) * kLdB + 8 * j + g];
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
-          const double a = Ps[(8 * i + g) * LDP + 4 * kk + t];
+          const double a = Ps[(8 * i + g) * LDP + 4 * (kk ^ (g & 3)) + t];
 #pragma unroll
           for (int j = 0; j < kNT; ++j) dmma884(msg[i][j][0], msg[i][j][1], a, bfrag[j]);
         }
@@ -255,27 +293,6 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
     }
 
     switch (code) {
-      case OP_MSG_OBS: {   // leaf with a hard code: column gather from P^T
-        const uint8_t* codes = reinterpret_cast<const uint8_t*>(obs);
-        const double* PTc = PT + (size_t)op.y * SP * SP;
-        const double* rs = rowsum + (size_t)op.y * SP;
-#pragma unroll
-        for (int j = 0; j < kNT; ++j)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int k = cvalid[j][h] ? codes[(int64_t)op.z * stride + csite[j][h]] : RT_MISSING;
-            if (k == RT_MISSING) {
-#pragma unroll
-              for (int i = 0; i < MT; ++i) acc[i][j][h] *= rs[8 * i + g];
-            } else if (k < S) {
-#pragma unroll
-              for (int i = 0; i < MT; ++i) acc[i][j][h] *= PTc[k * SP + 8 * i + g];
-            } else {
-#pragma unroll
-              for (int i = 0; i < MT; ++i) acc[i][j][h] = 0.0;
-            }
-          }
-      } break;
       case OP_MSG_ONES: {
         const double* rs = rowsum + (size_t)op.y * SP;
 #pragma unroll
@@ -339,42 +356,25 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
               esum[j][h] += e;
             }
           }
-        if (code == OP_STORE) {
-          __syncwarp();
+        // C-fragment layout -> HBM directly: for a fixed m-tile the 8 g-lanes hit 8 rows,
+        // the 4 t-lanes 64 contiguous bytes of each row (whole sectors)
+        auto store_global = [&](double* dst) {
 #pragma unroll
-          for (int i = 0; i < MT; ++i)
+          for (int i = 0; i < MT; ++i) {
+            const int s = 8 * i + g;
+            if (s < S) {
+              double* row = dst + (int64_t)s * stride;
 #pragma unroll
-            for (int j = 0; j < kNT; ++j) {
-              double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-              *reinterpret_cast<double2*>(&Bw[(8 * i + g) * kLdB + 8 * j + 2 * t]) = v;
+              for (int j = 0; j < kNT; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                  if (cvalid[j][h]) row[csite[j][h]] = acc[i][j][h];
             }
-          if (g == 0) {
-#pragma unroll
-            for (int j = 0; j < kNT; ++j)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) estk_w[op.z * kWarpSites + 8 * j + 2 * t + h] = esum[j][h];
           }
-          __syncwarp();
-          // coalesced copy of the tile to HBM (parked slot, or the kept partials)
-          double* dst = STORE ? partials + (int64_t)op.w * S * stride
-                              : slots_ws + (int64_t)op.z * S * stride;
-          for (int r0 = 0; r0 < S; r0 += 2) {
-            const int r = r0 + (lane >> 4), c = lane & 15;
-            const int64_t sg = site0 + c;
-            if (r < S && sg < n_sites) dst[(int64_t)r * stride + sg] = Bw[r * kLdB + c];
-          }
-          if (STORE && exponents && lane < kWarpSites) {
-            const int64_t sg = site0 + lane;
-            if (sg < n_sites) exponents[(int64_t)op.w * stride + sg] = estk_w[op.z * kWarpSites + lane];
-          }
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < kNT; ++j) acc[i][j][0] = acc[i][j][1] = 1.0;
-#pragma unroll
-          for (int j = 0; j < kNT; ++j) esum[j][0] = esum[j][1] = 0;
-        } else {
-          if (STORE) {
+        };
+        if (code == OP_STORE) {
+          const bool keep = (op.x >> 9) & 1, park = (op.x >> 10) & 1;
+          if (keep) {          // the parent consumes it next: it becomes the warp's B tile
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < MT; ++i)
@@ -383,14 +383,31 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
                 double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
                 *reinterpret_cast<double2*>(&Bw[(8 * i + g) * kLdB + 8 * j + 2 * t]) = v;
               }
-            __syncwarp();
-            double* dst = partials + (int64_t)op.w * S * stride;
-            for (int r0 = 0; r0 < S; r0 += 2) {
-              const int r = r0 + (lane >> 4), c = lane & 15;
-              const int64_t sg = site0 + c;
-              if (r < S && sg < n_sites) dst[(int64_t)r * stride + sg] = Bw[r * kLdB + c];
-            }
           }
+          if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < kNT; ++j)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) estk_w[op.z * kWarpSites + 8 * j + 2 * t + h] = esum[j][h];
+          }
+          if (STORE) store_global(partials + (int64_t)op.w * S * stride);
+          else if (park) store_global(slots_ws + (int64_t)op.z * S * stride);
+          if (STORE && exponents && g == 0) {
+#pragma unroll
+            for (int j = 0; j < kNT; ++j)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+                if (cvalid[j][h]) exponents[(int64_t)op.w * stride + csite[j][h]] = esum[j][h];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) acc[i][j][0] = acc[i][j][1] = 1.0;
+#pragma unroll
+          for (int j = 0; j < kNT; ++j) esum[j][0] = esum[j][1] = 0;
+        } else {
+          if (STORE) store_global(partials + (int64_t)op.w * S * stride);
 #pragma unroll
           for (int j = 0; j < kNT; ++j)
 #pragma unroll
@@ -432,7 +449,7 @@ int launch(int S, int64_t n_sites, int64_t stride, const int4* program, int n_op
            const void* obs, double* slots_ws, double* partials, int32_t* exponents, double* loglik,
            int8_t* status, double* loglik_sum, cudaStream_t stream) {
   constexpr int SP = 8 * MT;
-  constexpr int LDP = SP + 4;
+  constexpr int LDP = SP;
   auto kern = prune_dmma_kernel<MT, OBS, STORE>;
   size_t smem = sizeof(double) * (2 * SP * LDP + (size_t)kWarps * SP * kLdB + SP) +
                 sizeof(int) * (size_t)kWarps * n_slots * kWarpSites + sizeof(int4) * (size_t)n_ops;
@@ -473,7 +490,7 @@ int rt_prune_dmma_dispatch(int S, int obs_kind, bool store, int64_t n_sites, int
                            double* loglik_sum, cudaStream_t stream) {
   if (n_slots > kMaxSlots) return RT_ERR_UNSUPPORTED;
   const int MT = (S + 15) / 16 * 2;     // padded states 16 / 32 / 48 / 64
-  const int SP = 8 * MT, LDP = SP + 4;
+  const int SP = 8 * MT, LDP = SP;
   double* ws = nullptr;
   const size_t n_pad = (size_t)n_nodes * SP * LDP, n_pt = (size_t)n_nodes * SP * SP,
                n_rs = (size_t)n_nodes * SP;

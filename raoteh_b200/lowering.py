@@ -19,6 +19,8 @@ OP_APPLY_OBS = 3   # node=v, a=obs slot                     acc *= obs_v
 OP_STORE = 4       # node=v, a=stack slot, b=store index    rescale, park L_v
 OP_ROOT = 5        # node=root, b=store index               rescale, combine with pi
 OP_FLAG_FRESH = 1 << 8   # on OP_MSG_SLOT: L_c is the partial stored by the previous OP_STORE
+OP_FLAG_KEEP_ON_CHIP = 1 << 9   # on OP_STORE: the next op consumes this partial FRESH
+OP_FLAG_PARK = 1 << 10          # on OP_STORE: a later, non-fresh op reads it back from its slot
 
 MISSING = 255
 
@@ -143,6 +145,14 @@ class TreeSchedule(object):
                 s = alloc()
                 slot_of[v] = s
                 ops.append((OP_STORE, v, s, int(self.store_index[v])))
+        ops = [list(o) for o in ops]
+        for i, o in enumerate(ops):
+            if (o[0] & 0xff) != OP_STORE:
+                continue
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            fresh_next = (nxt is not None and (nxt[0] & 0xff) == OP_MSG_SLOT and
+                          (nxt[0] & OP_FLAG_FRESH) and nxt[1] == o[1])
+            o[0] |= OP_FLAG_KEEP_ON_CHIP if fresh_next else OP_FLAG_PARK
         return np.asarray(ops, dtype=np.int32).reshape(-1, 4), max(1, n_slots[0])
 
     # -- downward program -----------------------------------------------------
