@@ -136,10 +136,26 @@ def c2_bytes_per_site(sched, S):
     n_int = sched.n_store
     n_leaf = len(sched.leaves)
     up = n_leaf * 1 + n_int * S * 8 + 8 + 1
-    # down: every stored partial read once, every marginal written once and read once,
-    # leaf codes and status read once
-    down = n_int * S * 8 + 2 * n_int * S * 8 + n_leaf * 1 + 1
+    # down (fused walk): every stored partial read once, leaf codes and status read once;
+    # node marginals never leave the chip, W is S*S*n_edges doubles per CTA (negligible)
+    down = n_int * S * 8 + n_leaf * 1 + 1
     return up, down
+
+
+def ncu_traffic(kernel_substr):
+    """dram read+write bytes per launch from the committed `ncu --set full` capture."""
+    path = os.path.join(ROOT, 'profiles', 'r1_ncu_full_summary.json')
+    if not os.path.exists(path):
+        return None
+    mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for k in json.load(open(path)):
+        if kernel_substr in k['kernel']:
+            tot = 0.0
+            for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                v, u = k[key].split()
+                tot += float(v) * mult[u]
+            return tot
+    return None
 
 
 # ----------------------------------------------------------------------------
@@ -319,13 +335,17 @@ def run_gpu(args):
     up_b, down_b = c2_bytes_per_site(sched, S)
     down_gbs = N * down_b / (down_ms * 1e-3) / 1e9
     up_gbs = N * up_b / (up_ms * 1e-3) / 1e9
-    roofline = dict(bound='hbm', kernel='down_level_kernel<4,codes> (%d launches/step) + root_distn_kernel'
-                    % state['n_levels'], achieved=down_gbs, peak=peaks['hbm_gbs'], unit='GB/s',
+    roofline = dict(bound='hbm', kernel='down_walk_kernel<4,codes> (1 launch/step, %.0f%% of the step)'
+                    % (100 * down_ms / ms), achieved=down_gbs, peak=peaks['hbm_gbs'], unit='GB/s',
                     frac=down_gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
-                    traffic=None, algorithmic_bytes_per_launch_set=N * down_b, ms=down_ms,
+                    traffic=ncu_traffic('down_walk_kernel<4, 0>'),
+                    algorithmic_bytes_per_launch=N * down_b, ms=down_ms,
+                    note='S=4 walk is issue / FP64-pipe bound, not HBM bound (ncu: issue active 66%, '
+                         'fp64 pipe 36%, dram 12%); it reads each stored partial exactly once',
                     also=dict(kernel='prune_small_kernel<4,codes,store>', achieved=up_gbs,
                               frac=up_gbs / peaks['hbm_gbs'], ms=up_ms,
-                              algorithmic_bytes_per_launch=N * up_b))
+                              algorithmic_bytes_per_launch=N * up_b,
+                              traffic=ncu_traffic('prune_small_kernel<4, 0, 1')))
 
     extra = {}
     if rank == 0 and not args.no_extra:
@@ -360,7 +380,7 @@ def run_gpu(args):
                                    % (n_sample, per_site, n_edges / per_site))
 
     if rank == 0:
-        launches_per_step = 2 + 1 + 1 + state['n_levels'] + 3
+        launches_per_step = 2 + 1 + 1 + 3    # expm (2), up, down walk, Frechet contraction (3)
         line = dict(
             metric='site_edge_messages_per_sec', value=value, unit='messages/s', n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
