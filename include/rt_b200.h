@@ -161,10 +161,11 @@ int rt_joint_distn(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
  *   node_state uint8 [n_nodes][traj_stride]  state at every tree node
  *   ev_count   uint8 [n_nodes][traj_stride]  real jumps on the edge above node b
  *   ev_total   int32 [traj_stride]           total real jumps
- *   ev_time    float [cap][traj_stride]      jump times from the PARENT end of the
- *   ev_sb      uint8 [cap][traj_stride]      edge / state on the parent side; the
- *              jumps occupy rows [cap - ev_total, cap) in upward-program order
- *              (edges in program order, child end first).
+ *   ev_time    float [traj_stride][cap]      jump times from the PARENT end of the
+ *   ev_sb      uint8 [traj_stride][cap]      edge / state on the parent side; the
+ *              jumps of a trajectory are contiguous and occupy entries
+ *              [cap - ev_total, cap) in upward-program order (edges in program
+ *              order, child end first).
  * B = I + Q/omega, rate[s] = omega - q_s (raoteh/sampler/_sampler.py:346-355).
  * init_k >= 0: build an initial history with init_k equally spaced events on
  * every edge (one round of _sampler.get_restricted_feasible_history,

@@ -21,17 +21,16 @@
 // the pruning kernels walk):
 //   UP   (child -> parent along every edge): thin a Poisson process of rate
 //        omega - q_s onto every constant-state segment, and at each event
-//        (virtual or old jump) push the backward message through B.  Instead of
-//        keeping every message for the backward-sampling pass, the thread draws
-//        the next state for EVERY possible parent-side state right away (one
-//        uniform, S inverse-CDF look-ups that share the mat-vec's partial sums)
-//        and stores that S-entry table (4 bits per entry).  Partials then live
-//        only in a small per-thread stack in shared memory.
-//   DOWN (program reversed): sample the root from pi * L_root, then resolve the
-//        tables by look-up, drop self-transitions, accumulate dwell times and
-//        transition counts, and rewrite the jump lists.
-// The law is exactly that of FFBS: a table row is used only for the realised
-// parent state, and rows use independent randomness from everything upstream.
+//        (virtual or old jump) record the backward message just below it and push
+//        it through B.  Only events need a stored message: an edge without events
+//        forces equal end states, so node partials live only in a small per-thread
+//        slot stack in shared memory.  Virtual events are drawn in hazard space
+//        (unit-rate exponential gaps consumed by rate*length of each segment), so
+//        a segment without an event costs one multiply-compare and no random number.
+//   DOWN (program reversed): sample the root from pi * L_root, then at every event
+//        draw the child-side state from B[parent state, :] * message, drop
+//        self-transitions, accumulate dwell times and transition counts, and
+//        rewrite the jump lists.  This is FFBS on the implicit chunk tree.
 #include "rt_common.cuh"
 
 namespace {
@@ -73,6 +72,20 @@ struct Philox {
     --have;
     return out[have];
   }
+  // counter-addressed block: 4 words for (substream, block) of this (trajectory, sweep);
+  // every draw of the sweep has a fixed address, so lanes of a warp stay aligned inside
+  // an edge's event loop and a lane's stream never depends on its neighbours
+  __device__ __forceinline__ void block(uint32_t substream, uint32_t blk) {
+    c0 = (substream << 16) | (blk & 0xffffu);
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round(k0, k1, c);
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
   // uniform in (0, 1]
   __device__ __forceinline__ float uniform() { return ((float)next() + 1.0f) * 2.3283064365386963e-10f; }
   __device__ __forceinline__ double uniform_d() { return ((double)next() + 0.5) * 2.3283064365386963e-10; }
@@ -104,12 +117,13 @@ struct SweepArgs {
   const double* root_distn;
   const void* obs;
   uint8_t* node_state;   // [n_nodes][stride]
-  float* ev_time;        // [cap][stride]   jumps in up order, occupying [cap - total, cap)
-  uint8_t* ev_sb;        // [cap][stride]   state on the parent side of the jump
+  float* ev_time;        // [stride][cap]   jumps in up order, occupying [cap - total, cap)
+  uint8_t* ev_sb;        // [stride][cap]   state on the parent side of the jump
   uint8_t* ev_count;     // [n_nodes][stride]
   int32_t* ev_total;     // [stride]
-  float* scr_time;       // [scr_cap][stride]
-  uint32_t* scr_tab;     // [scr_cap][stride]
+  // candidate events of the sweep, up order, one contiguous record per event and
+  // trajectory: [stride][scr_cap] x { float time; uint32 u; double beta[S]; } padded to 16 B
+  unsigned char* scr_rec;
   uint8_t* scr_count;    // [n_nodes][stride]
   unsigned long long seed;
   long long sweep0;
@@ -120,56 +134,38 @@ struct SweepArgs {
   int8_t* status;        // [stride]
 };
 
-// One event on the way up: table[a] = draw from B[a,:] * beta, beta <- B beta.
-template <int S>
-__device__ __forceinline__ uint32_t event_up(const double* __restrict__ Bs, double (&beta)[S], double u) {
-  double nb[S];
-  uint32_t tab = 0;
-#pragma unroll
-  for (int a = 0; a < S; ++a) {
-    double w[S];
-    double tot = 0.0;
-#pragma unroll
-    for (int s = 0; s < S; ++s) { w[s] = Bs[a * S + s] * beta[s]; tot += w[s]; }
-    nb[a] = tot;
-    const double x = u * tot;
-    double cum = 0.0;
-    int pick = S - 1;
-    bool found = false;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      cum += w[s];
-      if (!found && w[s] > 0.0 && x <= cum) { pick = s; found = true; }
-    }
-    if (!found) {   // rounding at the top end: last state with positive weight
-#pragma unroll
-      for (int s = 0; s < S; ++s) if (w[s] > 0.0) pick = s;
-    }
-    tab |= (uint32_t)pick << (4 * a);
-  }
-#pragma unroll
-  for (int a = 0; a < S; ++a) beta[a] = nb[a];
-  return tab;
-}
+#define RT_U32_TO_UNIT(u) (((float)(u) + 1.0f) * 2.3283064365386963e-10f)   /* (0, 1] */
 
 template <int S, int OBS, bool STATS>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 raoteh_kernel(SweepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
   double* B_s = reinterpret_cast<double*>(prog_s + A.n_ops);
-  double* rate_s = B_s + S * S;
-  double* pi_s = rate_s + S;
-  float* len_s = reinterpret_cast<float*>(pi_s + S);
-  int* par_s = reinterpret_cast<int*>(len_s + A.n_nodes);
-  double* stk = reinterpret_cast<double*>(par_s + A.n_nodes);   // 8*n_nodes bytes so far: aligned
+  double* pi_s = B_s + S * S;
+  double* dwell_s = pi_s + S;                                       // [S][kBlock]
+  uint32_t* trans_s = reinterpret_cast<uint32_t*>(dwell_s + S * kBlock);   // [S*S][kBlock]
+  float* rate_s = reinterpret_cast<float*>(trans_s + S * S * kBlock);      // [S] poisson rates
+  float* rinv_s = rate_s + S;                                       // [S]
+  float* len_s = rinv_s + S;                                        // [n_nodes]
+  int* par_s = reinterpret_cast<int*>(len_s + A.n_nodes);           // [n_nodes]
+  double* stk = reinterpret_cast<double*>(
+      (reinterpret_cast<uintptr_t>(par_s + A.n_nodes) + 7) & ~(uintptr_t)7);   // [n_slots][S][kBlock]
   __shared__ double red[kBlock / 32][S * S + S];
 
   const int tid = threadIdx.x;
   for (int i = tid; i < A.n_ops; i += kBlock) prog_s[i] = A.program[i];
   for (int i = tid; i < S * S; i += kBlock) B_s[i] = A.B[i];
-  if (tid < S) { rate_s[tid] = A.rate[tid]; pi_s[tid] = A.root_distn ? A.root_distn[tid] : 1.0; }
+  if (tid < S) {
+    rate_s[tid] = (float)A.rate[tid];
+    rinv_s[tid] = A.rate[tid] > 0.0 ? (float)(1.0 / A.rate[tid]) : 0.0f;
+    pi_s[tid] = A.root_distn ? A.root_distn[tid] : 1.0;
+  }
   for (int i = tid; i < A.n_nodes; i += kBlock) { len_s[i] = (float)A.length[i]; par_s[i] = A.parent[i]; }
+#pragma unroll
+  for (int s = 0; s < S; ++s) dwell_s[s * kBlock + tid] = 0.0;
+#pragma unroll
+  for (int q = 0; q < S * S; ++q) trans_s[q * kBlock + tid] = 0u;
   __syncthreads();
 
   const int64_t traj = (int64_t)blockIdx.x * kBlock + tid;
@@ -177,16 +173,25 @@ raoteh_kernel(SweepArgs A) {
   const int64_t site = active ? (A.traj0 + traj) % A.n_sites : 0;
   const int64_t st = A.stride;
 
-  double dwell[S], trans[S * S];
-#pragma unroll
-  for (int s = 0; s < S; ++s) dwell[s] = 0.0;
-#pragma unroll
-  for (int s = 0; s < S * S; ++s) trans[s] = 0.0;
-
   if (active) {
     Philox rng;
+    uint8_t* ns_p = A.node_state + traj;
+    uint8_t* cnt_p = A.ev_count + traj;
+    uint8_t* scnt_p = A.scr_count + traj;
+    float* evt_p = A.ev_time + (size_t)traj * A.cap;      // [traj][cap]: a thread's jumps are contiguous
+    uint8_t* evs_p = A.ev_sb + (size_t)traj * A.cap;
+    constexpr int kRec = (8 + 8 * S + 15) / 16 * 16;        // bytes per scratch record
+    unsigned char* rec_p = A.scr_rec + (size_t)traj * A.scr_cap * kRec;
     for (int sw = 0; sw < A.n_sweeps; ++sw) {
       rng.init(A.seed, (uint64_t)(A.traj0 + traj), (uint32_t)(A.sweep0 + sw));
+      // substream 0: root draw (word 0) and the first unit-rate gap (word 1)
+      rng.block(0u, 0u);
+      const uint32_t u_root = rng.out[0];
+      // Virtual events: a Poisson process of rate omega - q_s on every segment, sampled
+      // in HAZARD space.  Walking the segments in program order, `hrem` is the hazard left
+      // until the next event (unit-rate exponential gaps); a segment of hazard h consumes
+      // it, and only an actual event costs a random number and a logarithm.
+      float hrem = -__logf(RT_U32_TO_UNIT(rng.out[1]));
       // =============================== UP ===============================
       int nA = 0;                                   // entries pushed to the scratch list
       int rd = A.cap - A.ev_total[traj];            // read cursor in the old jump list
@@ -213,58 +218,85 @@ raoteh_kernel(SweepArgs A) {
             for (int s = 0; s < S; ++s) beta[s] = 1.0;
           }
           const float tc = len_s[c];
+          // --- walk the edge from the child end to the parent end over its candidate
+          //     events (old jumps + fresh virtual events): one loop, one event site ---
           int kA = 0;
+          int cur = 0, k_old = 0;
+          float next_old = -1.0f;          // time of the next old jump toward the parent (-1: none)
+          int next_sb = 0;
+          float pos = tc;                  // current position (moving toward 0)
+          int init_left = 0;
           if (A.init_k >= 0) {
-            // initial history: init_k equally spaced events (_sampler.py:612-631)
-            for (int j = A.init_k; j >= 1; --j) {
-              const uint32_t tab = event_up<S>(B_s, beta, rng.uniform_d());
-              if (nA < A.scr_cap) {
-                A.scr_time[(int64_t)nA * st + traj] = tc * (float)j / (float)(A.init_k + 1);
-                A.scr_tab[(int64_t)nA * st + traj] = tab;
-              } else overflow = true;
-              ++nA; ++kA;
-            }
+            init_left = A.init_k;
           } else {
-            int cur = A.node_state[(int64_t)c * st + traj];
-            const int k_old = A.ev_count[(int64_t)c * st + traj];
-            float seg_end = tc;
-            for (int j = 0; j <= k_old; ++j) {
-              float seg_start = 0.0f;
-              int sb = 0;
-              if (j < k_old) {
-                seg_start = A.ev_time[(int64_t)rd * st + traj];
-                sb = A.ev_sb[(int64_t)rd * st + traj];
-                ++rd;
+            cur = ns_p[(int64_t)c * st];
+            k_old = cnt_p[(int64_t)c * st];
+            if (k_old > 0) {
+              next_old = evt_p[rd];
+              next_sb = evs_p[rd];
+            }
+          }
+          while (true) {
+            float cand;                    // position of the next candidate event
+            bool is_old = false, is_virtual = false;
+            if (A.init_k >= 0) {
+              if (init_left == 0) break;
+              cand = tc * (float)init_left / (float)(A.init_k + 1);
+              --init_left;
+            } else {
+              const float seg_start = next_old > 0.0f ? next_old : 0.0f;
+              const float h = rate_s[cur] * (pos - seg_start);
+              if (hrem < h) {
+                cand = pos - hrem * rinv_s[cur];
+                if (!(cand > seg_start)) cand = seg_start + 0.5f * (pos - seg_start);   // rounding guard
+                is_virtual = true;
+              } else {
+                hrem -= h;
+                if (next_old > 0.0f) { cand = next_old; is_old = true; }
+                else break;
               }
-              // virtual events on (seg_start, seg_end), state `cur`, rate omega - q_cur
-              const float r = (float)rate_s[cur];
-              if (r > 0.0f) {
-                float pos = seg_end;
-                while (true) {
-                  pos -= -__logf(rng.uniform()) / r;
-                  if (!(pos > seg_start)) break;
-                  const uint32_t tab = event_up<S>(B_s, beta, rng.uniform_d());
-                  if (nA < A.scr_cap) {
-                    A.scr_time[(int64_t)nA * st + traj] = pos;
-                    A.scr_tab[(int64_t)nA * st + traj] = tab;
-                  } else overflow = true;
-                  ++nA; ++kA;
-                }
+            }
+            // random words of this event: substream = edge op, two events per Philox block
+            if ((kA & 1) == 0) rng.block((uint32_t)ip + 1u, (uint32_t)(kA >> 1));
+            const bool odd = (kA & 1) != 0;
+            const uint32_t u_draw = odd ? rng.out[2] : rng.out[0];
+            const uint32_t u_gap = odd ? rng.out[3] : rng.out[1];
+            if (is_virtual) hrem = -__logf(RT_U32_TO_UNIT(u_gap));
+            // record beta just below the event, then push it through B
+            if (nA < A.scr_cap) {
+              unsigned char* rp = rec_p + (size_t)nA * kRec;
+              *reinterpret_cast<float2*>(rp) = make_float2(cand, __uint_as_float(u_draw));
+#pragma unroll
+              for (int s = 0; s < S; ++s) reinterpret_cast<double*>(rp + 8)[s] = beta[s];
+            } else overflow = true;
+            ++nA; ++kA;
+            {
+              double nb[S];
+#pragma unroll
+              for (int a2 = 0; a2 < S; ++a2) {
+                double t2 = 0.0;
+#pragma unroll
+                for (int s = 0; s < S; ++s) t2 = fma(B_s[a2 * S + s], beta[s], t2);
+                nb[a2] = t2;
               }
-              if (j < k_old) {   // the old jump itself stays a candidate event
-                const uint32_t tab = event_up<S>(B_s, beta, rng.uniform_d());
-                if (nA < A.scr_cap) {
-                  A.scr_time[(int64_t)nA * st + traj] = seg_start;
-                  A.scr_tab[(int64_t)nA * st + traj] = tab;
-                } else overflow = true;
-                ++nA; ++kA;
-                cur = sb;
-                seg_end = seg_start;
+#pragma unroll
+              for (int s = 0; s < S; ++s) beta[s] = nb[s];
+            }
+            pos = cand;
+            if (is_old) {
+              cur = next_sb;
+              ++rd;
+              --k_old;
+              if (k_old > 0) {
+                next_old = evt_p[rd];
+                next_sb = evs_p[rd];
+              } else {
+                next_old = -1.0f;
               }
             }
           }
           if (kA > 255) overflow = true;
-          A.scr_count[(int64_t)c * st + traj] = (uint8_t)(kA > 255 ? 255 : kA);
+          scnt_p[(int64_t)c * st] = (uint8_t)(kA > 255 ? 255 : kA);
           if (kA > 0) {   // keep the chain of B-steps in range
             double mx = beta[0];
 #pragma unroll
@@ -300,7 +332,7 @@ raoteh_kernel(SweepArgs A) {
 #pragma unroll
             for (int s = 0; s < S; ++s) { w[s] = pi_s[s] * acc[s]; tot += w[s]; }
             if (!(tot > 0.0)) infeasible = true;
-            const double x = rng.uniform_d() * tot;
+            const double x = ((double)u_root + 0.5) * 2.3283064365386963e-10 * tot;
             double cum = 0.0;
             bool found = false;
 #pragma unroll
@@ -319,7 +351,7 @@ raoteh_kernel(SweepArgs A) {
       if (overflow) { A.status[traj] = 3; break; }
 
       // ============================== DOWN ==============================
-      A.node_state[traj] = (uint8_t)root_state;
+      ns_p[0] = (uint8_t)root_state;
       int rdA = nA;          // scratch is consumed backwards
       int wr = A.cap;        // new jump list grows backwards from the end
       bool pool_overflow = false;
@@ -327,41 +359,52 @@ raoteh_kernel(SweepArgs A) {
         const int4 op = prog_s[ip];
         if ((op.x & 0xff) > OP_MSG_ONES) continue;
         const int c = op.y;
-        int cur = A.node_state[(int64_t)par_s[c] * st + traj];
-        const int kA = A.scr_count[(int64_t)c * st + traj];
+        int cur = ns_p[(int64_t)par_s[c] * st];
+        const int kA = scnt_p[(int64_t)c * st];
         const float tc = len_s[c];
         float prev = 0.0f;
         int kept = 0;
         for (int j = 0; j < kA; ++j) {
           --rdA;
-          const float tau = A.scr_time[(int64_t)rdA * st + traj];
-          const uint32_t tab = A.scr_tab[(int64_t)rdA * st + traj];
-          const int nxt = (tab >> (4 * cur)) & 15;
-          if (STATS) {
+          const unsigned char* rp = rec_p + (size_t)rdA * kRec;
+          const float2 tu = *reinterpret_cast<const float2*>(rp);
+          const float tau = tu.x;
+          const uint32_t u_draw = __float_as_uint(tu.y);
+          // child-side state ~ B[cur, :] * beta  (_sample_mc0.py:66-90)
+          double w[S], tot = 0.0;
 #pragma unroll
-            for (int s = 0; s < S; ++s) dwell[s] += (s == cur) ? (double)(tau - prev) : 0.0;
+          for (int s = 0; s < S; ++s) {
+            w[s] = B_s[cur * S + s] * reinterpret_cast<const double*>(rp + 8)[s];
+            tot += w[s];
           }
+          const double x = ((double)u_draw + 0.5) * 2.3283064365386963e-10 * tot;
+          double cum = 0.0;
+          int nxt = -1;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            cum += w[s];
+            if (nxt < 0 && w[s] > 0.0 && x <= cum) nxt = s;
+          }
+          if (nxt < 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) if (w[s] > 0.0) nxt = s;
+          }
+          if (STATS) dwell_s[cur * kBlock + tid] += (double)(tau - prev);
           prev = tau;
           if (nxt != cur) {
-            if (STATS) {
-#pragma unroll
-              for (int q = 0; q < S * S; ++q) trans[q] += (q == cur * S + nxt) ? 1.0 : 0.0;
-            }
+            if (STATS) trans_s[(cur * S + nxt) * kBlock + tid] += 1u;
             --wr;
             if (wr >= 0) {
-              A.ev_time[(int64_t)wr * st + traj] = tau;
-              A.ev_sb[(int64_t)wr * st + traj] = (uint8_t)cur;
+              evt_p[wr] = tau;
+              evs_p[wr] = (uint8_t)cur;
             } else pool_overflow = true;
             ++kept;
             cur = nxt;
           }
         }
-        if (STATS) {
-#pragma unroll
-          for (int s = 0; s < S; ++s) dwell[s] += (s == cur) ? (double)(tc - prev) : 0.0;
-        }
-        A.node_state[(int64_t)c * st + traj] = (uint8_t)cur;
-        A.ev_count[(int64_t)c * st + traj] = (uint8_t)kept;
+        if (STATS) dwell_s[cur * kBlock + tid] += (double)(tc - prev);
+        ns_p[(int64_t)c * st] = (uint8_t)cur;
+        cnt_p[(int64_t)c * st] = (uint8_t)kept;
       }
       // jumps were written in down order from the end backwards == up order forwards
       if (pool_overflow) { A.status[traj] = 4; A.ev_total[traj] = 0; break; }
@@ -372,7 +415,9 @@ raoteh_kernel(SweepArgs A) {
   if (STATS && A.dwell_sum) {
 #pragma unroll
     for (int q = 0; q < S + S * S; ++q) {
-      const double v = rt_warp_sum(q < S ? dwell[q < S ? q : 0] : trans[q >= S ? q - S : 0]);
+      const double mine = q < S ? dwell_s[(q < S ? q : 0) * kBlock + tid]
+                                : (double)trans_s[(q >= S ? q - S : 0) * kBlock + tid];
+      const double v = rt_warp_sum(mine);
       if ((tid & 31) == 0) red[tid >> 5][q] = v;
     }
     __syncthreads();
@@ -386,9 +431,10 @@ raoteh_kernel(SweepArgs A) {
 
 template <int S, int OBS>
 int launch(const SweepArgs& A, bool stats, cudaStream_t stream) {
-  size_t smem = sizeof(int4) * A.n_ops + sizeof(double) * (S * S + 2 * S) +
-                sizeof(float) * A.n_nodes + sizeof(int) * A.n_nodes +
-                sizeof(double) * (size_t)A.n_slots * S * kBlock + 16;
+  size_t smem = sizeof(int4) * A.n_ops + sizeof(double) * (S * S + S) +
+                sizeof(double) * S * kBlock + sizeof(uint32_t) * S * S * kBlock +
+                sizeof(float) * 2 * S + sizeof(float) * A.n_nodes + sizeof(int) * A.n_nodes +
+                sizeof(double) * (size_t)A.n_slots * S * kBlock + 32;
   if (smem > 200 * 1024) return RT_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((A.n_traj + kBlock - 1) / kBlock);
   if (stats) {
@@ -438,11 +484,11 @@ int rt_raoteh_dispatch(int S, int obs_kind, int n_nodes, int64_t n_traj, int64_t
   // scratch: full event list (time + table) and per-edge counts
   unsigned char* ws = nullptr;
   const size_t n_scr = (size_t)A.scr_cap * (size_t)stride;
-  const size_t bytes = n_scr * (sizeof(float) + sizeof(uint32_t)) + (size_t)n_nodes * (size_t)stride;
+  const size_t rec = (size_t)((8 + 8 * S + 15) / 16 * 16);
+  const size_t bytes = n_scr * rec + (size_t)n_nodes * (size_t)stride + 64;
   RT_CUDA_CHECK(cudaMallocAsync(&ws, bytes, stream));
-  A.scr_time = reinterpret_cast<float*>(ws);
-  A.scr_tab = reinterpret_cast<uint32_t*>(ws + n_scr * sizeof(float));
-  A.scr_count = ws + n_scr * (sizeof(float) + sizeof(uint32_t));
+  A.scr_rec = ws;
+  A.scr_count = ws + n_scr * rec;
   const bool stats = dwell_sum != nullptr && trans_sum != nullptr && init_k < 0;
   int rc;
   switch (S) {

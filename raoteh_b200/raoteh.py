@@ -66,8 +66,8 @@ class RaoTehChains(object):
         self.node_state = torch.zeros((n, T), dtype=torch.uint8, device=dev)
         self.ev_count = torch.zeros((n, T), dtype=torch.uint8, device=dev)
         self.ev_total = torch.zeros(T, dtype=torch.int32, device=dev)
-        self.ev_time = torch.zeros((self.cap, T), dtype=torch.float32, device=dev)
-        self.ev_sb = torch.zeros((self.cap, T), dtype=torch.uint8, device=dev)
+        self.ev_time = torch.zeros((T, self.cap), dtype=torch.float32, device=dev)
+        self.ev_sb = torch.zeros((T, self.cap), dtype=torch.uint8, device=dev)
         self.status = torch.zeros(T, dtype=torch.int8, device=dev)
         self.dwell_sum = torch.zeros(S, dtype=torch.float64, device=dev)
         self.trans_sum = torch.zeros((S, S), dtype=torch.float64, device=dev)
@@ -137,8 +137,8 @@ class RaoTehChains(object):
         n = self.sched.n
         cnt = self.ev_count[:, t].cpu().numpy().astype(int)
         tot = int(self.ev_total[t])
-        times = self.ev_time[self.cap - tot:, t].cpu().numpy()
-        sbs = self.ev_sb[self.cap - tot:, t].cpu().numpy().astype(int)
+        times = self.ev_time[t, self.cap - tot:].cpu().numpy()
+        sbs = self.ev_sb[t, self.cap - tot:].cpu().numpy().astype(int)
         ns = self.node_state[:, t].cpu().numpy().astype(int)
         out = {}
         pos = 0
