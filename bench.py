@@ -281,11 +281,13 @@ def run_gpu(args):
     sub = {}
 
     def step_e2e():
-        """Same step from HOST buffers: H2D codes, D2H log-lik, status, statistics."""
-        codes_dev.copy_(codes_pinned, non_blocking=True)
-        up, stats = step()
-        out_ll.copy_(up['loglik'], non_blocking=True)
-        out_st.copy_(up['status'], non_blocking=True)
+        """Same step through the public host-buffer API: H2D of the leaf codes from pinned
+        memory, D2H of per-site log-lik / status and of the statistics, all inside."""
+        mjp.events = None
+        mjp.set_rate_matrix(cfg['Q'])
+        r = mjp.expected_history_statistics_from_host(codes_pinned, cfg['leaves'], out_ll, out_st)
+        stats = rdist.pack_stats(r['loglik_sum'], r['dwell'], r['trans'], r['root_post_sum'])
+        rdist.allreduce_stats(stats)
         out_stats.copy_(stats, non_blocking=True)
 
     def timed(fn, steps, warmup, record=False):

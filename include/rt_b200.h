@@ -134,6 +134,15 @@ int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
                        double* node_distn, double* W, double* root_post_sum, void* stream);
 
 /*
+ * Pitched host<->device copy on `stream` (cudaMemcpy2DAsync): moves a chunk of sites
+ * [row][lo:hi] of a site-minor array between a pinned HOST array and the device
+ * array without staging, so chunk k+1 can be copied under the kernels of chunk k.
+ * to_device != 0: `src` is the host pointer; else `dst` is.
+ */
+int rt_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                    size_t width_bytes, size_t height, int to_device, void* stream);
+
+/*
  * Materialised per-edge joints and all-node marginals for small batches
  * (n_sites <= 65535):  J[b][site][a][c] = D[parent(b)][a] * norm(P_b[a,:] L_b)[c],
  * D_all[b][site][c] = sum_a J[b][site][a][c].  edges: all rows of the downward

@@ -154,6 +154,15 @@ int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
   return unsupported("rt_posterior_stats needs 1 <= S <= 64");
 }
 
+int rt_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                    size_t width_bytes, size_t height, int to_device, void* stream) {
+  if (!dst || !src) return arg_error("null pointer");
+  RT_CUDA_CHECK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height,
+                                  to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                  (cudaStream_t)stream));
+  return RT_OK;
+}
+
 int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, int64_t n_sites,
                      int64_t traj0, const int32_t* program, int n_ops, int n_slots,
                      const int32_t* parent, const double* length, const double* B,

@@ -276,6 +276,78 @@ class TreeMJP(object):
         D[0] = post['node_distn'][0, :, :N].T
         return J, D
 
+    # ---- host-buffer entry point (pipelined) ----------------------------------------
+    def expected_history_statistics_from_host(self, codes_pinned, leaf_nodes, out_loglik,
+                                              out_status, n_chunks=4):
+        """The C2 evaluation from HOST buffers: uint8 leaf codes [n_leaves, n_sites] in
+        pinned memory in, per-site log-likelihoods / status into pinned `out_*`, summed
+        statistics returned.  The site axis is cut into `n_chunks` chunks; the H2D copy
+        of chunk k+1 and the D2H copy of chunk k-1 run on their own streams under the
+        kernels of chunk k (sites are independent, W only accumulates)."""
+        lib = _native.lib()
+        L, N = codes_pinned.shape
+        S, n = self.S, self.sched.n
+        dev = self.device
+        leaf_nodes = self.sched.leaves if leaf_nodes is None else np.asarray(leaf_nodes)
+        obs_slot = np.full(n, -1, dtype=np.int32)
+        obs_slot[leaf_nodes] = np.arange(len(leaf_nodes), dtype=np.int32)
+        codes_dev = self._buf('h_codes', (L, N), torch.uint8)
+        loglik = self._buf('h_loglik', (N,), torch.float64)
+        status = self._buf('h_status', (N,), torch.int8)
+        partials = self._buf('partials', (self.sched.n_store, S, N), torch.float64)
+        W = self._buf('W', (n, S, S), torch.float64, zero=True)
+        rps = self._buf('root_post_sum', (S,), torch.float64, zero=True)
+        llsum = self._buf('h_llsum', (1,), torch.float64, zero=True)
+        obs = Observations(OBS_CODES, codes_dev, obs_slot, N)
+        prog = self._programs(obs)
+        lp = prog['level_ptr']
+        P = self.transition_matrices()
+        cur = torch.cuda.current_stream()
+        if getattr(self, '_copy_streams', None) is None:
+            self._copy_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = self._copy_streams
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        chunk = _round_up((N + n_chunks - 1) // n_chunks, 128)
+        bounds = [(lo, min(N, lo + chunk)) for lo in range(0, N, chunk)]
+        ev_in = []
+        for lo, hi in bounds:
+            rc = lib.rt_copy2d_async(codes_dev.data_ptr() + lo, N, codes_pinned.data_ptr() + lo, N,
+                                     hi - lo, L, 1, s_in.cuda_stream)
+            _native.check(rc, 'rt_copy2d_async')
+            e = torch.cuda.Event()
+            e.record(s_in)
+            ev_in.append(e)
+        for (lo, hi), e in zip(bounds, ev_in):
+            cur.wait_event(e)
+            rc = lib.rt_prune_loglik(
+                S, n, hi - lo, N, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'], _ptr(P),
+                _ptr(self.root_distn), OBS_CODES, codes_dev.data_ptr() + lo,
+                partials.data_ptr() + 8 * lo, None, loglik.data_ptr() + 8 * lo,
+                status.data_ptr() + lo, _ptr(llsum), cur.cuda_stream)
+            _native.check(rc, 'rt_prune_loglik')
+            rc = lib.rt_posterior_stats(
+                S, n, hi - lo, N, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
+                _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1, _ptr(P), _ptr(self.root_distn),
+                OBS_CODES, codes_dev.data_ptr() + lo, partials.data_ptr() + 8 * lo,
+                status.data_ptr() + lo, None, _ptr(W), _ptr(rps), cur.cuda_stream)
+            _native.check(rc, 'rt_posterior_stats')
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                out_loglik[lo:hi].copy_(loglik[lo:hi], non_blocking=True)
+                out_status[lo:hi].copy_(status[lo:hi], non_blocking=True)
+        M = self.frechet_contract(W)
+        M[0].zero_()
+        if getattr(self, '_offdiag', None) is None:
+            self._offdiag = 1.0 - torch.eye(S, dtype=torch.float64, device=dev)
+        Qe = self.Q[0].expand(n, S, S) if self.q_index is None else self.Q[self.q_index.long()]
+        dwell = torch.diagonal(M, dim1=1, dim2=2).sum(dim=0)
+        trans = (Qe * self._offdiag * M).sum(dim=0)
+        cur.wait_stream(s_out)
+        return dict(loglik_sum=llsum[0], dwell=dwell, trans=trans, root_post_sum=rps, M_edges=M)
+
     def frechet_contract(self, W):
         """M[b] = L(t_b Q_b^T, t_b W[b]) for every node b (slot 0 -> 0)."""
         n, S = self.sched.n, self.S

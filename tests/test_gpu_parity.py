@@ -283,3 +283,26 @@ def test_c2_full_size_properties(rt):
     np.testing.assert_allclose(float(e['dwell'].sum()), cfg['length'].sum() * 1_000_000, rtol=1e-10)
     np.testing.assert_allclose(float(e['root_post_sum'].sum()), 1_000_000, rtol=1e-12)
     assert bool((e['trans'] >= 0).all())
+
+
+def test_host_buffer_pipeline_matches_resident_path(rt):
+    """The chunked host-buffer entry point (e2e path of bench.py) gives the same numbers."""
+    import torch
+    from raoteh_b200 import synth
+    from raoteh_b200.lowering import TreeSchedule
+    cfg = synth.config_c2(n_sites=10_007, n_leaves=16)
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    mjp = rt.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'])
+    obs = rt.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'])
+    ref = mjp.expected_history_statistics(obs)
+    ref = {k: ref[k].clone() for k in ('loglik', 'status', 'dwell', 'trans', 'root_post_sum')}
+    codes_pinned = torch.from_numpy(cfg['codes']).pin_memory()
+    out_ll = torch.empty(10_007, dtype=torch.float64).pin_memory()
+    out_st = torch.empty(10_007, dtype=torch.int8).pin_memory()
+    r = mjp.expected_history_statistics_from_host(codes_pinned, cfg['leaves'], out_ll, out_st, n_chunks=3)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out_ll.numpy(), ref['loglik'].cpu().numpy(), rtol=1e-14)
+    assert (out_st.numpy() == ref['status'].cpu().numpy()).all()
+    np.testing.assert_allclose(r['dwell'].cpu().numpy(), ref['dwell'].cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(r['trans'].cpu().numpy(), ref['trans'].cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(float(r['loglik_sum']), float(ref['loglik'].sum()), rtol=1e-12)
