@@ -196,6 +196,7 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
 // accumulator in shared memory; one masked global atomicAdd per entry per CTA at the end.
 // ---------------------------------------------------------------------------------------
 constexpr int kWalkBlock = 128;
+constexpr int kWalkSites = 2;    // sites per thread
 
 template <int V>
 __device__ __forceinline__ void reduce_scatter_warp(double (&v)[V], int lane) {
@@ -224,6 +225,17 @@ __device__ __forceinline__ void reduce_scatter_warp(double (&v)[V], int lane) {
 
 template <int S> struct WalkV { static constexpr int value = (S <= 4) ? 16 : (S == 5 ? 32 : 64); };
 
+// 1/x to ~1 ulp: hardware seed (rcp.approx.ftz.f64, ~20 bits, full double range) plus two
+// Newton steps.  Replaces the ~20-instruction IEEE division; the quotient is within 2 ulp,
+// far inside the 1e-10 tolerance of the path.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = r * fma(-x, r, 2.0);
+  r = r * fma(-x, r, 2.0);
+  return r;
+}
+
 template <int S, int OBS>
 __global__ void __launch_bounds__(kWalkBlock)
 down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ program, int n_ops,
@@ -233,13 +245,14 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
                  double* __restrict__ node_distn, double* __restrict__ W,
                  double* __restrict__ root_post_sum) {
   constexpr int V = WalkV<S>::value;
+  constexpr int NS = kWalkSites;                       // sites per thread (ILP + one butterfly for both)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
   double* pi_s = reinterpret_cast<double*>(prog_s + n_ops);
   double* P_s = pi_s + S;                              // [n_nodes][S][S]
   double* W_s = P_s + (size_t)n_nodes * S * S;         // [n_nodes][S*S] per-CTA accumulator
   double* rp_s = W_s + (size_t)n_nodes * S * S;        // [S]
-  double* stk = rp_s + S;                              // [n_slots][S][kWalkBlock]
+  double* stk = rp_s + S;                              // [n_slots][NS][S][kWalkBlock]
 
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < n_ops; i += kWalkBlock) prog_s[i] = program[i];
@@ -247,92 +260,120 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
   for (int i = tid; i < n_nodes * S * S; i += kWalkBlock) { P_s[i] = P[i]; W_s[i] = 0.0; }
   __syncthreads();
 
-  const int64_t tiles = (n_sites + kWalkBlock - 1) / kWalkBlock;
+  const int64_t tile_sites = (int64_t)kWalkBlock * NS;
+  const int64_t tiles = (n_sites + tile_sites - 1) / tile_sites;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t site = tile * kWalkBlock + tid;
-    const bool live = site < n_sites && status[site] == RT_SITE_OK;
-    double cur[S];
+    int64_t site[NS];
+    bool live[NS];
 #pragma unroll
-    for (int s = 0; s < S; ++s) cur[s] = 0.0;
+    for (int q = 0; q < NS; ++q) {
+      site[q] = tile * tile_sites + q * kWalkBlock + tid;     // coalesced per q
+      live[q] = site[q] < n_sites && status[site[q]] == RT_SITE_OK;
+    }
+    double cur[NS][S];
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+      for (int s = 0; s < S; ++s) cur[q][s] = 0.0;
 
     for (int ip = n_ops - 1; ip >= 0; --ip) {
       const int4 op = prog_s[ip];
       const int code = op.x & 0xff;
       if (code == OP_ROOT) {
-        double tot = 0.0;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          cur[s] = live ? partials[((int64_t)op.w * S + s) * stride + site] * pi_s[s] : 0.0;
-          tot += cur[s];
+        for (int q = 0; q < NS; ++q) {
+          double tot = 0.0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            cur[q][s] = live[q] ? partials[((int64_t)op.w * S + s) * stride + site[q]] * pi_s[s] : 0.0;
+            tot += cur[q][s];
+          }
+          const double inv = tot > 0.0 ? 1.0 / tot : 0.0;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            cur[q][s] *= inv;
+            if (node_distn && site[q] < n_sites)
+              node_distn[((int64_t)op.w * S + s) * stride + site[q]] = cur[q][s];
+          }
         }
-        const double inv = tot > 0.0 ? 1.0 / tot : 0.0;
+        if (root_post_sum) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          cur[s] *= inv;
-          if (node_distn && site < n_sites) node_distn[((int64_t)op.w * S + s) * stride + site] = cur[s];
-          const double t = rt_warp_sum(cur[s]);
-          if (lane == 0 && root_post_sum && t != 0.0) atomicAdd(&rp_s[s], t);
+          for (int s = 0; s < S; ++s) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) t += cur[q][s];
+            t = rt_warp_sum(t);
+            if (lane == 0 && t != 0.0) atomicAdd(&rp_s[s], t);
+          }
         }
       } else if (code == OP_STORE) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) cur[s] = stk[(op.z * S + s) * kWalkBlock + tid];
+        for (int q = 0; q < NS; ++q)
+#pragma unroll
+          for (int s = 0; s < S; ++s) cur[q][s] = stk[((op.z * NS + q) * S + s) * kWalkBlock + tid];
       } else if (code <= OP_MSG_ONES) {
         const int c = op.y;
-        const double* Pc = P_s + (size_t)c * S * S;
-        double L[S];
-        if (code == OP_MSG_SLOT) {
-#pragma unroll
-          for (int s = 0; s < S; ++s)
-            L[s] = live ? __ldcs(&partials[((int64_t)op.w * S + s) * stride + site]) : 0.0;
-        } else if (code == OP_MSG_ONES) {
-#pragma unroll
-          for (int s = 0; s < S; ++s) L[s] = live ? 1.0 : 0.0;
-        } else if (OBS == OBS_CODES) {
-          const int k = live ? reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site] : -1;
-#pragma unroll
-          for (int s = 0; s < S; ++s) L[s] = (k == RT_MISSING || k == s) ? 1.0 : 0.0;
-        } else if (OBS == OBS_MASK) {
-          const unsigned long long mk =
-              live ? reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site] : 0ull;
-#pragma unroll
-          for (int s = 0; s < S; ++s) L[s] = ((mk >> s) & 1ull) ? 1.0 : 0.0;
-        } else {
-          const double* d = reinterpret_cast<const double*>(obs);
-#pragma unroll
-          for (int s = 0; s < S; ++s) L[s] = live ? d[((int64_t)op.z * S + s) * stride + site] : 0.0;
-        }
-        double G[S];
-#pragma unroll
-        for (int a = 0; a < S; ++a) {
-          double m = 0.0;
-#pragma unroll
-          for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], L[b], m);
-          G[a] = (cur[a] > 0.0 && m > 0.0) ? cur[a] / m : 0.0;
-        }
-        if (code == OP_MSG_SLOT) {   // the child is internal: park its marginal
-#pragma unroll
-          for (int b = 0; b < S; ++b) {
-            double t = 0.0;
-#pragma unroll
-            for (int a = 0; a < S; ++a) t = fma(G[a], Pc[a * S + b], t);
-            t *= L[b];
-            stk[(op.z * S + b) * kWalkBlock + tid] = t;
-            if (node_distn && site < n_sites) node_distn[((int64_t)op.w * S + b) * stride + site] = t;
-          }
-        }
-        // W_c += G (x) L over the 32 sites of the warp
+        const double* Pc = P_s + c * S * S;
         double w[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) w[i] = (i < S * S) ? G[i / S] * L[i % S] : 0.0;
+        for (int i = 0; i < V; ++i) w[i] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+          double L[S];
+          if (code == OP_MSG_SLOT) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              L[s] = live[q] ? __ldcs(&partials[((int64_t)op.w * S + s) * stride + site[q]]) : 0.0;
+          } else if (code == OP_MSG_ONES) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) L[s] = live[q] ? 1.0 : 0.0;
+          } else if (OBS == OBS_CODES) {
+            const int k = live[q] ? reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site[q]] : -1;
+#pragma unroll
+            for (int s = 0; s < S; ++s) L[s] = (k == RT_MISSING || k == s) ? 1.0 : 0.0;
+          } else if (OBS == OBS_MASK) {
+            const unsigned long long mk =
+                live[q] ? reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site[q]] : 0ull;
+#pragma unroll
+            for (int s = 0; s < S; ++s) L[s] = ((mk >> s) & 1ull) ? 1.0 : 0.0;
+          } else {
+            const double* d = reinterpret_cast<const double*>(obs);
+#pragma unroll
+            for (int s = 0; s < S; ++s) L[s] = live[q] ? d[((int64_t)op.z * S + s) * stride + site[q]] : 0.0;
+          }
+          double G[S];
+#pragma unroll
+          for (int a = 0; a < S; ++a) {
+            double m = 0.0;
+#pragma unroll
+            for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], L[b], m);
+            G[a] = (cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
+          }
+          if (code == OP_MSG_SLOT) {   // the child is internal: park its marginal
+#pragma unroll
+            for (int b = 0; b < S; ++b) {
+              double t = 0.0;
+#pragma unroll
+              for (int a = 0; a < S; ++a) t = fma(G[a], Pc[a * S + b], t);
+              t *= L[b];
+              stk[((op.z * NS + q) * S + b) * kWalkBlock + tid] = t;
+              if (node_distn && site[q] < n_sites)
+                node_distn[((int64_t)op.w * S + b) * stride + site[q]] = t;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+        }
+        // W_c += sum over the warp's 32*NS sites of G (x) L
         reduce_scatter_warp<V>(w, lane);
         if (V == 16) {
           if ((lane & 1) == 0 && (lane >> 1) < S * S && w[0] != 0.0)
-            atomicAdd(&W_s[(size_t)c * S * S + (lane >> 1)], w[0]);
+            atomicAdd(&W_s[c * S * S + (lane >> 1)], w[0]);
         } else if (V == 32) {
-          if (lane < S * S && w[0] != 0.0) atomicAdd(&W_s[(size_t)c * S * S + lane], w[0]);
+          if (lane < S * S && w[0] != 0.0) atomicAdd(&W_s[c * S * S + lane], w[0]);
         } else {
-          if (2 * lane < S * S && w[0] != 0.0) atomicAdd(&W_s[(size_t)c * S * S + 2 * lane], w[0]);
-          if (2 * lane + 1 < S * S && w[1] != 0.0) atomicAdd(&W_s[(size_t)c * S * S + 2 * lane + 1], w[1]);
+          if (2 * lane < S * S && w[0] != 0.0) atomicAdd(&W_s[c * S * S + 2 * lane], w[0]);
+          if (2 * lane + 1 < S * S && w[1] != 0.0) atomicAdd(&W_s[c * S * S + 2 * lane + 1], w[1]);
         }
       }
     }
@@ -352,7 +393,7 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
                 double* root_post_sum, cudaStream_t stream, bool* handled) {
   auto kern = down_walk_kernel<S, OBS>;
   const size_t smem = sizeof(int4) * n_ops + sizeof(double) * (2 * S + 2 * (size_t)n_nodes * S * S) +
-                      sizeof(double) * (size_t)n_slots * S * kWalkBlock;
+                      sizeof(double) * (size_t)n_slots * kWalkSites * S * kWalkBlock;
   *handled = false;
   if (smem > 100 * 1024) return RT_OK;        // fall back to the level-synchronous kernel
   RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -362,7 +403,7 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t tiles = (n_sites + kWalkBlock - 1) / kWalkBlock;
+  const int64_t tiles = (n_sites + kWalkBlock * kWalkSites - 1) / (kWalkBlock * kWalkSites);
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, kWalkBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots,

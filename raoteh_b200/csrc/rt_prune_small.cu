@@ -20,31 +20,50 @@ namespace {
 
 constexpr int kBlock = 128;
 
-// One observation row of one site, fetched one obs-consuming op ahead of its use.
-template <int S, int OBS>
-struct ObsVal {
-  int k;                    // OBS_CODES
-  unsigned long long mk;    // OBS_MASK
-  double d[S];              // OBS_DENSE
-  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride,
-                                        int64_t site) {
-    if (row < 0) return;
-    if (OBS == OBS_CODES) {
-      k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * stride + site];
-    } else if (OBS == OBS_MASK) {
-      mk = reinterpret_cast<const unsigned long long*>(obs)[(int64_t)row * stride + site];
-    } else {
-      const double* p = reinterpret_cast<const double*>(obs) + (int64_t)row * S * stride + site;
-#pragma unroll
-      for (int s = 0; s < S; ++s) d[s] = __ldcs(p + (int64_t)s * stride);
-    }
+// One observation row of one site, fetched one obs-consuming op ahead of its use
+// (one specialisation per encoding so that only the live member occupies registers).
+template <int S, int OBS> struct ObsVal;
+
+template <int S> struct ObsVal<S, OBS_CODES> {
+  int k;
+  __device__ __forceinline__ void init() { k = RT_MISSING; }
+  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site) {
+    if (row >= 0) k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * stride + site];
   }
+  __device__ __forceinline__ double get(int b) const { return (k == RT_MISSING || k == b) ? 1.0 : 0.0; }
+};
+
+template <int S> struct ObsVal<S, OBS_MASK> {
+  unsigned long long mk;
+  __device__ __forceinline__ void init() { mk = ~0ull; }
+  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site) {
+    if (row >= 0) mk = reinterpret_cast<const unsigned long long*>(obs)[(int64_t)row * stride + site];
+  }
+  __device__ __forceinline__ double get(int b) const { return ((mk >> b) & 1ull) ? 1.0 : 0.0; }
+};
+
+template <int S> struct ObsVal<S, OBS_DENSE> {
+  double d[S];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < S; ++s) d[s] = 1.0;
+  }
+  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site) {
+    if (row < 0) return;
+    const double* p = reinterpret_cast<const double*>(obs) + (int64_t)row * S * stride + site;
+#pragma unroll
+    for (int s = 0; s < S; ++s) d[s] = __ldcs(p + (int64_t)s * stride);
+  }
+  __device__ __forceinline__ double get(int b) const { return d[b]; }
 };
 
 // decoded op in shared memory: x = opcode, y = P offset in doubles (node*S*S),
-// z = stack offset in doubles (slot*S*kBlock) or unused, w = store index;
-// pre_s[ip] = observation row to prefetch when op ip is reached (-1 none)
-template <int S, int OBS, bool STORE, bool P_SMEM>
+// z = stack offset in doubles (slot*NS*S*kBlock) or obs row, w = store index;
+// pre_s[ip] = observation row to prefetch when op ip is reached (-1 none).
+// NS sites per thread: the op decode and every P element are loaded once and used
+// for NS sites (the kernel is issue-bound, not FLOP-bound), and NS independent
+// dependency chains hide the FP64 latency.
+template <int S, int OBS, bool STORE, bool P_SMEM, int NS>
 __global__ void __launch_bounds__(kBlock)
 prune_small_kernel(int64_t n_sites, int64_t stride,
                    const int4* __restrict__ program, int n_ops, int n_slots, int n_nodes,
@@ -62,7 +81,7 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
   double* rowsum_s = pi_s + S;
   double* P_s = rowsum_s + n_nodes * S;
   double* stk = P_s + (P_SMEM ? n_nodes * S * S : 0);
-  int* estk = reinterpret_cast<int*>(stk + n_slots * S * kBlock);
+  int* estk = reinterpret_cast<int*>(stk + n_slots * NS * S * kBlock);
 
   const int tid = threadIdx.x;
   for (int i = tid; i < n_ops; i += kBlock) {
@@ -71,20 +90,20 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
     int4 d;
     d.x = code;
     d.y = op.y * S * S;
-    d.z = (code == OP_MSG_SLOT || code == OP_STORE) ? op.z * S * kBlock : op.z;
+    d.z = (code == OP_MSG_SLOT || code == OP_STORE) ? op.z * NS * S * kBlock : op.z;
     d.w = op.w;
     prog_s[i] = d;
   }
   __syncthreads();
   if (tid == 0) {
-    // pre_s[ip]: row consumed by the next obs-consuming op after ip; pre_s[n_ops] unused.
+    // pre_s[ip]: row consumed by the next obs-consuming op after ip
     int nxt = -1;
     for (int i = n_ops - 1; i >= 0; --i) {
       pre_s[i] = nxt;
       const int code = prog_s[i].x;
       if (code == OP_MSG_OBS || code == OP_APPLY_OBS) nxt = prog_s[i].z;
     }
-    pre_s[n_ops] = nxt;     // first row of the program (slot n_ops is inside the padding)
+    pre_s[n_ops] = nxt;     // first row of the program
   }
   if (tid < S) pi_s[tid] = root_distn ? root_distn[tid] : 1.0;
   for (int i = tid; i < n_nodes * S; i += kBlock) {
@@ -97,130 +116,161 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
     for (int i = tid; i < n_nodes * S * S; i += kBlock) P_s[i] = P[i];
   __syncthreads();
 
-  const int64_t site = (int64_t)blockIdx.x * kBlock + tid;
-  const bool active = site < n_sites;
+  int64_t site[NS];
+  bool active[NS];
+#pragma unroll
+  for (int q = 0; q < NS; ++q) {
+    site[q] = ((int64_t)blockIdx.x * NS + q) * kBlock + tid;
+    active[q] = site[q] < n_sites;
+    if (!active[q]) site[q] = n_sites - 1;      // clamp: loads stay in range, results discarded
+  }
   double my_ll = 0.0;
 
-  if (active) {
-    double acc[S];
+  {
+    double acc[NS][S];
+    int esum[NS];
+    ObsVal<S, OBS> cur[NS], nxt[NS];
 #pragma unroll
-    for (int a = 0; a < S; ++a) acc[a] = 1.0;
-    int esum = 0;
-    ObsVal<S, OBS> cur, nxt;
-    nxt.k = RT_MISSING; nxt.mk = ~0ull;
+    for (int q = 0; q < NS; ++q) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) nxt.d[s] = 1.0;
-    nxt.fetch(obs, pre_s[n_ops], stride, site);
+      for (int a = 0; a < S; ++a) acc[q][a] = 1.0;
+      esum[q] = 0;
+      nxt[q].init();
+      cur[q].init();
+      nxt[q].fetch(obs, pre_s[n_ops], stride, site[q]);
+    }
 
     for (int ip = 0; ip < n_ops; ++ip) {
       const int4 op = prog_s[ip];
       const double* Pc = P_SMEM ? (P_s + op.y) : (P + op.y);
       if (op.x == OP_MSG_OBS || op.x == OP_APPLY_OBS) {
-        cur = nxt;
-        nxt.fetch(obs, pre_s[ip], stride, site);
+        const int row = pre_s[ip];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+          cur[q] = nxt[q];
+          nxt[q].fetch(obs, row, stride, site[q]);
+        }
       }
       switch (op.x) {
         case OP_MSG_SLOT: {
-          double v[S];
-          const double* sp = stk + op.z + tid;
+          double v[NS][S], m[NS][S];
 #pragma unroll
-          for (int b = 0; b < S; ++b) v[b] = sp[b * kBlock];
-          esum += estk[op.z / S + tid];
+          for (int q = 0; q < NS; ++q) {
+            const double* sp = stk + op.z + q * S * kBlock + tid;
 #pragma unroll
-          for (int a = 0; a < S; ++a) {
-            double m = 0.0;
+            for (int b = 0; b < S; ++b) v[q][b] = sp[b * kBlock];
+            esum[q] += estk[op.z / S + q * kBlock + tid];
 #pragma unroll
-            for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], v[b], m);
-            acc[a] *= m;
+            for (int a = 0; a < S; ++a) m[q][a] = 0.0;
           }
+#pragma unroll
+          for (int a = 0; a < S; ++a)
+#pragma unroll
+            for (int b = 0; b < S; ++b) {
+              const double p = Pc[a * S + b];
+#pragma unroll
+              for (int q = 0; q < NS; ++q) m[q][a] = fma(p, v[q][b], m[q][a]);
+            }
+#pragma unroll
+          for (int q = 0; q < NS; ++q)
+#pragma unroll
+            for (int a = 0; a < S; ++a) acc[q][a] *= m[q][a];
         } break;
         case OP_MSG_OBS: {
-          if (OBS == OBS_CODES) {
-            const int k = cur.k;
-            if (k == RT_MISSING) {
+          if constexpr (OBS == OBS_CODES) {
 #pragma unroll
-              for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y / S + a];
-            } else if (k < S) {
+            for (int q = 0; q < NS; ++q) {
+              const int k = cur[q].k;
+              if (k == RT_MISSING) {
 #pragma unroll
-              for (int a = 0; a < S; ++a) acc[a] *= Pc[a * S + k];
-            } else {
+                for (int a = 0; a < S; ++a) acc[q][a] *= rowsum_s[op.y / S + a];
+              } else if (k < S) {
 #pragma unroll
-              for (int a = 0; a < S; ++a) acc[a] = 0.0;
+                for (int a = 0; a < S; ++a) acc[q][a] *= Pc[a * S + k];
+              } else {
+#pragma unroll
+                for (int a = 0; a < S; ++a) acc[q][a] = 0.0;
+              }
             }
           } else {
-            double v[S];
-            if (OBS == OBS_MASK) {
+            double v[NS][S], m[NS][S];
 #pragma unroll
-              for (int b = 0; b < S; ++b) v[b] = ((cur.mk >> b) & 1ull) ? 1.0 : 0.0;
-            } else {
+            for (int q = 0; q < NS; ++q)
 #pragma unroll
-              for (int b = 0; b < S; ++b) v[b] = cur.d[b];
-            }
+              for (int b = 0; b < S; ++b) {
+                v[q][b] = cur[q].get(b);
+                m[q][b] = 0.0;
+              }
 #pragma unroll
-            for (int a = 0; a < S; ++a) {
-              double m = 0.0;
+            for (int a = 0; a < S; ++a)
 #pragma unroll
-              for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], v[b], m);
-              acc[a] *= m;
-            }
+              for (int b = 0; b < S; ++b) {
+                const double p = Pc[a * S + b];
+#pragma unroll
+                for (int q = 0; q < NS; ++q) m[q][a] = fma(p, v[q][b], m[q][a]);
+              }
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+#pragma unroll
+              for (int a = 0; a < S; ++a) acc[q][a] *= m[q][a];
           }
         } break;
         case OP_MSG_ONES: {
 #pragma unroll
-          for (int a = 0; a < S; ++a) acc[a] *= rowsum_s[op.y / S + a];
+          for (int a = 0; a < S; ++a) {
+            const double r = rowsum_s[op.y / S + a];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) acc[q][a] *= r;
+          }
         } break;
         case OP_APPLY_OBS: {
-          if (OBS == OBS_CODES) {
-            if (cur.k != RT_MISSING) {
 #pragma unroll
-              for (int a = 0; a < S; ++a) acc[a] = (a == cur.k) ? acc[a] : 0.0;
-            }
-          } else if (OBS == OBS_MASK) {
+          for (int q = 0; q < NS; ++q) {
 #pragma unroll
-            for (int a = 0; a < S; ++a) acc[a] = ((cur.mk >> a) & 1ull) ? acc[a] : 0.0;
-          } else {
-#pragma unroll
-            for (int a = 0; a < S; ++a) acc[a] *= cur.d[a];
+            for (int a = 0; a < S; ++a) acc[q][a] *= cur[q].get(a);
           }
         } break;
         case OP_STORE:
         case OP_ROOT: {
-          double mx = acc[0];
 #pragma unroll
-          for (int a = 1; a < S; ++a) mx = fmax(mx, acc[a]);
-          if (mx > 0.0) {
-            const int e = rt_exponent(mx);
-            const double sc = rt_pow2_neg(e);
+          for (int q = 0; q < NS; ++q) {
+            double mx = acc[q][0];
 #pragma unroll
-            for (int a = 0; a < S; ++a) acc[a] *= sc;
-            esum += e;
-          }
-          if (STORE && op.w >= 0) {
-            double* pp = partials + (int64_t)op.w * S * stride + site;
+            for (int a = 1; a < S; ++a) mx = fmax(mx, acc[q][a]);
+            if (mx > 0.0) {
+              const int e = rt_exponent(mx);
+              const double sc = rt_pow2_neg(e);
 #pragma unroll
-            for (int a = 0; a < S; ++a) __stcs(pp + (int64_t)a * stride, acc[a]);
-            if (exponents) exponents[(int64_t)op.w * stride + site] = esum;
-          }
-          if (op.x == OP_STORE) {
-            double* sp = stk + op.z + tid;
+              for (int a = 0; a < S; ++a) acc[q][a] *= sc;
+              esum[q] += e;
+            }
+            if (STORE && op.w >= 0 && active[q]) {
+              double* pp = partials + (int64_t)op.w * S * stride + site[q];
 #pragma unroll
-            for (int a = 0; a < S; ++a) sp[a * kBlock] = acc[a];
-            estk[op.z / S + tid] = esum;
+              for (int a = 0; a < S; ++a) __stcs(pp + (int64_t)a * stride, acc[q][a]);
+              if (exponents) exponents[(int64_t)op.w * stride + site[q]] = esum[q];
+            }
+            if (op.x == OP_STORE) {
+              double* sp = stk + op.z + q * S * kBlock + tid;
 #pragma unroll
-            for (int a = 0; a < S; ++a) acc[a] = 1.0;
-            esum = 0;
-          } else {
-            double lk = 0.0;
+              for (int a = 0; a < S; ++a) sp[a * kBlock] = acc[q][a];
+              estk[op.z / S + q * kBlock + tid] = esum[q];
 #pragma unroll
-            for (int a = 0; a < S; ++a) lk = fma(pi_s[a], acc[a], lk);
-            if (lk > 0.0) {
-              my_ll = log(lk) + (double)esum * RT_LN2;
-              loglik[site] = my_ll;
-              status[site] = RT_SITE_OK;
-            } else {
-              loglik[site] = -INFINITY;
-              status[site] = RT_SITE_STRUCTURAL_ZERO;
-              my_ll = 0.0;
+              for (int a = 0; a < S; ++a) acc[q][a] = 1.0;
+              esum[q] = 0;
+            } else if (active[q]) {
+              double lk = 0.0;
+#pragma unroll
+              for (int a = 0; a < S; ++a) lk = fma(pi_s[a], acc[q][a], lk);
+              if (lk > 0.0) {
+                const double ll = log(lk) + (double)esum[q] * RT_LN2;
+                loglik[site[q]] = ll;
+                status[site[q]] = RT_SITE_OK;
+                my_ll += ll;
+              } else {
+                loglik[site[q]] = -INFINITY;
+                status[site[q]] = RT_SITE_STRUCTURAL_ZERO;
+              }
             }
           }
         } break;
@@ -247,23 +297,25 @@ int launch_t(int64_t n_sites, int64_t stride, const int4* program, int n_ops, in
              int n_nodes, const double* P, const double* root_distn, const void* obs,
              double* partials, int32_t* exponents, double* loglik, int8_t* status,
              double* loglik_sum, cudaStream_t stream) {
+  constexpr int NS = (S <= 4) ? 2 : 1;      // sites per thread
   size_t base = (size_t)n_ops * sizeof(int4) + sizeof(int) * (((size_t)n_ops + 4) & ~(size_t)3) +
                 sizeof(double) * (S + (size_t)n_nodes * S);
-  size_t stack = (size_t)n_slots * S * kBlock * sizeof(double) + (size_t)n_slots * kBlock * sizeof(int);
+  size_t stack = (size_t)n_slots * NS * S * kBlock * sizeof(double) +
+                 (size_t)n_slots * NS * kBlock * sizeof(int);
   size_t pbytes = (size_t)n_nodes * S * S * sizeof(double);
   const size_t limit = 200 * 1024;
   const bool p_in_smem = base + stack + pbytes <= 96 * 1024;
   size_t smem = base + stack + (p_in_smem ? pbytes : 0);
   if (smem > limit) return RT_ERR_UNSUPPORTED;
-  const int64_t grid = (n_sites + kBlock - 1) / kBlock;
+  const int64_t grid = (n_sites + (int64_t)kBlock * NS - 1) / ((int64_t)kBlock * NS);
   if (p_in_smem) {
-    auto kern = prune_small_kernel<S, OBS, STORE, true>;
+    auto kern = prune_small_kernel<S, OBS, STORE, true, NS>;
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
                                                   P, root_distn, obs, partials, exponents, loglik,
                                                   status, loglik_sum);
   } else {
-    auto kern = prune_small_kernel<S, OBS, STORE, false>;
+    auto kern = prune_small_kernel<S, OBS, STORE, false, NS>;
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
                                                   P, root_distn, obs, partials, exponents, loglik,
