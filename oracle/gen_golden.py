@@ -263,8 +263,57 @@ def gen_sparse():
     print('mjp_sparse: %d cases (%d raise)' % (len(cases), sum('raises' in c for c in cases)))
 
 
+def gen_tolerance():
+    """_tmjp_dense.get_tolerance_summary on primary trajectories sampled by the reference's
+    own Rao-Teh sampler (toy model of _tmjp.get_example_tolerance_process_info)."""
+    ref_shim.load_reference()
+    import networkx as nx
+    import random
+    tmjpd = ref_shim.ref_module('_tmjp_dense')
+    sampler = ref_shim.ref_module('_sampler')
+    np.random.seed(7)
+    random.seed(7)
+    nprimary = 6
+    pre = np.array([[0, 1, 1, 0, 0, 0], [1, 0, 0, 1, 0, 0], [1, 0, 0, 1, 1, 0],
+                    [0, 1, 1, 0, 0, 1], [0, 0, 1, 0, 0, 1], [0, 0, 0, 1, 1, 0]], dtype=float)
+    Q_primary = pre - np.diag(pre.sum(axis=1))
+    Q_primary /= -np.dot(np.ones(nprimary) / nprimary, np.diag(Q_primary))
+    Q_nx = nx.DiGraph()
+    for i in range(nprimary):
+        for j in range(nprimary):
+            if i != j and Q_primary[i, j]:
+                Q_nx.add_edge(i, j, weight=float(Q_primary[i, j]))
+    primary_to_part = {0: 0, 1: 0, 2: 1, 3: 1, 4: 2, 5: 2}
+    T = nx.Graph()
+    for a, b, w in ((0, 1, 0.5), (1, 2, 0.7), (2, 3, 0.4), (2, 4, 0.9), (1, 5, 0.6)):
+        T.add_edge(a, b, weight=w)
+    root = 0
+    node_to_state = {0: 0, 3: 4, 4: 5, 5: 1}
+    distn = dict((i, 1.0 / nprimary) for i in range(nprimary))
+    cases = []
+    disease = [{0: {1}}, {0: {0}}, {0: {1}}]
+    for k, T_primary in enumerate(sampler.gen_histories(T, Q_nx, node_to_state, root=root,
+                                                        root_distn=distn, nhistories=8)):
+        for rate_on, rate_off, dd in ((1.0, 1.0, None), (0.3, 2.0, disease)):
+            out = tmjpd.get_tolerance_summary(primary_to_part, rate_on, rate_off, Q_primary,
+                                              T_primary, root, disease_data=dd)
+            cases.append(dict(
+                edges=[[int(a), int(b), float(T_primary[a][b]['weight']), int(T_primary[a][b]['state'])]
+                       for a, b in nx.bfs_edges(T_primary, root)],
+                root=root, rate_on=rate_on, rate_off=rate_off,
+                disease=None if dd is None else [dict((str(n), sorted(s)) for n, s in d.items()) for d in dd],
+                out=[float(x) for x in out]))
+    with open(os.path.join(OUT, 'tolerance_summary.json'), 'w') as f:
+        json.dump(dict(source='oracle/gen_golden.py gen_tolerance (reference _tmjp_dense.get_tolerance_summary)',
+                       Q_primary=Q_primary.tolist(),
+                       primary_to_part=dict((str(k), v) for k, v in primary_to_part.items()),
+                       cases=cases), f)
+    print('tolerance_summary: %d cases' % len(cases))
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    gen_tolerance()
     gen_sparse()
     gen_code2x3()
     gen_mjp_random()

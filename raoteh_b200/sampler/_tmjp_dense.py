@@ -1,0 +1,145 @@
+"""
+Tolerance-process expectations conditional on a primary trajectory:
+the dense reference functions of raoteh/sampler/_tmjp_dense.py that sit on the hot
+path of the Rao-Blackwellised tolerance sampler (examples/p53/blink.py:54-67).
+
+Given a primary trajectory, every tolerance class is an independent piecewise
+homogeneous 3-state MJP (off, on, absorbing) on the same tree
+(`get_inhomogeneous_mjp`, :965).  Its expectations are the generic hot path with
+S = 3 and one rate matrix per edge: rt_expm_batched, rt_support_sets,
+rt_prune_loglik, rt_posterior_stats, rt_frechet_contract replace
+pyfelscore.get_tolerance_rate_matrix (:239), the `kitchen_sink` calls (:297) and
+pyfelscore.get_tolerance_expectations (:339).
+"""
+from __future__ import division, print_function, absolute_import
+
+import networkx as nx
+import numpy as np
+from scipy import special
+
+from . import _core, _util
+from ..lowering import TreeSchedule, check_square_dense
+
+__all__ = []
+
+
+def get_two_state_tolerance_distn(rate_off, rate_on):
+    """raoteh/sampler/_tmjp_dense.py:352-377"""
+    if (rate_off < 0) or (rate_on < 0):
+        raise ValueError('rates must be non-negative')
+    total = rate_off + rate_on
+    if total <= 0:
+        raise ValueError('the total tolerance rate must be positive')
+    return np.array([rate_off, rate_on], dtype=float) / total
+
+
+def get_three_state_tolerance_distn(rate_off, rate_on):
+    """raoteh/sampler/_tmjp_dense.py:380-404"""
+    if (rate_off < 0) or (rate_on < 0):
+        raise ValueError('rates must be non-negative')
+    total = rate_off + rate_on
+    if total <= 0:
+        raise ValueError('the total tolerance rate must be positive')
+    return np.array([rate_off, rate_on, 0], dtype=float) / total
+
+
+def get_primary_state_to_absorption_rate(Q_primary, primary_to_part, tolerance_class):
+    """raoteh/sampler/_tmjp_dense.py:931-962"""
+    check_square_dense(Q_primary)
+    nprimary = len(primary_to_part)
+    out = {}
+    for sa in range(nprimary):
+        out[sa] = sum(Q_primary[sa, sb] for sb in range(nprimary)
+                      if sb != sa and primary_to_part[sb] == tolerance_class)
+    return out
+
+
+def get_inhomogeneous_mjp(primary_to_part, rate_on, rate_off, Q_primary, T_primary, root,
+                          T_primary_edges, tolerance_class):
+    """raoteh/sampler/_tmjp_dense.py:965-1085 (spec raoteh/sampler/_tmjp.py:815-902):
+    per edge of the primary trajectory, Q_tol = [[-on, on, 0], [off', -off'-abs, abs],
+    [0, 0, 0]] with off' = 0 and state 'off' forbidden at both ends where the primary
+    state belongs to the class.  Returns (T_tol, node_to_allowed_tolerances)."""
+    check_square_dense(Q_primary)
+    absorb = get_primary_state_to_absorption_rate(Q_primary, primary_to_part, tolerance_class)
+    T_tol = nx.Graph()
+    allowed = dict((n, {0, 1}) for n in T_primary)
+    for na, nb in T_primary_edges:
+        s = T_primary[na][nb]['state']
+        same = primary_to_part[s] == tolerance_class
+        off = 0.0 if same else rate_off
+        r = absorb[s]
+        Q = np.array([[-rate_on, rate_on, 0.0], [off, -off - r, r], [0.0, 0.0, 0.0]])
+        T_tol.add_edge(na, nb, weight=T_primary[na][nb]['weight'], Q=Q)
+        if same:
+            allowed[na].discard(0)
+            allowed[nb].discard(0)
+    return T_tol, allowed
+
+
+def get_expected_tolerance_history_statistics(T, node_to_allowed_states, root, root_distn=None):
+    """raoteh/sampler/_tmjp_dense.py:246-349 -> (dwell[2], root posterior[3],
+    transitions[2,2], absorption expectation)."""
+    if root not in T:
+        raise ValueError('the specified root is not in the tree')
+    sched = TreeSchedule.from_nx(T, root)
+    P, Qs = _core.expm_edges(sched, T, 3, None)
+    ev = _core.Evaluation(sched, P, root_distn, 3)
+    mask = _core.mask_from_allowed(sched, node_to_allowed_states, 3)
+    mask = ev.support(mask, passes=3)
+    ll, status, pmap = ev.upward_masks(mask)
+    if status != 0:
+        raise _util.NumericalZeroProb('the denominator is zero')
+    D, J = ev.downward()
+    M = ev.expectations(Qs, sched.length)
+    dwell = np.zeros(2)
+    trans = np.zeros((2, 2))
+    absorption = 0.0
+    for i in range(1, sched.n):
+        Q = Qs[i]
+        dwell[0] += M[i, 0, 0]
+        dwell[1] += M[i, 1, 1]
+        trans[0, 1] += Q[0, 1] * M[i, 0, 1]
+        trans[1, 0] += Q[1, 0] * M[i, 1, 0]
+        absorption += Q[1, 2] * M[i, 1, 1]
+    return dwell, D[0], trans, absorption
+
+
+def get_tolerance_summary(primary_to_part, rate_on, rate_off, Q_primary, T_primary, root,
+                          disease_data=None):
+    """raoteh/sampler/_tmjp_dense.py:724-855 -> the seven tolerance expectations."""
+    total_weight = T_primary.size(weight='weight')
+    nparts = len(set(primary_to_part.values()))
+    tolerance_distn = get_three_state_tolerance_distn(rate_off, rate_on)
+    edges = list(nx.bfs_edges(T_primary, root))
+    ngains = nlosses = dwell_on = initial_on = nabsorptions = 0.0
+    for tolerance_class in range(nparts):
+        T_tol, allowed = get_inhomogeneous_mjp(primary_to_part, rate_on, rate_off, Q_primary,
+                                               T_primary, root, edges, tolerance_class)
+        if disease_data is not None:
+            for node, tol_set in disease_data[tolerance_class].items():
+                allowed[node].intersection_update(tol_set)
+        dwell, post_root, trans, absorb = get_expected_tolerance_history_statistics(
+            T_tol, allowed, root, root_distn=tolerance_distn)
+        dwell_on += dwell[1]
+        ngains += trans[0, 1]
+        nlosses += trans[1, 0]
+        initial_on += post_root[1]
+        nabsorptions += absorb
+    initial_off = nparts - initial_on
+    dwell_off = total_weight * nparts - dwell_on
+    return (initial_on, initial_off, dwell_on, dwell_off, nabsorptions, ngains, nlosses)
+
+
+def get_tolerance_ll_contribs(rate_on, rate_off, total_tree_length,
+                              expected_initial_on, expected_initial_off,
+                              expected_dwell_on, expected_dwell_off,
+                              expected_nabsorptions, expected_ngains, expected_nlosses):
+    """raoteh/sampler/_tmjp_dense.py:858-928"""
+    tolerance_distn = get_three_state_tolerance_distn(rate_off, rate_on)
+    init_ll = (special.xlogy(expected_initial_on - 1, tolerance_distn[1]) +
+               special.xlogy(expected_initial_off, tolerance_distn[0]))
+    dwell_prim = -expected_nabsorptions
+    dwell_tol = -(expected_dwell_off * rate_on + (expected_dwell_on - total_tree_length) * rate_off)
+    trans_ll = special.xlogy(expected_ngains, rate_on) + special.xlogy(expected_nlosses, rate_off)
+    return init_ll, dwell_prim, dwell_tol, trans_ll

@@ -278,3 +278,25 @@ def test_gen_restricted_histories_input_validation(S):
         next(S._sampler.gen_restricted_histories(T, Q, {0: {0}, 7: {1}}, 0))
     with pytest.raises(ValueError):
         S._mjp_dense.get_likelihood(T, ok, 9, 2, Q_default=np.array([[-1., 1.], [1., -1.]]))
+
+
+def test_tolerance_summary_matches_reference_fixture():
+    """_tmjp_dense.get_tolerance_summary on primary trajectories sampled by
+    the reference's own Rao-Teh sampler (tests/golden/tolerance_summary.json)."""
+    from raoteh_b200.sampler import _tmjp_dense
+    g = load_golden('tolerance_summary.json')
+    Q_primary = np.array(g['Q_primary'])
+    primary_to_part = dict((int(k), v) for k, v in g['primary_to_part'].items())
+    for case in g['cases']:
+        T_primary = nx.Graph()
+        for a, b, w, s in case['edges']:
+            T_primary.add_edge(a, b, weight=w, state=s)
+        dd = None
+        if case['disease'] is not None:
+            dd = [dict((int(n), set(v)) for n, v in d.items()) for d in case['disease']]
+        out = _tmjp_dense.get_tolerance_summary(primary_to_part, case['rate_on'], case['rate_off'],
+                                                Q_primary, T_primary, case['root'], disease_data=dd)
+        assert_allclose(out, case['out'], rtol=1e-9, atol=1e-12)
+        contribs = _tmjp_dense.get_tolerance_ll_contribs(
+            case['rate_on'], case['rate_off'], T_primary.size(weight='weight'), *out)
+        assert all(np.isfinite(c) for c in contribs)
