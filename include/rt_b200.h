@@ -197,6 +197,107 @@ int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, in
                      int init_k, double* dwell_sum, double* trans_sum, int8_t* status,
                      void* stream);
 
+
+/*
+ * Warp-cooperative Rao-Teh kernels: one warp per (chain, site) trajectory.
+ *
+ * (1) Rao-Teh sweeps for 9 <= S <= 64 primary states (rt_raoteh_sweeps dispatches
+ *     here; n_parts = 0): lanes own the states of the FFBS messages.
+ * (2) The blocked Gibbs sampler of the compound TOLERANCE process
+ *     (raoteh/sampler/_sample_tmjp_dense.py:40-171 gen_histories_v1,
+ *     sparse twin _sample_tmjp.py:34-168): per sweep, Poisson events on the primary
+ *     trajectory (:116-124), primary states given all tolerance trajectories with
+ *     a chunk allowed iff none of its classes is ever off inside it
+ *     (resample_primary_states_v1 :175-371), then for every tolerance class
+ *     (lane = class) Poisson events (:146-155) and the 2-state FFBS with the class
+ *     forced on wherever the primary state belongs to it, plus per-node disease
+ *     data (resample_tolerance_states_v1 :374-506).  The merged trees and chunk
+ *     trees of the reference (_graph_transform.add_trajectories :508,
+ *     get_chunk_tree_type_b :298) are implicit in the per-edge event walk.
+ *     mode RT_TMJP_INIT_PRIMARY / RT_TMJP_INIT_TOLERANCE build the initial
+ *     feasible history (get_feasible_history :509-627: primary first, then one
+ *     tolerance event at a uniform time inside every primary segment).
+ * (3) The Rao-Blackwellised tolerance summary of a primary trajectory
+ *     (raoteh/sampler/_tmjp_dense.py:724-855 get_tolerance_summary ->
+ *     get_inhomogeneous_mjp :965, get_expected_tolerance_history_statistics :246,
+ *     pyfelscore.get_tolerance_rate_matrix :239 / get_tolerance_expectations :339,
+ *     closed forms raoteh/sampler/_linalg.py:14-118): lane = class, per segment
+ *     the 2x2 block of expm(t Q3) and its Frechet integrals in closed form.
+ *     mode RT_TMJP_SUMMARY, or flag RT_TMJP_F_SUMMARY after every sweep.
+ *
+ * Trajectory state, caller-owned device arrays:
+ *   p_node/p_cnt uint8, element (trajectory t, node v) at t*pn_traj_stride + v*pn_node_stride
+ *   p_total int32 [n_traj]; p_time float [n_traj][cap_p]; p_sb uint8 [n_traj][cap_p]
+ *       (same jump-list convention as rt_raoteh_sweeps)
+ *   t_node  uint32 [n_traj][n_nodes]          bit c = class c is ON at the node
+ *   t_cnt   uint8  [n_traj][n_nodes][n_parts]  toggles of class c on the edge above the node
+ *   t_total uint8  [n_traj][n_parts]
+ *   t_time  float  [n_traj][n_parts][cap_t]    toggle times, same ordering convention
+ * tol_obs (nullable): uint8 [n_tol_obs][n_parts][tol_obs_stride], bit0 = off allowed,
+ *   bit1 = on allowed (the reference's disease_data); tol_obs_slot int32 [n_nodes], -1 = none.
+ * status int8 [n_traj]: 0 ok, 1 infeasible (structural zero), 2 numerical zero in the
+ *   summary, 3 event capacity exceeded in a sweep, 4 jump capacity exceeded, 6 no feasible
+ *   tolerance history (disease data contradict the primary trajectory).
+ * Outputs (all nullable, += over trajectories and sweeps): prim_dwell [S], prim_trans [S*S]
+ *   (_mjp_dense.get_history_statistics, raoteh/sampler/_mjp_dense.py:150), tol_stats
+ *   [n_parts][4] = (root on, dwell on, gains, losses) of the SAMPLED tolerance
+ *   trajectories, summary_sum [8] = the 7 values of get_tolerance_summary (+ count);
+ *   summary_out [n_traj][8] = the same per trajectory (last sweep).
+ */
+#define RT_TMJP_INIT_PRIMARY 0
+#define RT_TMJP_INIT_TOLERANCE 1
+#define RT_TMJP_SWEEP 2
+#define RT_TMJP_SUMMARY 3
+#define RT_TMJP_F_STATS_PRIMARY 1
+#define RT_TMJP_F_STATS_TOLERANCE 2
+#define RT_TMJP_F_SUMMARY 4
+
+typedef struct rt_tmjp_args {
+  /* model and tree */
+  int32_t S, n_parts, n_nodes, n_ops, n_slots;
+  int32_t cap_p, cap_t, obs_kind;
+  const int32_t* program;      /* [n_ops][4] upward program */
+  const int32_t* parent;       /* [n_nodes] */
+  const double* length;        /* [n_nodes] */
+  const double* B;             /* [S][S] I + Q_primary/omega_p */
+  const double* rate_p;        /* [S] omega_p - q_s */
+  const double* pi_p;          /* [S] primary root distribution, NULL = ones */
+  const uint8_t* part;         /* [S] tolerance class of a primary state (n_parts > 0) */
+  const double* absorb;        /* [S][n_parts] sum of Q[s,s'] over s' != s in class c */
+  double rate_on, rate_off, omega_t;
+  /* observations */
+  const void* obs;             /* primary: codes or masks per site */
+  int64_t obs_stride;
+  const uint8_t* tol_obs;
+  const int32_t* tol_obs_slot;
+  int64_t tol_obs_stride;
+  /* trajectories */
+  int64_t n_traj, n_sites, traj0;
+  uint8_t* p_node;
+  uint8_t* p_cnt;
+  int64_t pn_traj_stride, pn_node_stride;
+  int32_t* p_total;
+  float* p_time;
+  uint8_t* p_sb;
+  uint32_t* t_node;
+  uint8_t* t_cnt;
+  uint8_t* t_total;
+  float* t_time;
+  int8_t* status;
+  /* control */
+  uint64_t seed;
+  int64_t sweep0;
+  int32_t n_sweeps, mode, init_k, flags;
+  /* outputs */
+  double* prim_dwell;
+  double* prim_trans;
+  double* tol_stats;
+  double* summary_sum;
+  double* summary_out;
+} rt_tmjp_args;
+
+int rt_tmjp_run(const rt_tmjp_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

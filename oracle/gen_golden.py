@@ -311,8 +311,100 @@ def gen_tolerance():
     print('tolerance_summary: %d cases' % len(cases))
 
 
+def _history_edges(T_aug, root):
+    import networkx as nx
+    return [(a, b, float(T_aug[a][b]['weight']), int(T_aug[a][b]['state']))
+            for a, b in nx.bfs_edges(T_aug, root)]
+
+
+def gen_tmjp_moments(nhistories=3000, burn=100):
+    """Moments of the reference's own blocked Gibbs sampler
+    (_sample_tmjp_dense.gen_histories_v1) on the toy tolerance model, with and without
+    disease data: per-state primary dwell, primary transition counts, and per class
+    (root on, dwell on, gains, losses).  Batch means give the Monte-Carlo standard errors."""
+    ref_shim.load_reference()
+    import networkx as nx
+    import random
+    tmjpd = ref_shim.ref_module('_tmjp_dense')
+    stm = ref_shim.ref_module('_sample_tmjp_dense')
+    nprimary = 6
+    pre = np.array([[0, 1, 1, 0, 0, 0], [1, 0, 0, 1, 0, 0], [1, 0, 0, 1, 1, 0],
+                    [0, 1, 1, 0, 0, 1], [0, 0, 1, 0, 0, 1], [0, 0, 0, 1, 1, 0]], dtype=float)
+    Q_primary = pre - np.diag(pre.sum(axis=1))
+    Q_primary /= -np.dot(np.ones(nprimary) / nprimary, np.diag(Q_primary))
+    primary_distn = np.ones(nprimary) / nprimary
+    primary_to_part = {0: 0, 1: 0, 2: 1, 3: 1, 4: 2, 5: 2}
+    nparts = 3
+    T = nx.Graph()
+    tree_edges = ((0, 1, 0.5), (1, 2, 0.7), (2, 3, 0.4), (2, 4, 0.9), (1, 5, 0.6))
+    for a, b, w in tree_edges:
+        T.add_edge(a, b, weight=w)
+    root = 0
+    node_to_state = {3: 4, 4: 5, 5: 1}
+    cases = []
+    for name, rate_on, rate_off, dd in (
+            ('plain', 0.7, 1.3, None),
+            ('disease', 0.7, 1.3, [{5: {1}, 3: {0}}, {4: {0}}, {5: {0, 1}}])):
+        np.random.seed(11)
+        random.seed(11)
+        ctm = tmjpd.CompoundToleranceModel(Q_primary, primary_distn, primary_to_part, rate_on, rate_off)
+        rows = []
+        for i, (T_prim, tol_trajs) in enumerate(stm.gen_histories_v1(
+                ctm, T, root, node_to_state, disease_data=dd, nhistories=burn + nhistories)):
+            if i < burn:
+                continue
+            dwell = np.zeros(nprimary)
+            trans = np.zeros((nprimary, nprimary))
+            for a, b in nx.bfs_edges(T_prim, root):
+                dwell[T_prim[a][b]['state']] += T_prim[a][b]['weight']
+            for v in T_prim:
+                if v != root and T_prim.degree(v) == 2:
+                    pred = [a for a, b in nx.bfs_edges(T_prim, root) if b == v][0]
+                    succ = [b for a, b in nx.bfs_edges(T_prim, root) if a == v][0]
+                    s0, s1 = T_prim[pred][v]['state'], T_prim[v][succ]['state']
+                    if s0 != s1:
+                        trans[s0, s1] += 1
+            tol = np.zeros((nparts, 4))
+            for c, tt in enumerate(tol_trajs):
+                bfs = list(nx.bfs_edges(tt, root))
+                first = [e for e in bfs if e[0] == root][0]
+                tol[c, 0] = tt[first[0]][first[1]]['state']
+                for a, b in bfs:
+                    if tt[a][b]['state']:
+                        tol[c, 1] += tt[a][b]['weight']
+                pred_of = dict((b, a) for a, b in bfs)
+                for a, b in bfs:
+                    if a in pred_of:
+                        s0, s1 = tt[pred_of[a]][a]['state'], tt[a][b]['state']
+                        # count a change once per node: only along the first outgoing edge
+                        if s0 != s1 and tt.degree(a) == 2:
+                            tol[c, 2 if s1 else 3] += 1
+            rows.append(np.concatenate([dwell, trans.ravel(), tol.ravel()]))
+        rows = np.array(rows)
+        nb = 30
+        per = len(rows) // nb
+        bm = rows[:nb * per].reshape(nb, per, -1).mean(axis=1)
+        cases.append(dict(name=name, rate_on=rate_on, rate_off=rate_off,
+                          disease=None if dd is None else [dict((str(n), sorted(s)) for n, s in d.items()) for d in dd],
+                          nhistories=int(len(rows)), mean=rows.mean(axis=0).tolist(),
+                          sem=(bm.std(axis=0, ddof=1) / np.sqrt(nb)).tolist()))
+        print(name, 'done', len(rows))
+    with open(os.path.join(OUT, 'tmjp_v1_moments.json'), 'w') as f:
+        json.dump(dict(source='oracle/gen_golden.py gen_tmjp_moments (reference '
+                              '_sample_tmjp_dense.gen_histories_v1, seed 11)',
+                       layout='mean/sem = [dwell[6], trans[6*6], tol[3*4] = (root on, dwell on, gains, losses)]',
+                       Q_primary=Q_primary.tolist(), primary_distn=primary_distn.tolist(),
+                       primary_to_part=dict((str(k), v) for k, v in primary_to_part.items()),
+                       tree_edges=[list(e) for e in tree_edges], root=root,
+                       node_to_state=dict((str(k), v) for k, v in node_to_state.items()),
+                       cases=cases), f)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'tmjp':
+        gen_tmjp_moments(int(sys.argv[2]) if len(sys.argv) > 2 else 3000)
+        sys.exit(0)
     gen_tolerance()
     gen_sparse()
     gen_code2x3()

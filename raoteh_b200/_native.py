@@ -42,6 +42,35 @@ EXPORTS = {
 }
 
 
+class TmjpArgs(ctypes.Structure):
+    """Mirror of `rt_tmjp_args` (include/rt_b200.h)."""
+    _fields_ = [
+        ('S', ctypes.c_int32), ('n_parts', ctypes.c_int32), ('n_nodes', ctypes.c_int32),
+        ('n_ops', ctypes.c_int32), ('n_slots', ctypes.c_int32),
+        ('cap_p', ctypes.c_int32), ('cap_t', ctypes.c_int32), ('obs_kind', ctypes.c_int32),
+        ('program', c_void_p), ('parent', c_void_p), ('length', c_void_p),
+        ('B', c_void_p), ('rate_p', c_void_p), ('pi_p', c_void_p),
+        ('part', c_void_p), ('absorb', c_void_p),
+        ('rate_on', ctypes.c_double), ('rate_off', ctypes.c_double), ('omega_t', ctypes.c_double),
+        ('obs', c_void_p), ('obs_stride', c_int64),
+        ('tol_obs', c_void_p), ('tol_obs_slot', c_void_p), ('tol_obs_stride', c_int64),
+        ('n_traj', c_int64), ('n_sites', c_int64), ('traj0', c_int64),
+        ('p_node', c_void_p), ('p_cnt', c_void_p),
+        ('pn_traj_stride', c_int64), ('pn_node_stride', c_int64),
+        ('p_total', c_void_p), ('p_time', c_void_p), ('p_sb', c_void_p),
+        ('t_node', c_void_p), ('t_cnt', c_void_p), ('t_total', c_void_p), ('t_time', c_void_p),
+        ('status', c_void_p),
+        ('seed', ctypes.c_uint64), ('sweep0', c_int64),
+        ('n_sweeps', ctypes.c_int32), ('mode', ctypes.c_int32), ('init_k', ctypes.c_int32),
+        ('flags', ctypes.c_int32),
+        ('prim_dwell', c_void_p), ('prim_trans', c_void_p), ('tol_stats', c_void_p),
+        ('summary_sum', c_void_p), ('summary_out', c_void_p),
+    ]
+
+
+EXPORTS['rt_tmjp_run'] = ([ctypes.POINTER(TmjpArgs), c_void_p], c_int)
+
+
 class NativeError(RuntimeError):
     pass
 

@@ -2,6 +2,7 @@
 #include "rt_common.cuh"
 #include "../../include/rt_b200.h"
 #include <stdio.h>
+#include <string.h>
 
 static thread_local char g_err[512] = "";
 
@@ -57,6 +58,8 @@ int rt_raoteh_dispatch(int, int, int, int64_t, int64_t, int64_t, int64_t, const 
                        const int32_t*, const double*, const double*, const double*, const double*,
                        const void*, int64_t, uint8_t*, float*, uint8_t*, uint8_t*, int32_t*, int,
                        uint64_t, int64_t, int, int, double*, double*, int8_t*, cudaStream_t);
+
+int rt_tmjp_dispatch(const rt_tmjp_args&, cudaStream_t);
 
 extern "C" {
 
@@ -178,11 +181,57 @@ int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, in
   if (traj_stride < n_traj || n_sites <= 0 || cap <= 0) return arg_error("sizes");
   if (n_traj <= 0) return RT_OK;
   ensure_pool_cached();
+  if ((S > 8 || S == 7) && S <= 64) {
+    // warp-per-trajectory kernel (csrc/rt_tmjp.cu) on the same trajectory layout
+    rt_tmjp_args A;
+    memset(&A, 0, sizeof(A));
+    A.S = S; A.n_parts = 0; A.n_nodes = n_nodes; A.n_ops = n_ops; A.n_slots = n_slots;
+    A.cap_p = cap; A.cap_t = 1; A.obs_kind = obs_kind;
+    A.program = program; A.parent = parent; A.length = length; A.B = B; A.rate_p = rate;
+    A.pi_p = root_distn; A.obs = obs; A.obs_stride = obs_stride;
+    A.n_traj = n_traj; A.n_sites = n_sites; A.traj0 = traj0;
+    A.p_node = node_state; A.p_cnt = ev_count; A.pn_traj_stride = 1; A.pn_node_stride = traj_stride;
+    A.p_total = ev_total; A.p_time = ev_time; A.p_sb = ev_sb; A.status = status;
+    A.seed = seed; A.sweep0 = sweep0; A.n_sweeps = n_sweeps;
+    A.mode = init_k >= 0 ? RT_TMJP_INIT_PRIMARY : RT_TMJP_SWEEP; A.init_k = init_k;
+    const bool st = dwell_sum != nullptr && trans_sum != nullptr && init_k < 0;
+    A.flags = st ? RT_TMJP_F_STATS_PRIMARY : 0;
+    A.prim_dwell = dwell_sum; A.prim_trans = trans_sum;
+    int rc = rt_tmjp_dispatch(A, (cudaStream_t)stream);
+    if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: shared-memory budget");
+    return rc;
+  }
   int rc = rt_raoteh_dispatch(S, obs_kind, n_nodes, n_traj, traj_stride, n_sites, traj0, program,
                               n_ops, n_slots, parent, length, B, rate, root_distn, obs, obs_stride,
                               node_state, ev_time, ev_sb, ev_count, ev_total, cap, seed, sweep0,
                               n_sweeps, init_k, dwell_sum, trans_sum, status, (cudaStream_t)stream);
   if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: S or shared-memory budget");
+  return rc;
+}
+
+int rt_tmjp_run(const rt_tmjp_args* a, void* stream) {
+  if (!a) return arg_error("null pointer");
+  const rt_tmjp_args& A = *a;
+  if (!A.program || !A.parent || !A.length || !A.B || !A.rate_p || !A.obs || !A.p_node ||
+      !A.p_cnt || !A.p_total || !A.p_time || !A.p_sb || !A.status)
+    return arg_error("null pointer");
+  if (A.S < 2 || A.S > 64) return unsupported("rt_tmjp_run needs 2 <= S <= 64");
+  if (A.n_parts < 0 || A.n_parts > 32) return unsupported("rt_tmjp_run needs n_parts <= 32");
+  if (A.n_parts > 0 && (!A.part || !A.absorb || !A.t_node || !A.t_cnt || !A.t_total || !A.t_time))
+    return arg_error("tolerance arrays missing");
+  if (A.n_parts > 0 && (!(A.rate_on > 0) || !(A.rate_off >= 0) || !(A.omega_t > 0)))
+    return arg_error("tolerance rates");
+  if (A.tol_obs && !A.tol_obs_slot) return arg_error("tol_obs without tol_obs_slot");
+  if (A.obs_kind != 0 && A.obs_kind != 1) return arg_error("rt_tmjp_run takes codes or masks");
+  if (A.cap_p <= 0 || A.cap_p > 4096 || A.cap_t <= 0 || A.cap_t > 255) return arg_error("capacities");
+  if ((int64_t)(A.n_parts + 2) * (A.n_ops + 1) >= 65536) return unsupported("program too long");
+  if (A.mode < 0 || A.mode > 3) return arg_error("mode");
+  if ((A.mode == RT_TMJP_INIT_TOLERANCE || A.mode == RT_TMJP_SUMMARY) && A.n_parts == 0)
+    return arg_error("mode needs tolerance classes");
+  if (A.n_traj <= 0) return RT_OK;
+  ensure_pool_cached();
+  int rc = rt_tmjp_dispatch(A, (cudaStream_t)stream);
+  if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: shared-memory budget");
   return rc;
 }
 

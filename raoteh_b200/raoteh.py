@@ -30,8 +30,8 @@ class RaoTehChains(object):
             raise ValueError('the uniformization factor must be greater than 1')
         Q = np.asarray(Q, dtype=np.float64)
         self.S = S = Q.shape[0]
-        if S not in (2, 3, 4, 5, 6, 8):
-            raise ValueError('the Rao-Teh kernel supports 2, 3, 4, 5, 6 or 8 states')
+        if not 2 <= S <= 64:
+            raise ValueError('the Rao-Teh kernels support 2..64 states')
         if obs.kind not in (OBS_CODES, OBS_MASK):
             raise ValueError('Rao-Teh sampling takes hard codes or allowed-state masks')
         self.sched = sched

@@ -1,0 +1,390 @@
+"""Warp-per-trajectory kernels (csrc/rt_tmjp.cu) on the GPU, through the C ABI (rt_tmjp_run,
+rt_raoteh_sweeps for S > 8):
+
+* K7  tolerance summary == the reference's _tmjp_dense.get_tolerance_summary on the golden
+      fixture (tests/golden/tolerance_summary.json), relative 1e-9;
+* K6w Rao-Teh sweeps for 9..64 states vs closed-form posterior expectations, |z| < 5;
+* K8  blocked Gibbs sampler of the compound tolerance process: structural invariants of
+      every sampled history and distributional agreement (|z| < 5) with the closed form of
+      the sampler's target law (oracle/np_tmjp.py), which tests/test_oracle_golden.py pins
+      to the moments of the reference's own gen_histories_v1.
+"""
+import numpy as np
+import pytest
+
+from helpers import load_golden
+from oracle import np_oracle, np_tmjp
+
+pytestmark = pytest.mark.gpu
+
+TOY_PRE = np.array([[0, 1, 1, 0, 0, 0], [1, 0, 0, 1, 0, 0], [1, 0, 0, 1, 1, 0],
+                    [0, 1, 1, 0, 0, 1], [0, 0, 1, 0, 0, 1], [0, 0, 0, 1, 1, 0]], dtype=float)
+
+
+def toy_model():
+    Q = TOY_PRE - np.diag(TOY_PRE.sum(axis=1))
+    Q /= -np.dot(np.ones(6) / 6, np.diag(Q))
+    part = np.array([0, 0, 1, 1, 2, 2])
+    return Q, np.ones(6) / 6, part
+
+
+def toy_tree():
+    from raoteh_b200.lowering import TreeSchedule
+    # nodes 0..5 in preorder: 0-1, 1-2, 2-3, 2-4, 1-5
+    parent = np.array([-1, 0, 1, 2, 2, 1], dtype=np.int32)
+    length = np.array([0.0, 0.5, 0.7, 0.4, 0.9, 0.6])
+    return TreeSchedule(parent, length)
+
+
+def _chains_for_fixture(sched, Q, part, rate_on, rate_off, n_traj, disease):
+    from raoteh_b200 import engine
+    from raoteh_b200.tmjp import ToleranceChains
+    codes = np.full((1, n_traj), 255, dtype=np.uint8)
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaf_nodes=sched.leaves[:1])
+    tol_obs = tol_nodes = None
+    if disease is not None:
+        nodes = sorted(set(int(n) for d in disease for n in d))
+        tol_nodes = [sched.node_index[n] for n in nodes]
+        tol_obs = np.full((len(nodes), 3, n_traj), 3, dtype=np.uint8)
+        for c, d in enumerate(disease):
+            for n, allowed in d.items():
+                bits = sum(1 << int(s) for s in allowed)
+                tol_obs[nodes.index(int(n)), c, :] = bits
+    return ToleranceChains(sched, Q, np.ones(6) / 6, dict(enumerate(part)), rate_on, rate_off, obs,
+                           n_chains=1, tol_obs=tol_obs, tol_obs_nodes=tol_nodes, cap_p=64, cap_t=16)
+
+
+def _fixture_trajectory(case, sched):
+    """edge list (na, nb, weight, state) of an augmented primary trajectory -> (node states,
+    dict child -> (jump times from the parent end, parent-side states))."""
+    base = set(sched.nodes)
+    succ = {}
+    for a, b, w, s in case['edges']:
+        succ.setdefault(a, []).append((b, w, s))
+    ns = np.zeros(sched.n, dtype=np.uint8)
+    jumps = {}
+    root = case['root']
+    ns[sched.node_index[root]] = succ[root][0][2]
+    stack = [root]
+    while stack:
+        a = stack.pop()
+        for b, w, s in succ.get(a, []):
+            # follow the chain of degree-2 extra nodes down to the next base node
+            times, states, t, cur_state = [], [], w, s
+            node = b
+            while node not in base:
+                (nb2, w2, s2), = succ[node]
+                if s2 != cur_state:
+                    times.append(t)
+                    states.append(cur_state)
+                    cur_state = s2
+                t += w2
+                node = nb2
+            c = sched.node_index[node]
+            np.testing.assert_allclose(t, sched.length[c], rtol=1e-9)
+            ns[c] = cur_state
+            jumps[c] = (times, states)
+            stack.append(node)
+    return ns, jumps
+
+
+def test_tolerance_summary_kernel_matches_reference_fixture():
+    g = load_golden('tolerance_summary.json')
+    Q = np.array(g['Q_primary'])
+    part = np.array([g['primary_to_part'][str(i)] for i in range(6)])
+    sched = toy_tree()
+    groups = {}
+    for case in g['cases']:
+        key = (case['rate_on'], case['rate_off'], repr(case['disease']))
+        groups.setdefault(key, []).append(case)
+    assert len(groups) >= 2
+    for (rate_on, rate_off, _), cases in groups.items():
+        ch = _chains_for_fixture(sched, Q, part, rate_on, rate_off, len(cases), cases[0]['disease'])
+        trajs = [_fixture_trajectory(c, sched) for c in cases]
+        ch.load_primary_trajectories(np.array([t[0] for t in trajs]), [t[1] for t in trajs])
+        out = ch.tolerance_summary().cpu().numpy()
+        want = np.array([c['out'] for c in cases])
+        # event times are stored in float32 on the device: 1e-6 relative on the inputs
+        np.testing.assert_allclose(out, want, rtol=2e-6, atol=1e-7)
+
+
+def test_tolerance_summary_kernel_matches_generic_path_fp64_times():
+    """Same quantity with jump times exactly representable in float32: relative 1e-9 against
+    the generic S = 3 per-edge-Q path of the oracle (np_oracle, pinned to the reference)."""
+    from raoteh_b200.sampler import _tmjp_dense  # noqa: F401  (mirror importable)
+    Q, pi, part = toy_model()
+    sched = toy_tree()
+    rng = np.random.default_rng(5)
+    n_traj = 12
+    ns = np.zeros((n_traj, sched.n), dtype=np.uint8)
+    jumps = []
+    # random trajectories on the toy tree with dyadic jump times
+    length = np.array([0.0, 0.5, 0.75, 0.375, 0.875, 0.625])
+    from raoteh_b200.lowering import TreeSchedule
+    sched = TreeSchedule(sched.parent, length)
+    nbrs = [np.nonzero(TOY_PRE[s])[0] for s in range(6)]
+    for t in range(n_traj):
+        ns[t, 0] = rng.integers(6)
+        ej = {}
+        for c in range(1, sched.n):
+            k = rng.integers(0, 4)
+            times = np.sort(rng.choice(np.arange(1, int(length[c] * 64)), size=k, replace=False)) / 64.0
+            cur = ns[t, sched.parent[c]]
+            sbs = []
+            for _ in range(k):
+                sbs.append(cur)
+                cur = rng.choice(nbrs[cur])
+            ns[t, c] = cur
+            ej[c] = (list(times), sbs)
+        jumps.append(ej)
+    for rate_on, rate_off in ((1.0, 1.0), (0.3, 2.0), (2.0, 0.0)):
+        ch = _chains_for_fixture(sched, Q, part, rate_on, rate_off, n_traj, None)
+        ch.load_primary_trajectories(ns, jumps)
+        out = ch.tolerance_summary().cpu().numpy()
+        for t in range(n_traj):
+            want = _oracle_summary(sched, Q, part, rate_on, rate_off, ns[t], jumps[t])
+            np.testing.assert_allclose(out[t], want, rtol=1e-9, atol=1e-12)
+
+
+def _oracle_summary(sched, Q, part, rate_on, rate_off, ns, jumps):
+    """get_tolerance_summary restated on the oracle's generic path: per class a 3-state
+    inhomogeneous MJP on the augmented tree (raoteh/sampler/_tmjp_dense.py:724-855, :965-1078)."""
+    n_parts = int(part.max()) + 1
+    absorb = np.zeros((6, n_parts))
+    off = Q - np.diag(np.diag(Q))
+    for c in range(n_parts):
+        absorb[:, c] = off[:, part == c].sum(axis=1)
+    # augmented tree: base nodes then jump nodes, in preorder
+    parent, length, seg_state = [-1], [0.0], [0]
+    index = {0: 0}
+
+    def add(par, t, s):
+        parent.append(par)
+        length.append(t)
+        seg_state.append(s)
+        return len(parent) - 1
+    for c in range(1, sched.n):
+        times, sbs = jumps[c]
+        cur = index[int(sched.parent[c])]
+        prev = 0.0
+        for tau, sb in zip(times, sbs):
+            cur = add(cur, tau - prev, sb)
+            prev = tau
+        index[c] = add(cur, sched.length[c] - prev, ns[c])
+    parent = np.array(parent)
+    length = np.array(length)
+    n = len(parent)
+    total = length.sum()
+    out = np.zeros(7)
+    distn = np.array([rate_off, rate_on, 0.0]) / (rate_on + rate_off)
+    for c in range(n_parts):
+        Qs = np.zeros((n, 3, 3))
+        allowed = np.ones((n, 1, 3), dtype=bool)
+        allowed[:, :, 2] = False
+        for b in range(1, n):
+            s = seg_state[b]
+            same = part[s] == c
+            w = 0.0 if same else rate_off
+            r = absorb[s, c]
+            Qs[b] = [[-rate_on, rate_on, 0], [w, -w - r, r], [0, 0, 0]]
+            if same:
+                allowed[b, :, 0] = False
+                allowed[parent[b], :, 0] = False
+        P = np_oracle.expm_edges(Qs, length, q_index=np.arange(n))
+        obs = np_oracle.Obs('dense', 3, 1, lik=allowed.astype(float), has=np.ones(n, dtype=bool))
+        r = np_oracle.expected_history_statistics(parent, length, Qs, P, obs, distn,
+                                                  q_index=np.arange(n))
+        M = r['M_edges']
+        for b in range(1, n):
+            out[2] += M[b, 1, 1]
+            out[5] += Qs[b, 0, 1] * M[b, 0, 1]
+            out[6] += Qs[b, 1, 0] * M[b, 1, 0]
+            out[4] += Qs[b, 1, 2] * M[b, 1, 1]
+        out[0] += r['root_post'][0][1]
+    out[1] = n_parts - out[0]
+    out[3] = total * n_parts - out[2]
+    return out
+
+
+# ---------------------------------------------------------------------------------------
+# K6w: plain Rao-Teh for 9..64 states
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize('S,n_leaves', [(11, 6), (20, 5), (40, 4)])
+def test_large_state_sweeps_match_closed_form(S, n_leaves):
+    from raoteh_b200 import synth, engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
+    rng = np.random.default_rng(300 + S)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.25, rng)
+    Q = rng.exponential(1.0, size=(S, S)) * (rng.random((S, S)) < 0.4)
+    Q += np.roll(np.eye(S), 1, axis=1) * 0.3      # keep it irreducible
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    Q /= np.abs(np.diag(Q)).mean()
+    pi = rng.dirichlet(np.ones(S) * 3)
+    n_sites = 2
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.1)
+    sched = TreeSchedule(parent, length)
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaves)
+    P = np_oracle.expm_edges(Q, length)
+    o = np_oracle.expected_history_statistics(
+        parent, length, Q, P, np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes), pi)
+    groups, n_chains, burn, n_sweeps = 16, 256, 60, 100
+    dwell = np.zeros((groups, S))
+    trans = np.zeros((groups, S, S))
+    for gidx in range(groups):
+        ch = RaoTehChains(sched, Q, obs, n_chains=n_chains, root_distn=pi, seed=2000 + gidx)
+        ch.sweep(burn, stats=False)
+        ch.sweep(n_sweeps)
+        ch.check()
+        dwell[gidx] = ch.dwell_sum.cpu().numpy() / (n_chains * n_sweeps)
+        trans[gidx] = ch.trans_sum.cpu().numpy() / (n_chains * n_sweeps)
+    np.testing.assert_allclose(dwell.sum(axis=1), length.sum() * n_sites, rtol=1e-5)
+    n_total = groups * n_chains * n_sweeps
+    _assert_z(dwell, o['dwell'], n_total)
+    _assert_z(trans.reshape(groups, -1), o['trans'].reshape(-1), n_total)
+    # structure of a few histories
+    ns, edges = ch.trajectory(3)
+    for c, (times, states) in edges.items():
+        assert states[0] == ns[parent[c]] and states[-1] == ns[c]
+        assert np.all(states[1:] != states[:-1])
+        for a, b in zip(states[:-1], states[1:]):
+            assert Q[a, b] > 0
+
+
+def _assert_z(got, want, n_total, zmax=5.0):
+    """|mean - want| < zmax * se; se from the spread over groups, floored by the Poisson
+    error sqrt(want / n_total) so that rare events (a handful of counts in the whole run,
+    possibly none) are judged fairly."""
+    groups = got.shape[0]
+    mean = got.mean(axis=0)
+    se = got.std(axis=0, ddof=1) / np.sqrt(groups)
+    for m, s, w in zip(mean, se, want):
+        if w == 0:
+            assert m == 0, (m, w)
+        else:
+            s = max(s, np.sqrt(abs(w) / n_total))
+            assert abs(m - w) < zmax * s + 1e-9, (m, w, s)
+
+
+# ---------------------------------------------------------------------------------------
+# K8: blocked Gibbs sampler of the tolerance process
+# ---------------------------------------------------------------------------------------
+def _toy_chains(n_chains, seed, disease, rate_on=0.7, rate_off=1.3, cap_p=64, cap_t=64):
+    from raoteh_b200 import engine
+    from raoteh_b200.tmjp import ToleranceChains
+    Q, pi, part = toy_model()
+    sched = toy_tree()
+    node_to_state = {3: 4, 4: 5, 5: 1}
+    leaves = np.array([3, 4, 5])
+    codes = np.array([[4], [5], [1]], dtype=np.uint8)
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaf_nodes=leaves)
+    tol_obs = tol_nodes = None
+    if disease is not None:
+        tol_nodes = sorted(set(n for d in disease for n in d))
+        tol_obs = np.full((len(tol_nodes), 3, 1), 3, dtype=np.uint8)
+        for c, d in enumerate(disease):
+            for n, allowed in d.items():
+                tol_obs[tol_nodes.index(n), c, 0] = sum(1 << s for s in allowed)
+    ch = ToleranceChains(sched, Q, pi, dict(enumerate(part)), rate_on, rate_off, obs,
+                         n_chains=n_chains, tol_obs=tol_obs, tol_obs_nodes=tol_nodes,
+                         cap_p=cap_p, cap_t=cap_t, seed=seed)
+    return ch, sched, Q, pi, part, node_to_state
+
+
+DISEASE = [{5: {1}, 3: {0}}, {4: {0}}, {5: {0, 1}}]
+
+
+@pytest.mark.parametrize('disease', [None, DISEASE])
+def test_tolerance_histories_respect_structure(disease):
+    ch, sched, Q, pi, part, node_to_state = _toy_chains(64, 5, disease)
+    ch.initialize()
+    ch.sweep(20)
+    for t in range(0, ch.n_traj, 7):
+        ns, edges = ch.primary_trajectory(t)
+        for v, s in node_to_state.items():
+            assert ns[v] == s
+        tol = [ch.tolerance_trajectory(t, c) for c in range(3)]
+        for c, (times, states) in edges.items():
+            assert states[0] == ns[sched.parent[c]] and states[-1] == ns[c]
+            assert np.all(states[1:] != states[:-1])
+            assert np.all(np.diff(times) > 0) or len(times) < 2
+            for a, b in zip(states[:-1], states[1:]):
+                assert Q[a, b] > 0
+            # compatibility: the class of the primary state is ON throughout every segment
+            bounds = np.concatenate([[0.0], times, [sched.length[c]]])
+            for i, s in enumerate(states):
+                bits, tedges = tol[part[s]]
+                tt, ts = tedges[c]
+                tb = np.concatenate([[0.0], tt, [sched.length[c]]])
+                for j, on in enumerate(ts):
+                    overlap = min(bounds[i + 1], tb[j + 1]) - max(bounds[i], tb[j])
+                    if overlap > 1e-7:
+                        assert on == 1, (t, c, i, j)
+        for cls in range(3):
+            bits, tedges = tol[cls]
+            for c, (tt, ts) in tedges.items():
+                assert ts[0] == bits[sched.parent[c]] and ts[-1] == bits[c]
+                assert len(ts) == len(tt) + 1
+            if disease is not None:
+                for v, allowed in disease[cls].items():
+                    assert bits[v] in allowed
+
+
+@pytest.mark.parametrize('disease', [None, DISEASE])
+def test_tolerance_gibbs_matches_target_law(disease):
+    """Means over 16 groups x 512 chains x 100 sweeps vs the closed form of the sampler's
+    target law (oracle/np_tmjp.py), |z| < 5 per statistic."""
+    ch0, sched, Q, pi, part, node_to_state = _toy_chains(1, 0, disease)
+    want = np_tmjp.expected_sampler_statistics(
+        sched.parent, sched.length, Q, part, 3, pi, 0.7, 1.3, node_to_state, disease)
+    groups, n_chains, burn, n_sweeps = 16, 512, 80, 100
+    dwell = np.zeros((groups, 6))
+    trans = np.zeros((groups, 36))
+    tol = np.zeros((groups, 12))
+    for gidx in range(groups):
+        ch = _toy_chains(n_chains, 4000 + gidx, disease)[0]
+        ch.sweep(burn, stats=False)
+        ch.sweep(n_sweeps)
+        norm = n_chains * n_sweeps
+        dwell[gidx] = ch.prim_dwell.cpu().numpy() / norm
+        trans[gidx] = ch.prim_trans.cpu().numpy().ravel() / norm
+        tol[gidx] = ch.tol_stats.cpu().numpy().ravel() / norm
+    np.testing.assert_allclose(dwell.sum(axis=1), sched.length.sum(), rtol=1e-5)
+    n_total = groups * n_chains * n_sweeps
+    _assert_z(dwell, want['prim_dwell'], n_total)
+    _assert_z(trans, want['prim_trans'].ravel(), n_total)
+    _assert_z(tol, want['tol'].ravel(), n_total)
+
+
+def test_fused_summary_equals_separate_summary():
+    ch, sched, Q, pi, part, node_to_state = _toy_chains(256, 77, None)
+    ch.initialize()
+    ch.sweep(10, stats=False)
+    ch.reset_statistics()
+    ch.sweep(1, stats=False, summary=True)
+    fused = ch.summary_out[:, :7].cpu().numpy().copy()
+    fused_sum = ch.summary_sum.cpu().numpy().copy()
+    ch.reset_statistics()
+    sep = ch.tolerance_summary().cpu().numpy()
+    np.testing.assert_allclose(fused, sep, rtol=1e-12)
+    np.testing.assert_allclose(fused_sum[:7], sep.sum(axis=0), rtol=1e-10)
+    assert fused_sum[7] == 256
+    # identities of the summary (raoteh/sampler/_tmjp_dense.py:848-855)
+    np.testing.assert_allclose(sep[:, 0] + sep[:, 1], 3.0, rtol=1e-12)
+    np.testing.assert_allclose(sep[:, 2] + sep[:, 3], 3.0 * sched.length.sum(), rtol=1e-12)
+
+
+def test_tolerance_sampler_is_counter_based():
+    import torch
+    full = _toy_chains(24, 9, DISEASE)[0]
+    full.sweep(6)
+    lo = _toy_chains(24, 9, DISEASE)[0]
+    lo.n_traj = 10
+    hi = _toy_chains(24, 9, DISEASE)[0]
+    hi.traj0, hi.n_traj = 10, 14
+    for p in (lo, hi):
+        p.sweep(6)
+    assert bool((torch.cat([lo.p_node[:10], hi.p_node[:14]]) == full.p_node).all())
+    assert bool((torch.cat([lo.t_node[:10], hi.t_node[:14]]) == full.t_node).all())
+    assert bool((torch.cat([lo.p_total[:10], hi.p_total[:14]]) == full.p_total).all())
