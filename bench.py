@@ -17,7 +17,8 @@ pass + per-edge weights, Frechet contraction, (N > 1) one NCCL allreduce of
             statistics inside the timed region.
 `roofline`: dominant kernel of the step (downward pass), algorithmic bytes /
             CUDA-event duration against MEASURED_PEAKS.json hbm_gbs.
-`extra`   : C3 (61-state DMMA pruning) and C4 (Rao-Teh sweeps) figures.
+`extra`   : C3 (61-state DMMA pruning), C4 (Rao-Teh sweeps), C5 (tolerance model:
+            likelihood + blocked Gibbs sampler + summary) and 61-state Rao-Teh figures.
 `--impl reference`: the oracle port of the reference's CPU path (numpy/scipy,
             one process per host core) on a bounded sample of the same workload.
 """
@@ -364,6 +365,16 @@ def run_gpu(args):
             extra['c4_raoteh_sweeps'] = raoteh_bench.bench_c4(dev, args)
         except Exception as e:
             extra['c4_raoteh_sweeps'] = dict(error=repr(e))
+        try:
+            from raoteh_b200 import raoteh_bench
+            extra['c5_tolerance'] = raoteh_bench.bench_c5(dev, args)
+        except Exception as e:
+            extra['c5_tolerance'] = dict(error=repr(e))
+        try:
+            from raoteh_b200 import raoteh_bench
+            extra['codon_raoteh_sweeps'] = raoteh_bench.bench_codon_raoteh(dev, args)
+        except Exception as e:
+            extra['codon_raoteh_sweeps'] = dict(error=repr(e))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:

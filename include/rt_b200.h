@@ -251,6 +251,8 @@ int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, in
 #define RT_TMJP_F_STATS_PRIMARY 1
 #define RT_TMJP_F_STATS_TOLERANCE 2
 #define RT_TMJP_F_SUMMARY 4
+#define RT_TMJP_F_SKIP_PRIMARY 8    /* sweep: tolerance half only (phase-split launches) */
+#define RT_TMJP_F_SKIP_TOLERANCE 16 /* sweep: primary half only */
 
 typedef struct rt_tmjp_args {
   /* model and tree */

@@ -27,7 +27,13 @@
 
 namespace {
 
-constexpr int kWarps = 8;
+#ifndef RT_TMJP_WARPS
+#define RT_TMJP_WARPS 16     // warps (= trajectories in flight) per CTA
+#endif
+#ifndef RT_TMJP_MINB
+#define RT_TMJP_MINB 1       // CTAs per SM the register budget is sized for
+#endif
+constexpr int kWarps = RT_TMJP_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -912,7 +918,7 @@ __host__ __device__ inline Layout make_layout(int S, int SPAD, int n_parts, int 
 }
 
 template <int SP>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, RT_TMJP_MINB)
 tmjp_kernel(rt_tmjp_args A, Scratch X) {
   constexpr int SPAD = SP * 32;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1021,11 +1027,13 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
     } else if (A.mode == RT_TMJP_SWEEP) {
       for (int sw = 0; sw < A.n_sweeps; ++sw) {
         const uint32_t sweep = (uint32_t)(A.sweep0 + sw);
-        st = primary_pass<SP>(A, C, W, lane, traj, site, sweep, false, NP > 0, scr_beta, scr_cap,
-                              p_total, stats_p);
-        if (st == 0 || st == 4) primary_dirty = true;
-        if (st) break;
-        if (NP > 0) {
+        if (!(A.flags & RT_TMJP_F_SKIP_PRIMARY)) {
+          st = primary_pass<SP>(A, C, W, lane, traj, site, sweep, false, NP > 0, scr_beta, scr_cap,
+                                p_total, stats_p);
+          if (st == 0 || st == 4) primary_dirty = true;
+          if (st) break;
+        }
+        if (NP > 0 && !(A.flags & RT_TMJP_F_SKIP_TOLERANCE)) {
           st = tol_pass(A, C, W, lane, traj, site, sweep, false, p_total, scr_tu, scr_tb, scr_tc,
                         X.cap_ts, stats_t);
           if (st == 0 || st == 4) tol_dirty = true;

@@ -67,3 +67,99 @@ if __name__ == '__main__':
     import sys
     print(json.dumps(bench_c4(torch.device('cuda:0'), None,
                               n_chains=int(sys.argv[1]) if len(sys.argv) > 1 else 128)))
+
+
+def bench_c5(dev, args, n_sites=100_000, sweeps_per_launch=5, launches=3, loglik_sites=1_000_000):
+    """C5 legs: (a) 61-state pruning log-likelihood under the primary proposal model on the
+    25-taxon tree, (b) blocked Gibbs sweeps of the compound tolerance process (61 codons x 20
+    amino-acid classes) with the Rao-Blackwellised tolerance summary fused after every sweep."""
+    from . import engine, synth
+    from .lowering import TreeSchedule
+    from .tmjp import ToleranceChains
+    cfg = synth.config_c5(n_sites=max(n_sites, loglik_sites))
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    out = dict(workload='C5: 61 codons x 20 tolerance classes, 25-taxon tree (48 edges x 0.1)')
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # (a) likelihood
+    obs_ll = engine.Observations.from_leaf_codes(sched, cfg['codes'][:, :loglik_sites], cfg['leaves'], device=dev)
+    mjp = engine.TreeMJP(sched, cfg['Q_proposal'], root_distn=cfg['pi'], device=dev)
+    ll = torch.empty(loglik_sites, dtype=torch.float64, device=dev)
+    st = torch.empty(loglik_sites, dtype=torch.int8, device=dev)
+    mjp.transition_matrices()
+    for _ in range(2):
+        mjp.log_likelihood(obs_ll, out=(ll, st))
+    ts = []
+    for _ in range(3):
+        a, b = ev(), ev()
+        a.record()
+        mjp.log_likelihood(obs_ll, out=(ll, st))
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    out['loglik'] = dict(n_sites=loglik_sites, ms=ms, messages_per_sec=loglik_sites * sched.n_edges / (ms * 1e-3),
+                         finite=bool(torch.isfinite(ll).all()))
+    del obs_ll, mjp, ll, st
+    # (b) blocked Gibbs sampler
+    obs = engine.Observations.from_leaf_codes(sched, cfg['codes'][:, :n_sites], cfg['leaves'], device=dev)
+    ch = ToleranceChains(sched, cfg['Q'], cfg['pi'], dict(enumerate(cfg['part'])), cfg['rate_on'],
+                         cfg['rate_off'], obs, n_chains=1, tol_obs=cfg['tol_obs'][:, :, :n_sites],
+                         tol_obs_nodes=cfg['tol_obs_nodes'], cap_p=96, cap_t=48, seed=20260205, device=dev)
+    k = ch.initialize()
+    ch.sweep(3, stats=False)
+    torch.cuda.synchronize()
+    res = {}
+    for name, summary in (('sweep', False), ('sweep_plus_summary', True)):
+        ts = []
+        for _ in range(launches):
+            a, b = ev(), ev()
+            a.record()
+            ch.sweep(sweeps_per_launch, stats=True, summary=summary)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.mean(ts))
+        res[name] = dict(ms_per_launch=ms, sweeps_per_sec=ch.n_traj * sweeps_per_launch / (ms * 1e-3))
+    a, b = ev(), ev()
+    a.record()
+    ch.tolerance_summary()
+    b.record()
+    torch.cuda.synchronize()
+    res['summary_only'] = dict(ms=a.elapsed_time(b), trajectories_per_sec=ch.n_traj / (a.elapsed_time(b) * 1e-3))
+    out['gibbs'] = dict(n_trajectories=ch.n_traj, init_events_per_edge=k, sweeps_per_launch=sweeps_per_launch,
+                        mean_primary_jumps=float(ch.p_total.double().mean()),
+                        mean_tolerance_toggles_per_class=float(ch.t_total.double().mean()),
+                        omega_primary=ch.omega_p, omega_tolerance=ch.omega_t, **res)
+    return out
+
+
+def bench_codon_raoteh(dev, args, n_sites=20_000, n_chains=4, sweeps_per_launch=5, launches=3):
+    """Plain Rao-Teh sweeps of the 61-state codon model on the C3 tree (warp-per-trajectory)."""
+    from . import engine, synth
+    from .lowering import TreeSchedule
+    from .raoteh import RaoTehChains
+    cfg = synth.config_c3(n_sites=n_sites)
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'], device=dev)
+    omega = 2 * float(np.max(-np.diag(cfg['Q'])))
+    cap = int(max(4 * omega * cfg["length"].sum() + 64, 2 * (sched.n - 1)))   # room for the initial history
+    ch = RaoTehChains(sched, cfg['Q'], obs, n_chains=n_chains, root_distn=cfg['pi'], seed=20260202,
+                      cap=cap, device=dev)
+    k = ch.initialize()
+    ch.sweep(3, stats=False)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(launches):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ch.sweep(sweeps_per_launch)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ch.check()
+    ms = float(np.mean(ts))
+    return dict(workload='61-state codon Rao-Teh, 128-leaf tree, %d chains x %d sites' % (n_chains, n_sites),
+                n_trajectories=ch.n_traj, cap=cap, init_events_per_edge=k, ms_per_launch=ms,
+                sweeps_per_sec=ch.n_traj * sweeps_per_launch / (ms * 1e-3),
+                mean_real_jumps_per_trajectory=float(ch.ev_total.double().mean()),
+                expected_candidate_events_per_sweep=float(omega * cfg['length'].sum()))

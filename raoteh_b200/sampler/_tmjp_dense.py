@@ -143,3 +143,89 @@ def get_tolerance_ll_contribs(rate_on, rate_off, total_tree_length,
     dwell_tol = -(expected_dwell_off * rate_on + (expected_dwell_on - total_tree_length) * rate_off)
     trans_ll = special.xlogy(expected_ngains, rate_on) + special.xlogy(expected_nlosses, rate_off)
     return init_ll, dwell_prim, dwell_tol, trans_ll
+
+
+# ---------------------------------------------------------------------------
+# the compound tolerance model (raoteh/sampler/_tmjp_dense.py:35-179)
+# ---------------------------------------------------------------------------
+class CompoundToleranceModel(object):
+    """Read-only description of the compound process: dense primary rate matrix with
+    diagonal, primary distribution (1d ndarray), primary state -> tolerance class, blink
+    rates.  Same attributes as raoteh/sampler/_tmjp_dense.py:35-82; init_compound() builds
+    the compound state space exactly as :84-179."""
+
+    def __init__(self, Q_primary, primary_distn, primary_to_part, rate_on, rate_off):
+        self.Q_primary = Q_primary
+        self.primary_distn = primary_distn
+        self.primary_to_part = primary_to_part
+        self.rate_on = rate_on
+        self.rate_off = rate_off
+        self.nprimary = len(primary_to_part)
+        self.nparts = len(set(primary_to_part.values()))
+        self.ncompound = int(np.ldexp(self.nprimary, self.nparts))
+        self.tolerance_distn = get_two_state_tolerance_distn(rate_off, rate_on)
+        self.Q_compound = None
+        self.compound_distn = None
+        self.compound_to_primary = None
+        self.compound_to_tolerances = None
+
+    def init_compound(self):
+        import itertools
+        if self.Q_compound is not None:
+            raise Exception('compound attributes should be initialized only once')
+        if self.ncompound > 1e6:
+            raise Exception('the compound state space is too big')
+        self.compound_to_primary = []
+        self.compound_to_tolerances = []
+        for primary, tolerances in itertools.product(
+                range(self.nprimary), itertools.product((0, 1), repeat=self.nparts)):
+            self.compound_to_primary.append(primary)
+            self.compound_to_tolerances.append(tolerances)
+        prim = np.array(self.compound_to_primary)
+        tols = np.array(self.compound_to_tolerances)
+        part_of = np.array([self.primary_to_part[p] for p in range(self.nprimary)])
+        n = self.ncompound
+        own_on = tols[np.arange(n), part_of[prim]] == 1
+        # P(tolerances) over the classes other than the primary state's own
+        logp = np.where(tols == 1, self.tolerance_distn[1], self.tolerance_distn[0]).astype(float)
+        logp[np.arange(n), part_of[prim]] = 1.0
+        self.compound_distn = np.where(own_on, np.asarray(self.primary_distn)[prim] * logp.prod(axis=1), 0.0)
+        for name, d in (('primary', np.asarray(self.primary_distn)), ('tolerance', self.tolerance_distn),
+                        ('compound', self.compound_distn)):
+            if not np.allclose(d.sum(), 1):
+                raise Exception('internal error')
+        Q = np.zeros((n, n), dtype=float)
+        diff = tols[:, None, :] != tols[None, :, :]
+        hdist = diff.sum(axis=2)
+        same_prim = prim[:, None] == prim[None, :]
+        # one tolerance change, same primary state, not the primary state's own class
+        ii, jj = np.nonzero((hdist == 1) & same_prim)
+        cls = diff[ii, jj].argmax(axis=1)
+        ok = cls != part_of[prim[ii]]
+        ii, jj, cls = ii[ok], jj[ok], cls[ok]
+        Q[ii, jj] = np.where(tols[jj, cls] == 1, self.rate_on, self.rate_off)
+        # a primary change into a tolerated class, tolerances unchanged
+        ii, jj = np.nonzero((hdist == 0) & ~same_prim)
+        ok = (tols[ii, part_of[prim[jj]]] == 1) & (np.asarray(self.Q_primary)[prim[ii], prim[jj]] != 0)
+        ii, jj = ii[ok], jj[ok]
+        Q[ii, jj] = np.asarray(self.Q_primary)[prim[ii], prim[jj]]
+        Q -= np.diag(Q.sum(axis=1))
+        self.Q_compound = Q
+
+
+def get_tolerance_rate_matrix(rate_off, rate_on):
+    """raoteh/sampler/_tmjp_dense.py:182-202"""
+    return np.array([[-rate_on, rate_on], [rate_off, -rate_off]], dtype=float)
+
+
+def get_primary_proposal_rate_matrix(Q_primary, primary_to_part, tolerance_distn):
+    """raoteh/sampler/_tmjp_dense.py:1081-1131: between-class rates scaled by P(on)."""
+    check_square_dense(Q_primary)
+    nprimary = len(primary_to_part)
+    part = np.array([primary_to_part[s] for s in range(nprimary)])
+    Q = np.array(Q_primary, dtype=float)
+    np.fill_diagonal(Q, 0.0)
+    cross = part[:, None] != part[None, :]
+    Q[cross] *= tolerance_distn[1]
+    Q -= np.diag(Q.sum(axis=1))
+    return Q

@@ -170,3 +170,60 @@ def config_c4(n_sites=10_000, seed=20260204, n_leaves=64):
     codes = simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.0)
     return dict(name='C4', parent=parent, length=length, leaves=leaves, Q=Q,
                 pi=pi, codes=codes, S=4)
+
+
+# topology of the 25-taxon mammalian p53 tree (examples/p53/p53S.const.tree), every branch 0.1
+_P53_TOPOLOGY = ((((((0, 1), 2), (((3, 4), 5), 6)), (7, 8)),
+                  ((((((9, 10), 11), (12, 13)), 14), (15, 16)), (17, 18))),
+                 (19, ((20, 21), ((22, 23), 24))))
+
+
+def tree_from_nested(nested, branch_length):
+    """Nested tuples of leaf labels -> (parent, length, leaves, leaf_labels) in DFS preorder."""
+    parent, leaves, labels = [], [], []
+
+    def walk(x, p):
+        i = len(parent)
+        parent.append(p)
+        if isinstance(x, tuple):
+            for ch in x:
+                walk(ch, i)
+        else:
+            leaves.append(i)
+            labels.append(x)
+    walk(nested, -1)
+    n = len(parent)
+    length = np.full(n, float(branch_length))
+    length[0] = 0.0
+    return (np.asarray(parent, dtype=np.int32), length, np.asarray(leaves, dtype=np.int32), labels)
+
+
+def tolerance_proposal(Q, part, p_on):
+    """Primary proposal rate matrix: between-class rates scaled by P(tolerance on)
+    (raoteh/sampler/_tmjp_dense.py:1081-1131)."""
+    Qp = Q - np.diag(np.diag(Q))
+    cross = part[:, None] != part[None, :]
+    Qp[cross] *= p_on
+    return Qp - np.diag(Qp.sum(axis=1))
+
+
+def config_c5(n_sites=1_000_000, seed=20260205):
+    """C5: p53-style tolerance MJP.  Primary = the C3 codon model with omega = 1
+    (examples/p53/blink.py:113-120), 20 amino-acid tolerance classes, rate_on = 0.21925,
+    rate_off = 0.78075 (:122-127), 25-taxon tree with all lengths 0.1; sites simulated forward
+    under the primary proposal model; disease data = tolerance states of the first leaf
+    ('Has') fully observed, Bernoulli(0.2 off) except the leaf codon's own class (:244-269)."""
+    rng = np.random.default_rng(seed)
+    parent, length, leaves, _ = tree_from_nested(_P53_TOPOLOGY, 0.1)
+    Q, pi, residues = mg94(omega=1.0)
+    aas = sorted(set(residues))
+    part = np.array([aas.index(r) for r in residues], dtype=np.int64)
+    rate_on, rate_off = 0.21925, 0.78075
+    Qp = tolerance_proposal(Q, part, rate_on / (rate_on + rate_off))
+    codes = simulate_leaf_codes(parent, length, leaves, Qp, pi, n_sites, rng, 0.0)
+    n_parts = len(aas)
+    tol = np.where(rng.random((n_parts, n_sites)) < 0.2, 1, 2).astype(np.uint8)   # bit0 off / bit1 on
+    tol[part[codes[0]], np.arange(n_sites)] = 2
+    return dict(name='C5', parent=parent, length=length, leaves=leaves, Q=Q, Q_proposal=Qp, pi=pi,
+                codes=codes, S=61, part=part, n_parts=n_parts, rate_on=rate_on, rate_off=rate_off,
+                tol_obs=tol[None], tol_obs_nodes=[int(leaves[0])])

