@@ -24,6 +24,10 @@ enum {
   OP_STORE = 4,
   OP_ROOT = 5
 };
+// flags in bits 8.. of the op code (raoteh_b200/lowering.py)
+#define OP_FLAG_FRESH (1 << 8)          // OP_MSG_SLOT: the child's partial was stored by the previous op
+#define OP_FLAG_KEEP_ON_CHIP (1 << 9)   // OP_STORE: the next op consumes this partial FRESH
+#define OP_FLAG_PARK (1 << 10)          // OP_STORE: a later, non-fresh op reads it back from its slot
 
 // ---- observation encodings ---------------------------------------------------
 enum {

@@ -195,8 +195,13 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
 // V/2 + V/4 + ... exchanges instead of V full reductions -- and then added to a per-CTA
 // accumulator in shared memory; one masked global atomicAdd per entry per CTA at the end.
 // ---------------------------------------------------------------------------------------
-constexpr int kWalkBlock = 128;
-constexpr int kWalkSites = 2;    // sites per thread
+#ifndef RT_WALK_PF
+#define RT_WALK_PF 0
+#endif
+#ifndef RT_WALK_BLOCK
+#define RT_WALK_BLOCK 128
+#endif
+constexpr int kWalkBlock = RT_WALK_BLOCK;
 
 template <int V>
 __device__ __forceinline__ void reduce_scatter_warp(double (&v)[V], int lane) {
@@ -224,6 +229,12 @@ __device__ __forceinline__ void reduce_scatter_warp(double (&v)[V], int lane) {
 }
 
 template <int S> struct WalkV { static constexpr int value = (S <= 4) ? 16 : (S == 5 ? 32 : 64); };
+// sites per thread: more sites amortise the per-op work (program decode, P loads, the
+// cross-lane reduction of W) over more arithmetic; bounded by registers
+#ifndef RT_WALK_NS
+#define RT_WALK_NS 2
+#endif
+template <int S> struct WalkNS { static constexpr int value = (S <= 4) ? RT_WALK_NS : 2; };
 
 // 1/x to ~1 ulp: hardware seed (rcp.approx.ftz.f64, ~20 bits, full double range) plus two
 // Newton steps.  Replaces the ~20-instruction IEEE division; the quotient is within 2 ulp,
@@ -245,30 +256,47 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
                  double* __restrict__ node_distn, double* __restrict__ W,
                  double* __restrict__ root_post_sum) {
   constexpr int V = WalkV<S>::value;
-  constexpr int NS = kWalkSites;                       // sites per thread (ILP + one butterfly for both)
+  constexpr int NS = WalkNS<S>::value;
+  constexpr int SP1 = S + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
-  double* pi_s = reinterpret_cast<double*>(prog_s + n_ops);
+  long long* off_s = reinterpret_cast<long long*>(prog_s + n_ops);   // [n_ops] element offset of the op's rows
+  double* pi_s = reinterpret_cast<double*>(off_s + n_ops);
   double* P_s = pi_s + S;                              // [n_nodes][S][S]
-  double* W_s = P_s + (size_t)n_nodes * S * S;         // [n_nodes][S*S] per-CTA accumulator
+  double* Pl_s = P_s + (size_t)n_nodes * S * S;        // [n_nodes][S][S+1]: columns + row sum (leaf edges)
+  double* W_s = Pl_s + (size_t)n_nodes * S * SP1;      // [n_nodes][S*S] per-CTA accumulator
   double* rp_s = W_s + (size_t)n_nodes * S * S;        // [S]
   double* stk = rp_s + S;                              // [n_slots][NS][S][kWalkBlock]
 
   const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < n_ops; i += kWalkBlock) prog_s[i] = program[i];
+  for (int i = tid; i < n_ops; i += kWalkBlock) {
+    const int4 op = program[i];
+    prog_s[i] = op;
+    const int code = op.x & 0xff;
+    long long off = 0;
+    if (code == OP_MSG_SLOT || code == OP_ROOT) off = (long long)op.w * S * stride;
+    else if (code == OP_MSG_OBS) off = (OBS == OBS_DENSE) ? (long long)op.z * S * stride : (long long)op.z * stride;
+    off_s[i] = off;
+  }
   if (tid < S) { pi_s[tid] = root_distn ? root_distn[tid] : 1.0; rp_s[tid] = 0.0; }
   for (int i = tid; i < n_nodes * S * S; i += kWalkBlock) { P_s[i] = P[i]; W_s[i] = 0.0; }
+  for (int i = tid; i < n_nodes * S; i += kWalkBlock) {
+    double t = 0.0;
+#pragma unroll
+    for (int b = 0; b < S; ++b) { const double v = P[(size_t)i * S + b]; Pl_s[i * SP1 + b] = v; t += v; }
+    Pl_s[i * SP1 + S] = t;
+  }
   __syncthreads();
 
   const int64_t tile_sites = (int64_t)kWalkBlock * NS;
   const int64_t tiles = (n_sites + tile_sites - 1) / tile_sites;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    int64_t site[NS];
+    const int64_t site0 = tile * tile_sites + tid;            // site of q: site0 + q*kWalkBlock
     bool live[NS];
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
-      site[q] = tile * tile_sites + q * kWalkBlock + tid;     // coalesced per q
-      live[q] = site[q] < n_sites && status[site[q]] == RT_SITE_OK;
+      const int64_t site = site0 + q * kWalkBlock;
+      live[q] = site < n_sites && status[site] == RT_SITE_OK;
     }
     double cur[NS][S];
 #pragma unroll
@@ -276,24 +304,45 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
 #pragma unroll
       for (int s = 0; s < S; ++s) cur[q][s] = 0.0;
 
-    for (int ip = n_ops - 1; ip >= 0; --ip) {
+    // The walk of one site is a serial chain, so the loads of op ip-1 (stored partial of an
+    // internal child, or the code byte of a leaf) are issued into a second register buffer
+    // before op ip is computed: ping-pong buffers, loop unrolled by two.
+    auto issue = [&](int j, double (&Lb)[NS][S], int (&kb)[NS]) {
+      if (j < 0) return;
+      const int4 nx = prog_s[j];
+      const int ncode = nx.x & 0xff;
+      if (ncode == OP_MSG_SLOT) {
+        const double* src = partials + off_s[j] + site0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q)
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            Lb[q][s] = live[q] ? __ldcs(&src[(int64_t)s * stride + q * kWalkBlock]) : 0.0;
+      } else if (ncode == OP_MSG_OBS && OBS == OBS_CODES) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(obs) + off_s[j] + site0;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) kb[q] = live[q] ? src[q * kWalkBlock] : 0;
+      }
+    };
+    auto do_op = [&](int ip, const double (&Lb)[NS][S], const int (&kb)[NS]) {
       const int4 op = prog_s[ip];
       const int code = op.x & 0xff;
       if (code == OP_ROOT) {
+        const double* src = partials + off_s[ip] + site0;
 #pragma unroll
         for (int q = 0; q < NS; ++q) {
           double tot = 0.0;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            cur[q][s] = live[q] ? partials[((int64_t)op.w * S + s) * stride + site[q]] * pi_s[s] : 0.0;
+            cur[q][s] = live[q] ? src[(int64_t)s * stride + q * kWalkBlock] * pi_s[s] : 0.0;
             tot += cur[q][s];
           }
           const double inv = tot > 0.0 ? 1.0 / tot : 0.0;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
             cur[q][s] *= inv;
-            if (node_distn && site[q] < n_sites)
-              node_distn[((int64_t)op.w * S + s) * stride + site[q]] = cur[q][s];
+            if (node_distn && site0 + q * kWalkBlock < n_sites)
+              node_distn[off_s[ip] + (int64_t)s * stride + site0 + q * kWalkBlock] = cur[q][s];
           }
         }
         if (root_post_sum) {
@@ -307,62 +356,104 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
           }
         }
       } else if (code == OP_STORE) {
+        // a marginal parked by a non-fresh OP_MSG_SLOT (a fresh one is still in `cur`)
+        if (op.x & OP_FLAG_PARK) {
 #pragma unroll
-        for (int q = 0; q < NS; ++q)
+          for (int q = 0; q < NS; ++q)
 #pragma unroll
-          for (int s = 0; s < S; ++s) cur[q][s] = stk[((op.z * NS + q) * S + s) * kWalkBlock + tid];
+            for (int s = 0; s < S; ++s) cur[q][s] = stk[((op.z * NS + q) * S + s) * kWalkBlock + tid];
+        }
       } else if (code <= OP_MSG_ONES) {
         const int c = op.y;
-        const double* Pc = P_s + c * S * S;
         double w[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) w[i] = 0.0;
+        if (code == OP_MSG_SLOT) {
+          // ---- internal child: its marginal D_c = L o (P^T G) is parked (or kept) ----
+          double Pr[S * S];
 #pragma unroll
-        for (int q = 0; q < NS; ++q) {
-          double L[S];
-          if (code == OP_MSG_SLOT) {
+          for (int i = 0; i < S * S; ++i) Pr[i] = P_s[c * S * S + i];
+          const bool fresh = (op.x & OP_FLAG_FRESH) != 0;   // next (reverse) op is the child's OP_STORE
 #pragma unroll
-            for (int s = 0; s < S; ++s)
-              L[s] = live[q] ? __ldcs(&partials[((int64_t)op.w * S + s) * stride + site[q]]) : 0.0;
-          } else if (code == OP_MSG_ONES) {
+          for (int q = 0; q < NS; ++q) {
+            double L[S];
 #pragma unroll
-            for (int s = 0; s < S; ++s) L[s] = live[q] ? 1.0 : 0.0;
-          } else if (OBS == OBS_CODES) {
-            const int k = live[q] ? reinterpret_cast<const uint8_t*>(obs)[(int64_t)op.z * stride + site[q]] : -1;
+            for (int s = 0; s < S; ++s) L[s] = Lb[q][s];
+            double G[S];
 #pragma unroll
-            for (int s = 0; s < S; ++s) L[s] = (k == RT_MISSING || k == s) ? 1.0 : 0.0;
-          } else if (OBS == OBS_MASK) {
-            const unsigned long long mk =
-                live[q] ? reinterpret_cast<const unsigned long long*>(obs)[(int64_t)op.z * stride + site[q]] : 0ull;
+            for (int a = 0; a < S; ++a) {
+              double m = 0.0;
 #pragma unroll
-            for (int s = 0; s < S; ++s) L[s] = ((mk >> s) & 1ull) ? 1.0 : 0.0;
-          } else {
-            const double* d = reinterpret_cast<const double*>(obs);
-#pragma unroll
-            for (int s = 0; s < S; ++s) L[s] = live[q] ? d[((int64_t)op.z * S + s) * stride + site[q]] : 0.0;
-          }
-          double G[S];
-#pragma unroll
-          for (int a = 0; a < S; ++a) {
-            double m = 0.0;
-#pragma unroll
-            for (int b = 0; b < S; ++b) m = fma(Pc[a * S + b], L[b], m);
-            G[a] = (cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
-          }
-          if (code == OP_MSG_SLOT) {   // the child is internal: park its marginal
+              for (int b = 0; b < S; ++b) m = fma(Pr[a * S + b], L[b], m);
+              G[a] = (cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
+            }
+            double t[S];
 #pragma unroll
             for (int b = 0; b < S; ++b) {
-              double t = 0.0;
+              double acc = 0.0;
 #pragma unroll
-              for (int a = 0; a < S; ++a) t = fma(G[a], Pc[a * S + b], t);
-              t *= L[b];
-              stk[((op.z * NS + q) * S + b) * kWalkBlock + tid] = t;
-              if (node_distn && site[q] < n_sites)
-                node_distn[((int64_t)op.w * S + b) * stride + site[q]] = t;
+              for (int a = 0; a < S; ++a) acc = fma(G[a], Pr[a * S + b], acc);
+              t[b] = acc * L[b];
+            }
+#pragma unroll
+            for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+#pragma unroll
+            for (int b = 0; b < S; ++b) {
+              if (fresh) cur[q][b] = t[b];
+              else stk[((op.z * NS + q) * S + b) * kWalkBlock + tid] = t[b];
+              if (node_distn && site0 + q * kWalkBlock < n_sites)
+                node_distn[off_s[ip] + (int64_t)b * stride + site0 + q * kWalkBlock] = t[b];
             }
           }
+        } else if (code == OP_MSG_OBS && OBS == OBS_CODES) {
+          // ---- observed leaf, hard code k: P L is column k of P (the row sum when missing) ----
+          const double* Pl = Pl_s + c * S * SP1;
 #pragma unroll
-          for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+          for (int q = 0; q < NS; ++q) {
+            const int k = kb[q];
+            const int col = k == RT_MISSING ? S : k;
+            double G[S], L[S];
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+              const double m = Pl[a * SP1 + col];
+              G[a] = (live[q] && cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
+              L[a] = (k == RT_MISSING || k == a) ? 1.0 : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+          }
+        } else {
+          // ---- leaf with a mask / dense emission row / no observation ----
+          double Pr[S * S];
+#pragma unroll
+          for (int i = 0; i < S * S; ++i) Pr[i] = P_s[c * S * S + i];
+#pragma unroll
+          for (int q = 0; q < NS; ++q) {
+            double L[S];
+            if (code == OP_MSG_ONES) {
+#pragma unroll
+              for (int s = 0; s < S; ++s) L[s] = live[q] ? 1.0 : 0.0;
+            } else if (OBS == OBS_MASK) {
+              const unsigned long long mk = live[q]
+                  ? reinterpret_cast<const unsigned long long*>(obs)[off_s[ip] + site0 + q * kWalkBlock] : 0ull;
+#pragma unroll
+              for (int s = 0; s < S; ++s) L[s] = ((mk >> s) & 1ull) ? 1.0 : 0.0;
+            } else {
+              const double* d = reinterpret_cast<const double*>(obs) + off_s[ip] + site0 + q * kWalkBlock;
+#pragma unroll
+              for (int s = 0; s < S; ++s) L[s] = live[q] ? d[(int64_t)s * stride] : 0.0;
+            }
+            double G[S];
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+              double m = 0.0;
+#pragma unroll
+              for (int b = 0; b < S; ++b) m = fma(Pr[a * S + b], L[b], m);
+              G[a] = (cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+          }
         }
         // W_c += sum over the warp's 32*NS sites of G (x) L
         reduce_scatter_warp<V>(w, lane);
@@ -376,7 +467,24 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
           if (2 * lane + 1 < S * S && w[1] != 0.0) atomicAdd(&W_s[c * S * S + 2 * lane + 1], w[1]);
         }
       }
+    };
+    double LA[NS][S], LB[NS][S];
+    int kA[NS], kB[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      kA[q] = 0; kB[q] = 0;
+#pragma unroll
+      for (int s = 0; s < S; ++s) { LA[q][s] = 0.0; LB[q][s] = 0.0; }
     }
+    int ip = n_ops - 1;
+    issue(ip, LA, kA);
+    for (; ip >= 1; ip -= 2) {
+      issue(ip - 1, LB, kB);
+      do_op(ip, LA, kA);
+      issue(ip - 2, LA, kA);
+      do_op(ip - 1, LB, kB);
+    }
+    if (ip == 0) do_op(0, LA, kA);
   }
   __syncthreads();
   for (int i = tid; i < n_nodes * S * S; i += kWalkBlock) {
@@ -391,9 +499,11 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
                 int n_nodes, const double* P, const double* root_distn, const void* obs,
                 const double* partials, const int8_t* status, double* node_distn, double* W,
                 double* root_post_sum, cudaStream_t stream, bool* handled) {
+  constexpr int NS = WalkNS<S>::value;
   auto kern = down_walk_kernel<S, OBS>;
-  const size_t smem = sizeof(int4) * n_ops + sizeof(double) * (2 * S + 2 * (size_t)n_nodes * S * S) +
-                      sizeof(double) * (size_t)n_slots * kWalkSites * S * kWalkBlock;
+  const size_t smem = (sizeof(int4) + sizeof(long long)) * n_ops +
+                      sizeof(double) * (2 * S + (size_t)n_nodes * (2 * S * S + S * (S + 1))) +
+                      sizeof(double) * (size_t)n_slots * NS * S * kWalkBlock;
   *handled = false;
   if (smem > 100 * 1024) return RT_OK;        // fall back to the level-synchronous kernel
   RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -403,7 +513,7 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t tiles = (n_sites + kWalkBlock * kWalkSites - 1) / (kWalkBlock * kWalkSites);
+  const int64_t tiles = (n_sites + kWalkBlock * NS - 1) / (kWalkBlock * NS);
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, kWalkBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots,
