@@ -57,6 +57,26 @@ template <int S> struct ObsVal<S, OBS_DENSE> {
   __device__ __forceinline__ double get(int b) const { return d[b]; }
 };
 
+// Optional: dense emission rows streamed through a per-thread ring in shared memory with
+// cp.async (RT_DENSE_RING rows in flight per site).  MEASURED SLOWER on B200 than the
+// one-row register prefetch (C2, 1e6 sites: ring 0/1/2/4 -> 0.287/0.360/0.392/0.524 ms): the
+// ring's shared memory costs more occupancy than the extra bytes in flight buy, and the
+// kernel's floor is its instruction issue (0.262 ms with 1-byte codes), so it is off (0).
+#ifndef RT_DENSE_RING
+#define RT_DENSE_RING 0
+#endif
+constexpr int kRing = RT_DENSE_RING;            // rows in flight
+constexpr int kRingSlots = kRing + 1;
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
 // decoded op in shared memory: x = opcode, y = P offset in doubles (node*S*S),
 // z = stack offset in doubles (slot*NS*S*kBlock) or obs row, w = store index;
 // pre_s[ip] = observation row to prefetch when op ip is reached (-1 none).
@@ -82,6 +102,10 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
   double* P_s = rowsum_s + n_nodes * S;
   double* stk = P_s + (P_SMEM ? n_nodes * S * S : 0);
   int* estk = reinterpret_cast<int*>(stk + n_slots * NS * S * kBlock);
+  // dense emissions only: ring [slot][site q][state][thread] and the obs rows in order of use
+  double* ring = reinterpret_cast<double*>(
+      (reinterpret_cast<uintptr_t>(estk + n_slots * NS * kBlock) + 7) & ~(uintptr_t)7);
+  int* orow_s = reinterpret_cast<int*>(ring + ((OBS == OBS_DENSE && kRing > 0) ? kRingSlots * NS * S * kBlock : 0));
 
   const int tid = threadIdx.x;
   for (int i = tid; i < n_ops; i += kBlock) {
@@ -104,6 +128,14 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
       if (code == OP_MSG_OBS || code == OP_APPLY_OBS) nxt = prog_s[i].z;
     }
     pre_s[n_ops] = nxt;     // first row of the program
+    if (OBS == OBS_DENSE && kRing > 0) {
+      int j = 0;
+      for (int i = 0; i < n_ops; ++i) {
+        const int code = prog_s[i].x;
+        if (code == OP_MSG_OBS || code == OP_APPLY_OBS) orow_s[j++] = prog_s[i].z;
+      }
+      for (int d = 0; d < kRing; ++d) orow_s[j++] = -1;
+    }
   }
   if (tid < S) pi_s[tid] = root_distn ? root_distn[tid] : 1.0;
   for (int i = tid; i < n_nodes * S; i += kBlock) {
@@ -137,18 +169,47 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
       esum[q] = 0;
       nxt[q].init();
       cur[q].init();
-      nxt[q].fetch(obs, pre_s[n_ops], stride, site[q]);
+      if (!(OBS == OBS_DENSE && kRing > 0)) nxt[q].fetch(obs, pre_s[n_ops], stride, site[q]);
+    }
+    int jobs = 0;                    // index of the next obs-consuming op (dense ring)
+    auto ring_issue = [&](int j) {   // start the copy of the j-th obs row into its ring slot
+      const int row = orow_s[j];
+      if (row >= 0) {
+        double* dst = ring + (size_t)(j % kRingSlots) * NS * S * kBlock + tid;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+          const double* src = reinterpret_cast<const double*>(obs) + (int64_t)row * S * stride + site[q];
+#pragma unroll
+          for (int b = 0; b < S; ++b) cp_async8(dst + (q * S + b) * kBlock, src + (int64_t)b * stride);
+        }
+      }
+      cp_async_commit();
+    };
+    if (OBS == OBS_DENSE && kRing > 0) {
+#pragma unroll
+      for (int d = 0; d < kRing; ++d) ring_issue(d);
     }
 
     for (int ip = 0; ip < n_ops; ++ip) {
       const int4 op = prog_s[ip];
       const double* Pc = P_SMEM ? (P_s + op.y) : (P + op.y);
       if (op.x == OP_MSG_OBS || op.x == OP_APPLY_OBS) {
-        const int row = pre_s[ip];
+        if constexpr (OBS == OBS_DENSE && kRing > 0) {
+          cp_async_wait<(kRing > 0 ? kRing - 1 : 0)>();          // the oldest row in flight has landed
+          const double* src = ring + (size_t)(jobs % kRingSlots) * NS * S * kBlock + tid;
 #pragma unroll
-        for (int q = 0; q < NS; ++q) {
-          cur[q] = nxt[q];
-          nxt[q].fetch(obs, row, stride, site[q]);
+          for (int q = 0; q < NS; ++q)
+#pragma unroll
+            for (int b = 0; b < S; ++b) cur[q].d[b] = src[(q * S + b) * kBlock];
+          ring_issue(jobs + kRing);            // reuses the slot read one obs op ago
+          ++jobs;
+        } else {
+          const int row = pre_s[ip];
+#pragma unroll
+          for (int q = 0; q < NS; ++q) {
+            cur[q] = nxt[q];
+            nxt[q].fetch(obs, row, stride, site[q]);
+          }
         }
       }
       switch (op.x) {
@@ -301,7 +362,9 @@ int launch_t(int64_t n_sites, int64_t stride, const int4* program, int n_ops, in
   size_t base = (size_t)n_ops * sizeof(int4) + sizeof(int) * (((size_t)n_ops + 4) & ~(size_t)3) +
                 sizeof(double) * (S + (size_t)n_nodes * S);
   size_t stack = (size_t)n_slots * NS * S * kBlock * sizeof(double) +
-                 (size_t)n_slots * NS * kBlock * sizeof(int);
+                 (size_t)n_slots * NS * kBlock * sizeof(int) + 8;
+  if (OBS == OBS_DENSE && kRing > 0)
+    stack += (size_t)kRingSlots * NS * S * kBlock * sizeof(double) + sizeof(int) * ((size_t)n_ops + kRing + 2);
   size_t pbytes = (size_t)n_nodes * S * S * sizeof(double);
   const size_t limit = 200 * 1024;
   const bool p_in_smem = base + stack + pbytes <= 96 * 1024;

@@ -27,14 +27,10 @@
 
 namespace {
 
-#ifndef RT_TMJP_WARPS
-#define RT_TMJP_WARPS 16     // warps (= trajectories in flight) per CTA
-#endif
-#ifndef RT_TMJP_MINB
-#define RT_TMJP_MINB 1       // CTAs per SM the register budget is sized for
-#endif
-constexpr int kWarps = RT_TMJP_WARPS;
-constexpr int kThreads = kWarps * 32;
+// warps (= trajectories in flight) per CTA: 16 when the per-warp shared-memory state fits
+// (measured best on C5: 16 warps per SM at 128 registers), else 8, 4 or 2; the register
+// budget is always sized for 16 warps per SM.
+constexpr int kMaxWarps = 16;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct Scratch {
@@ -884,7 +880,7 @@ struct Layout {     // dynamic shared memory carve-up (bytes)
 __host__ __device__ inline size_t al(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __host__ __device__ inline Layout make_layout(int S, int SPAD, int n_parts, int n_nodes, int n_ops,
-                                              int n_slots, int cap_p, int scr_cap) {
+                                              int n_slots, int cap_p, int scr_cap, int kWarps) {
   Layout L;
   size_t o = 0;
   L.prog = o; o += sizeof(int4) * (size_t)n_ops;
@@ -917,15 +913,16 @@ __host__ __device__ inline Layout make_layout(int S, int SPAD, int n_parts, int 
   return L;
 }
 
-template <int SP>
-__global__ void __launch_bounds__(kThreads, RT_TMJP_MINB)
+template <int SP, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, kMaxWarps / kWarps)
 tmjp_kernel(rt_tmjp_args A, Scratch X) {
   constexpr int SPAD = SP * 32;
+  constexpr int kThreads = kWarps * 32;
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ double total_len_s;
   const int S = A.S, NP = A.n_parts;
   const int scr_cap = X.scr_cap;
-  const Layout L = make_layout(S, SPAD, NP, A.n_nodes, A.n_ops, A.n_slots, A.cap_p, scr_cap);
+  const Layout L = make_layout(S, SPAD, NP, A.n_nodes, A.n_ops, A.n_slots, A.cap_p, scr_cap, kWarps);
   int4* prog_s = reinterpret_cast<int4*>(smem + L.prog);
   double* Bt_s = reinterpret_cast<double*>(smem + L.Bt);
   double* pi_s = reinterpret_cast<double*>(smem + L.pi_p);
@@ -1084,9 +1081,10 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
   if (A.summary_sum && tid < 8 && sum_s[tid] != 0.0) atomicAdd(&A.summary_sum[tid], sum_s[tid]);
 }
 
-template <int SP>
+template <int SP, int kWarps>
 int launch(const rt_tmjp_args& A, cudaStream_t stream) {
   constexpr int SPAD = SP * 32;
+  constexpr int kThreads = kWarps * 32;
   int dev = 0, n_sm = 148;
   RT_CUDA_CHECK(cudaGetDevice(&dev));
   RT_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -1099,9 +1097,9 @@ int launch(const rt_tmjp_args& A, cudaStream_t stream) {
   X.cap_ts = A.cap_t;
   if (A.mode == RT_TMJP_INIT_TOLERANCE) X.cap_ts = (A.n_nodes - 1) + A.cap_p;
   X.n_seg = (A.n_nodes - 1) + A.cap_p;
-  const Layout L = make_layout(A.S, SPAD, A.n_parts, A.n_nodes, A.n_ops, A.n_slots, A.cap_p, X.scr_cap);
+  const Layout L = make_layout(A.S, SPAD, A.n_parts, A.n_nodes, A.n_ops, A.n_slots, A.cap_p, X.scr_cap, kWarps);
   if (L.total > 220 * 1024) return RT_ERR_UNSUPPORTED;
-  auto kern = tmjp_kernel<SP>;
+  auto kern = tmjp_kernel<SP, kWarps>;
   RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   int per_sm = 1;
   RT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, L.total));
@@ -1135,8 +1133,17 @@ int launch(const rt_tmjp_args& A, cudaStream_t stream) {
 
 }  // namespace
 
+template <int SP>
+static int launch_fit(const rt_tmjp_args& A, cudaStream_t stream) {
+  int rc = launch<SP, 16>(A, stream);
+  if (rc == RT_ERR_UNSUPPORTED) rc = launch<SP, 8>(A, stream);
+  if (rc == RT_ERR_UNSUPPORTED) rc = launch<SP, 4>(A, stream);
+  if (rc == RT_ERR_UNSUPPORTED) rc = launch<SP, 2>(A, stream);
+  return rc;
+}
+
 int rt_tmjp_dispatch(const rt_tmjp_args& A, cudaStream_t stream) {
-  if (A.S <= 32) return launch<1>(A, stream);
-  if (A.S <= 64) return launch<2>(A, stream);
+  if (A.S <= 32) return launch_fit<1>(A, stream);
+  if (A.S <= 64) return launch_fit<2>(A, stream);
   return RT_ERR_UNSUPPORTED;
 }
