@@ -83,3 +83,46 @@ class ShardedEvaluation(object):
         out['loglik_local'] = r['loglik']
         out['site_range'] = (self.lo, self.hi)
         return out
+
+
+# ---------------------------------------------------------------------------------------
+# sharded samplers (Rao-Teh chains, tolerance chains)
+# ---------------------------------------------------------------------------------------
+def shard_trajectories(n_chains, n_sites, rank=None, world_size=None):
+    """Contiguous block (traj0, n_traj) of the flattened (chain, site) axis for `rank`.
+    Pass it to RaoTehChains / ToleranceChains as traj0= and n_traj=; the Philox key of a
+    trajectory is its GLOBAL index, so the sampled histories are those of one big run."""
+    lo, hi = shard_range(int(n_chains) * int(n_sites), rank, world_size)
+    return lo, hi - lo
+
+
+def pack_sampler_stats(chains):
+    """One flat fp64 vector of every accumulated sufficient statistic of a sampler shard:
+    RaoTehChains -> [dwell S | trans S*S]; ToleranceChains -> [prim_dwell S | prim_trans S*S |
+    tol_stats 4*n_parts | summary_sum 8]."""
+    if hasattr(chains, 'prim_dwell'):
+        parts = [chains.prim_dwell, chains.prim_trans, chains.tol_stats, chains.summary_sum]
+    else:
+        parts = [chains.dwell_sum, chains.trans_sum]
+    return torch.cat([p.reshape(-1) for p in parts])
+
+
+def unpack_sampler_stats(vec, S, n_parts=None):
+    o = 0
+    out = {}
+    out['dwell'] = vec[o:o + S]
+    o += S
+    out['trans'] = vec[o:o + S * S].reshape(S, S)
+    o += S * S
+    if n_parts is not None:
+        out['tol_stats'] = vec[o:o + 4 * n_parts].reshape(n_parts, 4)
+        o += 4 * n_parts
+        out['summary_sum'] = vec[o:o + 8]
+    return out
+
+
+def allreduce_sampler_stats(chains):
+    """The sampler path's only collective: one allreduce(sum, fp64) of the packed statistics."""
+    vec = pack_sampler_stats(chains)
+    allreduce_stats(vec)
+    return unpack_sampler_stats(vec, chains.S, getattr(chains, 'n_parts', None))

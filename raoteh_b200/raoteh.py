@@ -130,6 +130,16 @@ class RaoTehChains(object):
         self.dwell_sum.zero_()
         self.trans_sum.zero_()
 
+    _STATE = ('node_state', 'ev_count', 'ev_total', 'ev_time', 'ev_sb')
+
+    def snapshot(self):
+        """Copy of the trajectory state (for Metropolis-Hastings rejection)."""
+        return dict((k, getattr(self, k).clone()) for k in self._STATE)
+
+    def restore(self, snap):
+        for k in self._STATE:
+            getattr(self, k).copy_(snap[k])
+
     # -- host-side views --------------------------------------------------------
     def trajectory(self, t):
         """Trajectory t as per-edge arrays: dict child node -> (times from the parent

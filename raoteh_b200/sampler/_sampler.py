@@ -43,9 +43,9 @@ def _trajectory_to_graph(sched, states, ns, edges, next_node):
     return T_out
 
 
-def gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=None,
-                             uniformization_factor=2, nhistories=None, seed=None, cap=None):
-    """raoteh/sampler/_sampler.py:300-390 (generator of nx.Graph histories)."""
+def _make_chain(T, Q, node_to_allowed_states, root, root_distn, uniformization_factor, seed, cap):
+    """Validation and lowering shared by the history generators
+    (raoteh/sampler/_sampler.py:329-362, :431-470)."""
     bad = set(node_to_allowed_states) - set(T)
     if bad:
         raise ValueError('some of the nodes which have been annotated with state restrictions '
@@ -89,12 +89,67 @@ def gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=None
         chain.initialize()
     except RuntimeError:
         raise Exception('failed to find a feasible history')
+    return chain, sched, states
+
+
+def gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=None,
+                             uniformization_factor=2, nhistories=None, seed=None, cap=None):
+    """raoteh/sampler/_sampler.py:300-390 (generator of nx.Graph histories)."""
+    chain, sched, states = _make_chain(T, Q, node_to_allowed_states, root, root_distn,
+                                       uniformization_factor, seed, cap)
     next_node = max(T) + 1
     for i in itertools.count():
         ns, edges = chain.trajectory(0)
         yield _trajectory_to_graph(sched, states, ns, edges, next_node)
         if nhistories is not None and i + 1 >= nhistories:
             return
+        chain.sweep(1, stats=False)
+        chain.check()
+
+
+def gen_mh_histories(T, Q, node_to_allowed_states, target_log_likelihood_callback,
+                     root, root_distn=None, uniformization_factor=2, nhistories=None,
+                     seed=None, cap=None):
+    """raoteh/sampler/_sampler.py:393-551: Rao-Teh sweeps as Metropolis-Hastings proposals.
+    Yields (history, accept_flag); a rejected proposal re-yields the previous history.  The
+    proposal density is the trajectory likelihood under Q (_mjp.get_trajectory_log_likelihood,
+    :462-463), the target is the caller's callback on the history graph; the accept draw
+    uses Python's `random` like the reference (:527)."""
+    import random
+    chain, sched, states = _make_chain(T, Q, node_to_allowed_states, root, root_distn,
+                                       uniformization_factor, seed, cap)
+    next_node = max(T) + 1
+
+    def biased(T_aug):
+        return _mjp.get_trajectory_log_likelihood(T_aug, root, root_distn, Q)
+
+    T_prev = None
+    saved = None
+    ll_biased_prev = ll_target_prev = None
+    for i in itertools.count():
+        ns, edges = chain.trajectory(0)
+        T_cur = _trajectory_to_graph(sched, states, ns, edges, next_node)
+        if T_prev is None:
+            accept_flag = True
+        else:
+            if ll_biased_prev is None:
+                ll_biased_prev = biased(T_prev)
+            ll_biased_curr = biased(T_cur)
+            if ll_target_prev is None:
+                ll_target_prev = target_log_likelihood_callback(T_prev)
+            ll_target_curr = target_log_likelihood_callback(T_cur)
+            log_mh_ratio = ll_target_curr - ll_target_prev - ll_biased_curr + ll_biased_prev
+            accept_flag = bool(log_mh_ratio > 0 or random.random() < np.exp(log_mh_ratio))
+            if accept_flag:
+                ll_biased_prev, ll_target_prev = ll_biased_curr, ll_target_curr
+        if not accept_flag:
+            T_cur = T_prev
+            chain.restore(saved)          # the device trajectory goes back to the previous sample
+        yield T_cur, accept_flag
+        T_prev = T_cur
+        if nhistories is not None and i + 1 >= nhistories:
+            return
+        saved = chain.snapshot()
         chain.sweep(1, stats=False)
         chain.check()
 

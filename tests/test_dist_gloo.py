@@ -91,3 +91,48 @@ def test_sharded_evaluation_two_ranks_gloo():
         np.testing.assert_allclose(r[4], full['dwell'], rtol=1e-12)
         np.testing.assert_allclose(r[5], full['trans'], rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(r[6], full['root_post'].sum(axis=0), rtol=1e-12)
+
+
+class _FakeChains(object):
+    """Host stand-in with the statistic tensors of raoteh_b200.tmjp.ToleranceChains."""
+
+    def __init__(self, S, n_parts, traj0, n_traj):
+        g = torch.Generator().manual_seed(0)
+        # statistics are sums over trajectories: give trajectory t the contribution f(t)
+        t = torch.arange(traj0, traj0 + n_traj, dtype=torch.float64)
+        self.S, self.n_parts = S, n_parts
+        self.prim_dwell = torch.stack([(t * (s + 1)).sum() for s in range(S)])
+        self.prim_trans = torch.stack([(t % (k + 2)).sum() for k in range(S * S)]).reshape(S, S)
+        self.tol_stats = torch.stack([(t + k).sum() for k in range(4 * n_parts)]).reshape(n_parts, 4)
+        self.summary_sum = torch.stack([(t * 0 + 1).sum() * (k + 1) for k in range(8)])
+
+
+def _sampler_worker(rank, world_size, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    traj0, n_traj = rdist.shard_trajectories(3, 101)
+    out = rdist.allreduce_sampler_stats(_FakeChains(5, 3, traj0, n_traj))
+    q.put((rank, traj0, n_traj, out['dwell'].numpy().copy(), out['trans'].numpy().copy(),
+           out['tol_stats'].numpy().copy(), out['summary_sum'].numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_sharded_sampler_statistics_two_ranks_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert (res[0][1], res[0][2], res[1][1], res[1][2]) == (0, 152, 152, 151)
+    full = _FakeChains(5, 3, 0, 303)
+    for r in res:
+        np.testing.assert_allclose(r[3], full.prim_dwell.numpy(), rtol=1e-12)
+        np.testing.assert_allclose(r[4], full.prim_trans.numpy(), rtol=1e-12)
+        np.testing.assert_allclose(r[5], full.tol_stats.numpy(), rtol=1e-12)
+        np.testing.assert_allclose(r[6], full.summary_sum.numpy(), rtol=1e-12)

@@ -150,3 +150,47 @@ def test_infeasible_data_is_reported():
     ch = RaoTehChains(sched, Q, obs, n_chains=3, seed=1)
     with pytest.raises(RuntimeError):
         ch.initialize()
+
+
+def test_mh_histories_with_exact_target_always_accepts_and_biased_target_rejects():
+    """raoteh/sampler/_sampler.py:393-551.  With target == proposal the MH ratio is 1 and
+    every proposal is accepted; with a target that penalises transitions some proposals are
+    rejected, a rejected step re-yields the previous history object, and the sample mean of
+    the number of transitions drops."""
+    import functools
+    import random
+    import networkx as nx
+    from raoteh_b200.sampler import _sampler, _mjp
+    random.seed(5)
+    Q = nx.DiGraph()
+    for a, b, w in ((0, 1, 1.0), (1, 0, 0.5), (1, 2, 0.7), (2, 1, 0.9), (2, 0, 0.3), (0, 2, 0.4)):
+        Q.add_edge(a, b, weight=w)
+    T = nx.Graph()
+    for a, b, w in ((0, 1, 0.8), (1, 2, 0.6), (1, 3, 1.1), (0, 4, 0.9)):
+        T.add_edge(a, b, weight=w)
+    allowed = {0: {0, 1, 2}, 1: {0, 1, 2}, 2: {0}, 3: {2}, 4: {1}}
+    distn = {0: 0.3, 1: 0.3, 2: 0.4}
+    exact = functools.partial(_mjp.get_trajectory_log_likelihood, root=0, prior_root_distn=distn,
+                              Q_default=Q)
+    flags = [f for _, f in _sampler.gen_mh_histories(T, Q, allowed, exact, 0, root_distn=distn,
+                                                     nhistories=40, seed=1)]
+    assert all(flags)
+
+    def ntrans(T_aug):
+        return sum(1 for v in T_aug if v not in T)
+
+    def penalised(T_aug):
+        return exact(T_aug) - 1.5 * ntrans(T_aug)
+    prev, counts, rejected = None, [], 0
+    for T_aug, flag in _sampler.gen_mh_histories(T, Q, allowed, penalised, 0, root_distn=distn,
+                                                 nhistories=300, seed=2):
+        assert abs(T_aug.size(weight='weight') - T.size(weight='weight')) < 1e-5
+        if not flag:
+            rejected += 1
+            assert T_aug is prev
+        prev = T_aug
+        counts.append(ntrans(T_aug))
+    assert 10 < rejected < 290
+    plain = [ntrans(h) for h in _sampler.gen_restricted_histories(T, Q, allowed, 0, root_distn=distn,
+                                                                   nhistories=300, seed=3)]
+    assert np.mean(counts[50:]) < np.mean(plain[50:])
