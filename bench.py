@@ -343,8 +343,9 @@ def run_gpu(args):
                     frac=down_gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
                     traffic=ncu_traffic('down_walk_kernel<4, 0>'),
                     algorithmic_bytes_per_launch=N * down_b, ms=down_ms,
-                    note='S=4 walk is issue / FP64-pipe bound, not HBM bound (ncu: issue active 66%, '
-                         'fp64 pipe 36%, dram 12%); it reads each stored partial exactly once',
+                    note='S=4 walk is issue / FP64-pipe bound, not HBM bound (ncu, profiles/'
+                         'r1_ncu_full_summary.json: issue active 53%, fp64 pipe 38%, dram 18%); it reads '
+                         'each stored partial exactly once (dram bytes = algorithmic bytes)',
                     also=dict(kernel='prune_small_kernel<4,codes,store>', achieved=up_gbs,
                               frac=up_gbs / peaks['hbm_gbs'], ms=up_ms,
                               algorithmic_bytes_per_launch=N * up_b,
