@@ -37,7 +37,6 @@ struct Scratch {
   double* p_beta;      // [n_warps][scr_cap][SPAD]    primary: message just below every event
   float2* t_tu;        // [n_warps][cap_ts][32]       tolerance: (time, uniform) per event and lane
   double2* t_beta;     // [n_warps][cap_ts][32]
-  uint8_t* t_cnt;      // [n_warps][n_nodes][32]      tolerance: candidate events per edge and lane
   double2* seg;        // [n_warps][n_seg][32]        summary: message at the low end of every segment
   int scr_cap, cap_ts, n_seg;
 };
@@ -51,7 +50,7 @@ struct Cta {
   const float* rinv_p;
   const double* pi_p;
   const uint8_t* part;
-  const double* absorb;  // [S][n_parts]
+  const double* absorb;  // [S][n_parts][3]  (lam1, sq, r) of the tolerance block per state and class
   const int* tslot;      // [n_nodes] tolerance observation slot
   double* dwell_acc;     // [S]
   unsigned* trans_acc;   // [S*S]
@@ -66,6 +65,8 @@ struct Wp {
   uint8_t* psb;    // [cap_p]
   float* pt;       // [cap_p]
   uint32_t* tn;    // [n_nodes]  tolerance bits at the nodes
+  uint8_t* tc;     // [n_nodes][n_parts]  toggles of class c on the edge above a node
+  uint8_t* tcc;    // [n_nodes][32]       tolerance candidate events of the sweep, per lane
   float2* tu;      // [scr_cap]  (time, uniform) of the primary candidate events
   double* vec;     // [SPAD]
   double* stk;     // [n_slots][64]
@@ -175,8 +176,10 @@ __device__ int primary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
   }
   const bool tl = use_tol && lane < NP;
   const float* my_tt = A.t_time + ((size_t)traj * (size_t)(NP > 0 ? NP : 1) + (size_t)(tl ? lane : 0)) * (size_t)A.cap_t;
-  const uint8_t* my_tc = A.t_cnt + (size_t)traj * (size_t)A.n_nodes * (size_t)(NP > 0 ? NP : 1);
   int t_rd = tl ? A.cap_t - (int)A.t_total[(size_t)traj * NP + lane] : 0;
+  // the next toggle of this lane's class in pool order, loaded one consumption ahead so that
+  // its global-memory latency is never on the (serial) walk
+  float pend = (tl && t_rd < A.cap_t) ? my_tt[t_rd] : -1.0f;
   const uint32_t partmask = NP >= 32 ? FULL : ((1u << NP) - 1u);
 
   double acc[SP];
@@ -219,8 +222,8 @@ __device__ int primary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
           off_now = ~W.tn[c] & partmask;
           chunk_off = off_now;
           if (tl) {
-            my_k = my_tc[(size_t)c * NP + lane];
-            if (my_k > 0) my_next = my_tt[t_rd];
+            my_k = W.tc[c * NP + lane];
+            if (my_k > 0) my_next = pend;
           }
         }
       }
@@ -259,7 +262,8 @@ __device__ int primary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
               if (mine) {
                 ++t_rd;
                 --my_k;
-                my_next = my_k > 0 ? my_tt[t_rd] : -1.0f;
+                pend = t_rd < A.cap_t ? my_tt[t_rd] : -1.0f;
+                my_next = my_k > 0 ? pend : -1.0f;
               }
               pos = nt;
               continue;
@@ -357,6 +361,9 @@ __device__ int primary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
   int rdA = nA;
   int wr = A.cap_p;
   bool pool_overflow = false;
+  double bnext[SP];
+#pragma unroll
+  for (int j = 0; j < SP; ++j) bnext[j] = nA > 0 ? scr_beta[(size_t)(nA - 1) * SPAD + SP * lane + j] : 0.0;
   for (int ip = A.n_ops - 1; ip >= 0; --ip) {
     const int4 op = C.prog[ip];
     if ((op.x & 0xff) > OP_MSG_ONES) continue;
@@ -375,7 +382,11 @@ __device__ int primary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
 #pragma unroll
       for (int j = 0; j < SP; ++j) {
         const int s = SP * lane + j;
-        w[j] = C.Bt[s * SPAD + cur] * scr_beta[(size_t)rdA * SPAD + s];
+        w[j] = C.Bt[s * SPAD + cur] * bnext[j];
+      }
+      if (rdA > 0) {   // the record of the next event (whatever edge it is on) while this one is drawn
+#pragma unroll
+        for (int j = 0; j < SP; ++j) bnext[j] = scr_beta[(size_t)(rdA - 1) * SPAD + SP * lane + j];
       }
       int nxt = warp_sample<SP>(w, u_draw, lane);
       if (nxt < 0) nxt = cur;
@@ -405,7 +416,7 @@ __device__ int primary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
 // =====================================================================================
 __device__ int tol_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int lane, int64_t traj,
                         int64_t site, uint32_t sweep, bool init, int p_total, float2* scr_tu,
-                        double2* scr_b, uint8_t* scr_cnt, int cap_ts, bool stats) {
+                        double2* scr_b, int cap_ts, bool stats) {
   const int NP = A.n_parts;
   const bool tl = lane < NP;
   Philox rng;
@@ -420,8 +431,8 @@ __device__ int tol_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int la
   const float ri0 = r0 > 0.0f ? 1.0f / r0 : 0.0f, ri1 = r1 > 0.0f ? 1.0f / r1 : 0.0f;
   const double pi0 = A.rate_off / (A.rate_on + A.rate_off), pi1 = A.rate_on / (A.rate_on + A.rate_off);
   float* my_tt = A.t_time + ((size_t)traj * NP + (tl ? lane : 0)) * (size_t)A.cap_t;
-  uint8_t* my_tc = A.t_cnt + (size_t)traj * (size_t)A.n_nodes * NP;
   int rd = (tl && !init) ? A.cap_t - (int)A.t_total[(size_t)traj * NP + lane] : A.cap_t;
+  float pend = (tl && rd < A.cap_t) ? my_tt[rd] : -1.0f;   // next old toggle, one consumption ahead
   int prd = A.cap_p - p_total;
   double a0 = 1.0, a1 = 1.0;
   int nA = 0;
@@ -457,8 +468,8 @@ __device__ int tol_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int la
         int next_psb = pk > 0 ? W.psb[pr] : 0;
         bool need_on = C.part[pstate] == lane;
         int cur_t = (W.tn[c] >> lane) & 1;
-        int k_old = init ? 0 : my_tc[(size_t)c * NP + lane];
-        float next_old = k_old > 0 ? my_tt[rd] : -1.0f;
+        int k_old = init ? 0 : W.tc[c * NP + lane];
+        float next_old = k_old > 0 ? pend : -1.0f;
         float pos = tc;
         bool placed = false;
         while (true) {
@@ -532,12 +543,13 @@ __device__ int tol_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int la
             cur_t ^= 1;
             ++rd;
             --k_old;
-            next_old = k_old > 0 ? my_tt[rd] : -1.0f;
+            pend = rd < A.cap_t ? my_tt[rd] : -1.0f;
+            next_old = k_old > 0 ? pend : -1.0f;
           }
         }
         if (need_on) be0 = 0.0;
         if (kA > 255) overflow = true;
-        scr_cnt[(size_t)c * 32 + lane] = (uint8_t)(kA > 255 ? 255 : kA);
+        W.tcc[c * 32 + lane] = (uint8_t)(kA > 255 ? 255 : kA);
         if (kA > 0) {
           const double mx = fmax(be0, be1);
           if (mx > 0.0) {
@@ -591,20 +603,30 @@ __device__ int tol_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int la
   int wr = A.cap_t;
   bool pool_overflow = false;
   double dwell_on = 0.0, gains = 0.0, losses = 0.0;
+  float2 tu_next = make_float2(0.0f, 0.0f);
+  double2 b_next = make_double2(0.0, 0.0);
+  if (tl && nA > 0) {
+    tu_next = scr_tu[(size_t)(nA - 1) * 32 + lane];
+    b_next = scr_b[(size_t)(nA - 1) * 32 + lane];
+  }
   for (int ip = A.n_ops - 1; ip >= 0; --ip) {
     const int4 op = C.prog[ip];
     if ((op.x & 0xff) > OP_MSG_ONES) continue;
     const int c = op.y;
     int cur = (W.tn[C.par[c]] >> lane) & 1;
     if (tl) {
-      const int kA = scr_cnt[(size_t)c * 32 + lane];
+      const int kA = W.tcc[c * 32 + lane];
       const float tc = C.len[c];
       float prev = 0.0f;
       int kept = 0;
       for (int e = 0; e < kA; ++e) {
         --rdA;
-        const float2 tu = scr_tu[(size_t)rdA * 32 + lane];
-        const double2 b = scr_b[(size_t)rdA * 32 + lane];
+        const float2 tu = tu_next;
+        const double2 b = b_next;
+        if (rdA > 0) {   // next record of this lane while the current event is drawn
+          tu_next = scr_tu[(size_t)(rdA - 1) * 32 + lane];
+          b_next = scr_b[(size_t)(rdA - 1) * 32 + lane];
+        }
         const float tau = tu.x;
         const uint32_t u_draw = __float_as_uint(tu.y);
         const double w0 = (cur ? b10 : b00) * b.x, w1 = (cur ? b11 : b01) * b.y;
@@ -623,7 +645,7 @@ __device__ int tol_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int la
         }
       }
       if (cur) dwell_on += (double)(tc - prev);
-      my_tc[(size_t)c * NP + lane] = (uint8_t)kept;
+      W.tc[c * NP + lane] = (uint8_t)kept;
     }
     W.tn[c] = __ballot_sync(FULL, tl && cur == 1);
   }
@@ -650,53 +672,61 @@ __constant__ double kInvFact1[18] = {   // 1/(k+1)!
     1.1470745597729725e-11, 7.647163731819816e-13, 4.779477332387385e-14, 2.8114572543455206e-15,
     1.5619206968586225e-16};
 
-// phi1 = (e^x - 1)/x, phi2 = (e^x - 1 - x)/x^2, g3 = (x e^x - 2(e^x - 1) + x)/x^3,  x <= 0
-__device__ __forceinline__ void phi_funcs(double x, double& p1, double& p2, double& g3) {
-  if (x > -0.5) {
-    // p1 = sum x^k/(k+1)!, p2 = sum x^k/(k+2)!, g3 = sum (k+1) x^k/(k+3)!
-    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int k = 15; k >= 0; --k) {
-      s1 = fma(s1, x, kInvFact1[k]);
-      s2 = fma(s2, x, kInvFact1[k + 1]);
-      s3 = fma(s3, x, kInvFact1[k + 2] * (double)(k + 1));
-    }
-    p1 = s1; p2 = s2; g3 = s3;
-  } else {
-    const double e = expm1(x);
-    const double ix = 1.0 / x;
-    p1 = e * ix;
-    p2 = (e - x) * ix * ix;
-    g3 = (x * (e + 2.0) - 2.0 * e) * ix * ix * ix;
-  }
-}
-
+// phi1 = (e^x - 1)/x, phi2 = (e^x - 1 - x)/x^2, g3 = (x e^x - 2(e^x - 1) + x)/x^3 for x <= 0:
+// p1 = sum x^k/(k+1)!, p2 = sum x^k/(k+2)!, g3 = sum (k+1) x^k/(k+3)! below |x| = 1/2.
 struct Seg {          // A = [[-a, a], [w, -w-r]] = top-left block of Q3 (_linalg.py:14-29)
   double n00, n01, n10, n11;   // N = A - lam1 I
   double e1t, psit, I1, I2, t;
   double p00, p01, p10, p11;   // exp(tA)
 };
 
-__device__ __forceinline__ void seg_setup(double a, double w, double r, double t, bool frechet, Seg& s) {
+// Per (primary state, class) constants of A (computed once per CTA): lam1 (the eigenvalue
+// nearer 0), sq = lam1 - lam2 >= 0, r (absorption rate).  lam1 lam2 = det A = a r.
+__device__ __forceinline__ void seg_constants(double a, double w, double r, double& lam1, double& sq) {
   const double tr = -(a + w + r);
   const double disc = (a - r) * (a - r) + w * w + 2.0 * w * (a + r);
-  const double sq = sqrt(disc);
+  sq = sqrt(disc);
   const double lam2 = 0.5 * (tr - sq);
-  const double lam1 = lam2 < 0.0 ? (a * r) / lam2 : 0.0;   // lam1 lam2 = det = a r
-  const double x = -sq * t;                                // (lam2 - lam1) t <= 0
-  double p1, p2, g3;
-  phi_funcs(x, p1, p2, g3);
+  lam1 = lam2 < 0.0 ? (a * r) / lam2 : 0.0;
+}
+
+// exp(tA) = e^{lam1 t} (I + psi(t) N), psi(t) = t phi1(x), x = -sq t.  (Keeping e^{lam1 t} and
+// expm1(x) from the upward pass for the downward pass was measured slower than recomputing:
+// most segments are short, |x| < 1/2, where the series needs no expm1 at all.)
+__device__ __forceinline__ void seg_setup(double a, double w, double r, double lam1, double sq,
+                                          double t, bool frechet, Seg& s) {
+  const double x = -sq * t;
   s.t = t;
   s.n00 = -a - lam1; s.n01 = a; s.n10 = w; s.n11 = -w - r - lam1;
   s.e1t = exp(lam1 * t);
+  double p1;
+  if (x > -0.5) {
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 15; k >= 0; --k) {
+      s1 = fma(s1, x, kInvFact1[k]);
+      if (frechet) {
+        s2 = fma(s2, x, kInvFact1[k + 1]);
+        s3 = fma(s3, x, kInvFact1[k + 2] * (double)(k + 1));
+      }
+    }
+    p1 = s1;
+    if (frechet) { s.I1 = t * t * s2; s.I2 = t * t * t * s3; }
+  } else {
+    const double em1 = expm1(x);
+    const double ix = 1.0 / x;
+    p1 = em1 * ix;
+    if (frechet) {
+      s.I1 = t * t * ((em1 - x) * ix * ix);
+      s.I2 = t * t * t * ((x * (em1 + 2.0) - 2.0 * em1) * ix * ix * ix);
+    }
+  }
   s.psit = t * p1;
-  if (frechet) { s.I1 = t * t * p2; s.I2 = t * t * t * g3; }
   s.p00 = s.e1t * (1.0 + s.psit * s.n00);
   s.p01 = s.e1t * s.psit * s.n01;
   s.p10 = s.e1t * s.psit * s.n10;
   s.p11 = s.e1t * (1.0 + s.psit * s.n11);
-  // guard tiny negative round-off on the diagonal
-  if (s.p00 < 0.0) s.p00 = 0.0;
+  if (s.p00 < 0.0) s.p00 = 0.0;      // tiny negative round-off on the diagonal
   if (s.p11 < 0.0) s.p11 = 0.0;
 }
 
@@ -742,13 +772,14 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
           const double bound = pk > 0 ? (double)W.pt[pr] : 0.0;
           const bool same = C.part[pstate] == lane;
           const double w = same ? 0.0 : A.rate_off;
-          const double r = C.absorb[pstate * NP + lane];
+          const double* ct = C.absorb + (size_t)(pstate * NP + lane) * 3;   // (lam1, sq, r)
+          const double t = pos - bound;
           if (same) be0 = 0.0;
           if (nseg < n_seg_cap) scr_seg[(size_t)nseg * 32 + lane] = make_double2(be0, be1);
           else overflow = true;
           ++nseg;
           Seg s;
-          seg_setup(a, w, r, pos - bound, false, s);
+          seg_setup(a, w, ct[2], ct[0], ct[1], t, false, s);
           const double n0 = s.p00 * be0 + s.p01 * be1;
           const double n1 = s.p10 * be0 + s.p11 * be1;
           be0 = same ? 0.0 : n0;
@@ -802,6 +833,8 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
   double dc0 = d0, dc1 = d1;       // marginal of the node whose child edges are being walked
   int sg = nseg;
   int pr = A.cap_p - 1;            // the jump list read backwards = down order
+  double2 l_next = make_double2(0.0, 0.0);
+  if (tl && nseg > 0) l_next = scr_seg[(size_t)(nseg - 1) * 32 + lane];
   for (int ip = A.n_ops - 1; ip >= 0; --ip) {
     const int4 op = C.prog[ip];
     const int code = op.x & 0xff;
@@ -822,12 +855,14 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
         if (i < k) { st = W.psb[pr - i]; tend = (double)W.pt[pr - i]; }
         else { st = W.pn[c]; tend = (double)C.len[c]; }
         --sg;
-        const double2 l = scr_seg[(size_t)sg * 32 + lane];
+        const double2 l = l_next;
+        if (sg > 0) l_next = scr_seg[(size_t)(sg - 1) * 32 + lane];   // next record meanwhile
         const bool same = C.part[st] == lane;
         const double w = same ? 0.0 : A.rate_off;
-        const double r = C.absorb[st * NP + lane];
+        const double* ct = C.absorb + (size_t)(st * NP + lane) * 3;
+        const double r = ct[2];
         Seg s;
-        seg_setup(a, w, r, tend - tprev, true, s);
+        seg_setup(a, w, r, ct[0], ct[1], tend - tprev, true, s);
         const double m0 = s.p00 * l.x + s.p01 * l.y;
         const double m1 = s.p10 * l.x + s.p11 * l.y;
         const double g0 = (t0 > 0.0 && m0 > 0.0) ? t0 / m0 : 0.0;
@@ -874,7 +909,7 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
 // =====================================================================================
 struct Layout {     // dynamic shared memory carve-up (bytes)
   size_t prog, len, par, Bt, rate_p, rinv_p, pi_p, part, absorb, tslot, dwell, trans, tol, sum;
-  size_t warp0, w_pn, w_pc, w_sc, w_psb, w_pt, w_tn, w_tu, w_vec, w_stk, warp_bytes, total;
+  size_t warp0, w_pn, w_pc, w_sc, w_psb, w_pt, w_tn, w_tc, w_tcc, w_tu, w_vec, w_stk, warp_bytes, total;
 };
 
 __host__ __device__ inline size_t al(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -886,7 +921,7 @@ __host__ __device__ inline Layout make_layout(int S, int SPAD, int n_parts, int 
   L.prog = o; o += sizeof(int4) * (size_t)n_ops;
   L.Bt = o = al(o, 16); o += sizeof(double) * (size_t)SPAD * SPAD;
   L.pi_p = o; o += sizeof(double) * (size_t)SPAD;
-  L.absorb = o; o += sizeof(double) * (size_t)S * (size_t)(n_parts > 0 ? n_parts : 1);
+  L.absorb = o; o += sizeof(double) * 3 * (size_t)S * (size_t)(n_parts > 0 ? n_parts : 1);
   L.dwell = o; o += sizeof(double) * (size_t)S;
   L.tol = o; o += sizeof(double) * 4 * (size_t)(n_parts > 0 ? n_parts : 1);
   L.sum = o; o += sizeof(double) * 8;
@@ -908,6 +943,8 @@ __host__ __device__ inline Layout make_layout(int S, int SPAD, int n_parts, int 
   L.w_pc = w; w += (size_t)n_nodes;
   L.w_sc = w; w += (size_t)n_nodes;
   L.w_psb = w; w += (size_t)cap_p;
+  L.w_tc = w; w += (size_t)n_nodes * (size_t)n_parts;
+  L.w_tcc = w; w += n_parts > 0 ? (size_t)n_nodes * 32 : 0;
   L.warp_bytes = al(w, 16);
   L.total = L.warp0 + L.warp_bytes * kWarps;
   return L;
@@ -951,7 +988,15 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
     rinv_s[i] = r > 0.0 ? (float)(1.0 / r) : 0.0f;
     part_s[i] = (i < S && A.part) ? A.part[i] : 255;
   }
-  for (int i = tid; i < S * NP; i += kThreads) absorb_s[i] = A.absorb ? A.absorb[i] : 0.0;
+  for (int i = tid; i < S * NP; i += kThreads) {
+    const double r = A.absorb ? A.absorb[i] : 0.0;
+    const bool same = A.part && A.part[i / NP] == (i % NP);
+    double lam1, sq;
+    seg_constants(A.rate_on, same ? 0.0 : A.rate_off, r, lam1, sq);
+    absorb_s[3 * i] = lam1;
+    absorb_s[3 * i + 1] = sq;
+    absorb_s[3 * i + 2] = r;
+  }
   for (int i = tid; i < A.n_nodes; i += kThreads) {
     len_s[i] = (float)A.length[i];
     par_s[i] = A.parent[i];
@@ -983,13 +1028,13 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
   W.pt = reinterpret_cast<float*>(wb + L.w_pt);
   W.tn = reinterpret_cast<uint32_t*>(wb + L.w_tn);
   W.pn = wb + L.w_pn; W.pc = wb + L.w_pc; W.sc = wb + L.w_sc; W.psb = wb + L.w_psb;
+  W.tc = wb + L.w_tc; W.tcc = wb + L.w_tcc;
 
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp;
   const int64_t nw = (int64_t)gridDim.x * kWarps;
   double* scr_beta = X.p_beta + (size_t)gw * (size_t)scr_cap * SPAD;
   float2* scr_tu = X.t_tu ? X.t_tu + (size_t)gw * (size_t)X.cap_ts * 32 : nullptr;
   double2* scr_tb = X.t_beta ? X.t_beta + (size_t)gw * (size_t)X.cap_ts * 32 : nullptr;
-  uint8_t* scr_tc = X.t_cnt ? X.t_cnt + (size_t)gw * (size_t)A.n_nodes * 32 : nullptr;
   double2* scr_seg = X.seg ? X.seg + (size_t)gw * (size_t)X.n_seg * 32 : nullptr;
   const bool stats_p = (A.flags & RT_TMJP_F_STATS_PRIMARY) != 0;
   const bool stats_t = (A.flags & RT_TMJP_F_STATS_TOLERANCE) != 0;
@@ -1007,6 +1052,8 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
       W.pt[i] = A.p_time[(size_t)traj * A.cap_p + i];
       W.psb[i] = A.p_sb[(size_t)traj * A.cap_p + i];
     }
+    if (NP > 0)
+      for (int i = lane; i < A.n_nodes * NP; i += 32) W.tc[i] = A.t_cnt[(size_t)traj * A.n_nodes * NP + i];
     int p_total = A.p_total[traj];
     __syncwarp();
     int st = 0;
@@ -1019,7 +1066,7 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
       primary_dirty = st == 0 || st == 4;
     } else if (A.mode == RT_TMJP_INIT_TOLERANCE) {
       st = tol_pass(A, C, W, lane, traj, site, (uint32_t)A.sweep0, true, p_total, scr_tu, scr_tb,
-                    scr_tc, X.cap_ts, false);
+                    X.cap_ts, false);
       tol_dirty = st == 0 || st == 4;
     } else if (A.mode == RT_TMJP_SWEEP) {
       for (int sw = 0; sw < A.n_sweeps; ++sw) {
@@ -1031,7 +1078,7 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
           if (st) break;
         }
         if (NP > 0 && !(A.flags & RT_TMJP_F_SKIP_TOLERANCE)) {
-          st = tol_pass(A, C, W, lane, traj, site, sweep, false, p_total, scr_tu, scr_tb, scr_tc,
+          st = tol_pass(A, C, W, lane, traj, site, sweep, false, p_total, scr_tu, scr_tb,
                         X.cap_ts, stats_t);
           if (st == 0 || st == 4) tol_dirty = true;
           if (st) break;
@@ -1065,8 +1112,10 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
       }
       if (lane == 0) A.p_total[traj] = p_total;
     }
-    if (tol_dirty && A.t_node)
+    if (tol_dirty && A.t_node) {
       for (int v = lane; v < A.n_nodes; v += 32) A.t_node[(size_t)traj * A.n_nodes + v] = W.tn[v];
+      for (int i = lane; i < A.n_nodes * NP; i += 32) A.t_cnt[(size_t)traj * A.n_nodes * NP + i] = W.tc[i];
+    }
     if (have7 && A.summary_out && lane < 7) A.summary_out[(size_t)traj * 8 + lane] = out7[lane];
     if (st && lane == 0) A.status[traj] = (int8_t)st;
     __syncwarp();
@@ -1114,15 +1163,13 @@ int launch(const rt_tmjp_args& A, cudaStream_t stream) {
   const size_t b_beta = al(n_warps * (size_t)X.scr_cap * SPAD * sizeof(double), 256);
   const size_t b_tu = tol ? al(n_warps * (size_t)X.cap_ts * 32 * sizeof(float2), 256) : 0;
   const size_t b_tb = tol ? al(n_warps * (size_t)X.cap_ts * 32 * sizeof(double2), 256) : 0;
-  const size_t b_tc = tol ? al(n_warps * (size_t)A.n_nodes * 32, 256) : 0;
   const size_t b_seg = want_seg ? al(n_warps * (size_t)X.n_seg * 32 * sizeof(double2), 256) : 0;
   unsigned char* ws = nullptr;
-  RT_CUDA_CHECK(cudaMallocAsync(&ws, b_beta + b_tu + b_tb + b_tc + b_seg + 256, stream));
+  RT_CUDA_CHECK(cudaMallocAsync(&ws, b_beta + b_tu + b_tb + b_seg + 256, stream));
   unsigned char* p = ws;
   X.p_beta = reinterpret_cast<double*>(p); p += b_beta;
   X.t_tu = tol ? reinterpret_cast<float2*>(p) : nullptr; p += b_tu;
   X.t_beta = tol ? reinterpret_cast<double2*>(p) : nullptr; p += b_tb;
-  X.t_cnt = tol ? p : nullptr; p += b_tc;
   X.seg = want_seg ? reinterpret_cast<double2*>(p) : nullptr;
   kern<<<(unsigned)grid, kThreads, L.total, stream>>>(A, X);
   cudaError_t e = cudaGetLastError();
