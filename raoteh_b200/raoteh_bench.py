@@ -126,6 +126,27 @@ def bench_c5(dev, args, n_sites=100_000, sweeps_per_launch=5, launches=3, loglik
     b.record()
     torch.cuda.synchronize()
     res['summary_only'] = dict(ms=a.elapsed_time(b), trajectories_per_sec=ch.n_traj / (a.elapsed_time(b) * 1e-3))
+    # CPU leg: pure-Python/numpy restatement of the same sweep, one trajectory, one core
+    try:
+        import time
+        from oracle import np_tmjp
+        rng = np.random.default_rng(0)
+        nodes = dict((int(v), int(cfg['codes'][i, 0])) for i, v in enumerate(cfg['leaves']))
+        dd = [dict() for _ in range(cfg['n_parts'])]
+        for c in range(cfg['n_parts']):
+            bits = int(cfg['tol_obs'][0, c, 0])
+            dd[c][int(cfg['tol_obs_nodes'][0])] = set(s for s in (0, 1) if (bits >> s) & 1)
+        margs = (cfg['parent'], cfg['length'], cfg['Q'], cfg['part'], cfg['n_parts'], cfg['pi'],
+                 cfg['rate_on'], cfg['rate_off'], nodes, dd)
+        prim, tols = np_tmjp.gibbs_init(*margs, rng)
+        t0 = time.perf_counter()
+        n_cpu = 60
+        for _ in range(n_cpu):
+            prim, tols = np_tmjp.gibbs_sweep(*margs, prim, tols, rng)
+        res['cpu_port_sweeps_per_sec_1core'] = n_cpu / (time.perf_counter() - t0)
+        res['cpu_port_sample'] = '%d sweeps of one C5 trajectory, oracle/np_tmjp.py gibbs_sweep' % n_cpu
+    except Exception as e:   # pragma: no cover
+        res['cpu_port_error'] = repr(e)
     out['gibbs'] = dict(n_trajectories=ch.n_traj, init_events_per_edge=k, sweeps_per_launch=sweeps_per_launch,
                         mean_primary_jumps=float(ch.p_total.double().mean()),
                         mean_tolerance_toggles_per_class=float(ch.t_total.double().mean()),
