@@ -242,12 +242,18 @@ int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, in
  *   (_mjp_dense.get_history_statistics, raoteh/sampler/_mjp_dense.py:150), tol_stats
  *   [n_parts][4] = (root on, dwell on, gains, losses) of the SAMPLED tolerance
  *   trajectories, summary_sum [8] = the 7 values of get_tolerance_summary (+ count);
- *   summary_out [n_traj][8] = the same per trajectory (last sweep).
+ *   summary_out [n_traj][8] = the same per trajectory (last sweep), with [7] = the log-likelihood
+ *   of the primary trajectory under the compound process with the tolerance histories integrated
+ *   out (get_tolerance_process_log_likelihood, raoteh/sampler/_tmjp_dense.py:407-505).
  */
 #define RT_TMJP_INIT_PRIMARY 0
 #define RT_TMJP_INIT_TOLERANCE 1
 #define RT_TMJP_SWEEP 2
 #define RT_TMJP_SUMMARY 3
+#define RT_TMJP_TRAJ_LOGLIK 4   /* traj_loglik[t] = log-likelihood of primary trajectory t under (B, omega_p, pi_p):
+                                   _mjp.get_trajectory_log_likelihood, raoteh/sampler/_mjp.py:186-250; with
+                                   RT_TMJP_F_STATS_PRIMARY also prim_dwell / prim_trans += the statistics of the
+                                   CURRENT histories (_mjp_dense.get_history_statistics :150) */
 #define RT_TMJP_F_STATS_PRIMARY 1
 #define RT_TMJP_F_STATS_TOLERANCE 2
 #define RT_TMJP_F_SUMMARY 4
@@ -267,6 +273,7 @@ typedef struct rt_tmjp_args {
   const uint8_t* part;         /* [S] tolerance class of a primary state (n_parts > 0) */
   const double* absorb;        /* [S][n_parts] sum of Q[s,s'] over s' != s in class c */
   double rate_on, rate_off, omega_t;
+  double omega_p;              /* primary uniformization rate (Q[a][b] = omega_p * B[a][b], a != b) */
   /* observations */
   const void* obs;             /* primary: codes or masks per site */
   int64_t obs_stride;
@@ -296,6 +303,7 @@ typedef struct rt_tmjp_args {
   double* tol_stats;
   double* summary_sum;
   double* summary_out;
+  double* traj_loglik;         /* [n_traj], mode RT_TMJP_TRAJ_LOGLIK */
 } rt_tmjp_args;
 
 int rt_tmjp_run(const rt_tmjp_args* args, void* stream);

@@ -270,6 +270,8 @@ def gen_tolerance():
     import networkx as nx
     import random
     tmjpd = ref_shim.ref_module('_tmjp_dense')
+    tmjp = ref_shim.ref_module('_tmjp')
+    mjp = ref_shim.ref_module('_mjp')
     sampler = ref_shim.ref_module('_sampler')
     np.random.seed(7)
     random.seed(7)
@@ -297,7 +299,15 @@ def gen_tolerance():
         for rate_on, rate_off, dd in ((1.0, 1.0, None), (0.3, 2.0, disease)):
             out = tmjpd.get_tolerance_summary(primary_to_part, rate_on, rate_off, Q_primary,
                                               T_primary, root, disease_data=dd)
-            cases.append(dict(
+            extra = {}
+            if dd is None:
+                # the compound-process log-likelihood with the tolerance histories integrated out
+                # (sparse module: the dense twin's body still indexes Q_primary like a graph) and
+                # the trajectory log-likelihood under the primary process itself
+                ctm_s = tmjp.CompoundToleranceModel(Q_nx, distn, primary_to_part, rate_on, rate_off)
+                extra['tol_ll'] = float(tmjp.get_tolerance_process_log_likelihood(ctm_s, T_primary, root))
+                extra['traj_ll'] = float(mjp.get_trajectory_log_likelihood(T_primary, root, distn, Q_nx))
+            cases.append(dict(extra, 
                 edges=[[int(a), int(b), float(T_primary[a][b]['weight']), int(T_primary[a][b]['state'])]
                        for a, b in nx.bfs_edges(T_primary, root)],
                 root=root, rate_on=rate_on, rate_off=rate_off,
@@ -402,6 +412,9 @@ def gen_tmjp_moments(nhistories=3000, burn=100):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'tolerance':
+        gen_tolerance()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'tmjp':
         gen_tmjp_moments(int(sys.argv[2]) if len(sys.argv) > 2 else 3000)
         sys.exit(0)

@@ -52,6 +52,7 @@ class TmjpArgs(ctypes.Structure):
         ('B', c_void_p), ('rate_p', c_void_p), ('pi_p', c_void_p),
         ('part', c_void_p), ('absorb', c_void_p),
         ('rate_on', ctypes.c_double), ('rate_off', ctypes.c_double), ('omega_t', ctypes.c_double),
+        ('omega_p', ctypes.c_double),
         ('obs', c_void_p), ('obs_stride', c_int64),
         ('tol_obs', c_void_p), ('tol_obs_slot', c_void_p), ('tol_obs_stride', c_int64),
         ('n_traj', c_int64), ('n_sites', c_int64), ('traj0', c_int64),
@@ -64,7 +65,7 @@ class TmjpArgs(ctypes.Structure):
         ('n_sweeps', ctypes.c_int32), ('mode', ctypes.c_int32), ('init_k', ctypes.c_int32),
         ('flags', ctypes.c_int32),
         ('prim_dwell', c_void_p), ('prim_trans', c_void_p), ('tol_stats', c_void_p),
-        ('summary_sum', c_void_p), ('summary_out', c_void_p),
+        ('summary_sum', c_void_p), ('summary_out', c_void_p), ('traj_loglik', c_void_p),
     ]
 
 

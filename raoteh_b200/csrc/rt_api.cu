@@ -225,7 +225,8 @@ int rt_tmjp_run(const rt_tmjp_args* a, void* stream) {
   if (A.obs_kind != 0 && A.obs_kind != 1) return arg_error("rt_tmjp_run takes codes or masks");
   if (A.cap_p <= 0 || A.cap_p > 4096 || A.cap_t <= 0 || A.cap_t > 255) return arg_error("capacities");
   if ((int64_t)(A.n_parts + 2) * (A.n_ops + 1) >= 65536) return unsupported("program too long");
-  if (A.mode < 0 || A.mode > 3) return arg_error("mode");
+  if (A.mode < 0 || A.mode > 4) return arg_error("mode");
+  if (A.mode == RT_TMJP_TRAJ_LOGLIK && (!A.traj_loglik || !(A.omega_p > 0))) return arg_error("traj_loglik / omega_p");
   if ((A.mode == RT_TMJP_INIT_TOLERANCE || A.mode == RT_TMJP_SUMMARY) && A.n_parts == 0)
     return arg_error("mode needs tolerance classes");
   if (A.n_traj <= 0) return RT_OK;

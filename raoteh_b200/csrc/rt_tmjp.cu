@@ -70,6 +70,7 @@ struct Wp {
   float2* tu;      // [scr_cap]  (time, uniform) of the primary candidate events
   double* vec;     // [SPAD]
   double* stk;     // [n_slots][64]
+  int* estk;       // [n_slots][32]  power-of-two exponents of the parked tolerance partials (summary)
 };
 
 __device__ __forceinline__ double warp_max_d(double v) {
@@ -730,20 +731,28 @@ __device__ __forceinline__ void seg_setup(double a, double w, double r, double l
   if (s.p11 < 0.0) s.p11 = 0.0;
 }
 
-// out7 (valid on every lane after the call): initial_on, initial_off, dwell_on, dwell_off,
-// nabsorptions, ngains, nlosses  (raoteh/sampler/_tmjp_dense.py:852-855)
+// out8 (valid on every lane after the call): initial_on, initial_off, dwell_on, dwell_off,
+// nabsorptions, ngains, nlosses  (raoteh/sampler/_tmjp_dense.py:852-855), and [7] = the
+// log-likelihood of the primary trajectory under the compound process with the tolerance
+// histories integrated out (get_tolerance_process_log_likelihood, _tmjp_dense.py:407-505):
+// log pi(root state) + sum over jumps log Q[s,s'] + sum over classes log L_c, where class c
+// starts from (0, 1) if the root's primary state belongs to it and from tolerance_distn else.
+template <int SP>
 __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int lane, int64_t site,
                             int p_total, double2* scr_seg, int n_seg_cap, double total_len,
-                            double (&out7)[7]) {
+                            double (&out7)[8]) {
   const int NP = A.n_parts;
   const bool tl = lane < NP;
   const double a = A.rate_on;
   const double pi0 = A.rate_off / (A.rate_on + A.rate_off), pi1 = A.rate_on / (A.rate_on + A.rate_off);
   double a0 = 1.0, a1 = 1.0;
+  int esum = 0;                    // exponent of the partial being built (true = value * 2^esum)
   int nseg = 0;
   int prd = A.cap_p - p_total;
   bool bad = false, overflow = false;
   double d0 = 0.0, d1 = 0.0;
+  double class_ll = 0.0;           // log L_c of this lane's class
+  double jump_ll = 0.0;            // sum over primary jumps of log Q[s, s'] (same on every lane)
 
   // =============================== UP ===============================
   for (int ip = 0; ip < A.n_ops; ++ip) {
@@ -755,6 +764,7 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
       if (code == OP_MSG_SLOT) {
         be0 = W.stk[(op.z * 2 + 0) * 32 + lane];
         be1 = W.stk[(op.z * 2 + 1) * 32 + lane];
+        esum += W.estk[op.z * 32 + lane];
       } else if (tl && A.tol_obs) {
         const int ts = C.tslot[c];
         if (ts >= 0) {
@@ -791,6 +801,14 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
           pos = bound;
         }
       }
+      if (lane == 0) {   // the primary jumps of this edge: rate Q[parent side][child side]
+        int below = W.pn[c];
+        for (int i = 0; i < pk0; ++i) {
+          const int above = W.psb[prd + i];
+          jump_ll += log(C.Bt[below * (SP * 32) + above] * A.omega_p);
+          below = above;
+        }
+      }
       prd += pk0;
       a0 *= be0;
       a1 *= be1;
@@ -806,20 +824,28 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
       }
       const double mx = fmax(a0, a1);
       if (mx > 0.0) {
-        const double sc = rt_pow2_neg(rt_exponent(mx));
+        const int e = rt_exponent(mx);
+        const double sc = rt_pow2_neg(e);
         a0 *= sc;
         a1 *= sc;
+        esum += e;
       }
       if (code == OP_STORE) {
         W.stk[(op.z * 2 + 0) * 32 + lane] = a0;
         W.stk[(op.z * 2 + 1) * 32 + lane] = a1;
+        W.estk[op.z * 32 + lane] = esum;
         a0 = 1.0;
         a1 = 1.0;
+        esum = 0;
       } else {
         const double w0 = pi0 * a0, w1 = pi1 * a1;
         const double tot = w0 + w1;
         if (!(tot > 0.0)) bad = true;
         else { d0 = w0 / tot; d1 = w1 / tot; }
+        // likelihood prior of the class: (0, 1) when the root's primary state belongs to it
+        const bool own = C.part[W.pn[0]] == lane;
+        const double lk = own ? a1 : tot;
+        class_ll = lk > 0.0 ? log(lk) + (double)esum * RT_LN2 : -INFINITY;
       }
     }
   }
@@ -903,13 +929,68 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
   out7[4] = nabs;
   out7[5] = gains;
   out7[6] = losses;
+  if (!tl) class_ll = 0.0;
+  class_ll = rt_warp_sum(class_ll);
+  jump_ll = __shfl_sync(FULL, jump_ll, 0);
+  const double prior = C.pi_p[W.pn[0]];
+  out7[7] = (prior > 0.0 ? log(prior) : -INFINITY) + jump_ll + class_ll;
   return 0;
+}
+
+// log-likelihood of the primary trajectory under the MJP (B, omega_p, pi_p) itself
+// (_mjp.get_trajectory_log_likelihood, raoteh/sampler/_mjp.py:186-250):
+// log pi(root) - sum_s dwell_s q_s + sum over jumps log Q[s, s'].  Lanes take 32 edges at a time;
+// the offset of an edge's jumps in the pool is a warp prefix sum over the program order.
+template <int SP>
+__device__ double trajectory_loglik(const rt_tmjp_args& A, const Cta& C, const Wp& W, int lane,
+                                    int p_total, bool stats) {
+  constexpr int SPAD = SP * 32;
+  double ll = 0.0;
+  int base = A.cap_p - p_total;
+  for (int ip0 = 0; ip0 < A.n_ops; ip0 += 32) {
+    const int ip = ip0 + lane;
+    int c = -1, k = 0;
+    if (ip < A.n_ops) {
+      const int4 op = C.prog[ip];
+      if ((op.x & 0xff) <= OP_MSG_ONES) { c = op.y; k = W.pc[c]; }
+    }
+    int inc = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int start = base + inc - k;
+    base += __shfl_sync(FULL, inc, 31);
+    if (c >= 0) {
+      // jumps of the edge, child end first: (time from the parent end, parent-side state)
+      int below = W.pn[c];
+      double pos = (double)C.len[c];
+      for (int i = 0; i < k; ++i) {
+        const double tau = (double)W.pt[start + i];
+        const int above = W.psb[start + i];
+        ll -= (pos - tau) * (A.omega_p - A.rate_p[below]);
+        ll += log(C.Bt[below * SPAD + above] * A.omega_p);
+        if (stats) {   // _mjp_dense.get_history_statistics of the current history (:150)
+          atomicAdd(&C.dwell_acc[below], pos - tau);
+          atomicAdd(&C.trans_acc[above * A.S + below], 1u);
+        }
+        below = above;
+        pos = tau;
+      }
+      ll -= pos * (A.omega_p - A.rate_p[below]);
+      if (stats) atomicAdd(&C.dwell_acc[below], pos);
+    }
+  }
+  ll = rt_warp_sum(ll);
+  const double prior = C.pi_p[W.pn[0]];
+  return ll + (prior > 0.0 ? log(prior) : -INFINITY);
 }
 
 // =====================================================================================
 struct Layout {     // dynamic shared memory carve-up (bytes)
   size_t prog, len, par, Bt, rate_p, rinv_p, pi_p, part, absorb, tslot, dwell, trans, tol, sum;
-  size_t warp0, w_pn, w_pc, w_sc, w_psb, w_pt, w_tn, w_tc, w_tcc, w_tu, w_vec, w_stk, warp_bytes, total;
+  size_t warp0, w_pn, w_pc, w_sc, w_psb, w_pt, w_tn, w_tc, w_tcc, w_tu, w_vec, w_stk, w_estk, warp_bytes, total;
 };
 
 __host__ __device__ inline size_t al(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -936,6 +1017,7 @@ __host__ __device__ inline Layout make_layout(int S, int SPAD, int n_parts, int 
   size_t w = 0;
   L.w_vec = w; w += sizeof(double) * 64;
   L.w_stk = w; w += sizeof(double) * 64 * (size_t)n_slots;
+  L.w_estk = w; w += n_parts > 0 ? sizeof(int) * 32 * (size_t)n_slots : 0;
   L.w_tu = w; w += sizeof(float2) * (size_t)scr_cap;
   L.w_pt = w; w += sizeof(float) * (size_t)cap_p;
   L.w_tn = w; w += sizeof(uint32_t) * (size_t)n_nodes;
@@ -1024,6 +1106,7 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
   Wp W;
   W.vec = reinterpret_cast<double*>(wb + L.w_vec);
   W.stk = reinterpret_cast<double*>(wb + L.w_stk);
+  W.estk = reinterpret_cast<int*>(wb + L.w_estk);
   W.tu = reinterpret_cast<float2*>(wb + L.w_tu);
   W.pt = reinterpret_cast<float*>(wb + L.w_pt);
   W.tn = reinterpret_cast<uint32_t*>(wb + L.w_tn);
@@ -1058,7 +1141,7 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
     __syncwarp();
     int st = 0;
     bool primary_dirty = false, tol_dirty = false;
-    double out7[7];
+    double out7[8];
     bool have7 = false;
     if (A.mode == RT_TMJP_INIT_PRIMARY) {
       st = primary_pass<SP>(A, C, W, lane, traj, site, (uint32_t)A.sweep0, true, false, scr_beta,
@@ -1083,7 +1166,7 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
           if (st == 0 || st == 4) tol_dirty = true;
           if (st) break;
           if (A.flags & RT_TMJP_F_SUMMARY) {
-            st = summary_pass(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7);
+            st = summary_pass<SP>(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7);
             if (st) break;
             have7 = true;
             if (lane < 7) atomicAdd(&C.sum_acc[lane], out7[lane]);
@@ -1091,8 +1174,11 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
           }
         }
       }
+    } else if (A.mode == RT_TMJP_TRAJ_LOGLIK) {
+      const double ll = trajectory_loglik<SP>(A, C, W, lane, p_total, stats_p);
+      if (lane == 0 && A.traj_loglik) A.traj_loglik[traj] = ll;
     } else {   // RT_TMJP_SUMMARY
-      st = summary_pass(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7);
+      st = summary_pass<SP>(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7);
       if (st == 0) {
         have7 = true;
         if (lane < 7) atomicAdd(&C.sum_acc[lane], out7[lane]);
@@ -1116,7 +1202,7 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
       for (int v = lane; v < A.n_nodes; v += 32) A.t_node[(size_t)traj * A.n_nodes + v] = W.tn[v];
       for (int i = lane; i < A.n_nodes * NP; i += 32) A.t_cnt[(size_t)traj * A.n_nodes * NP + i] = W.tc[i];
     }
-    if (have7 && A.summary_out && lane < 7) A.summary_out[(size_t)traj * 8 + lane] = out7[lane];
+    if (have7 && A.summary_out && lane < 8) A.summary_out[(size_t)traj * 8 + lane] = out7[lane];
     if (st && lane == 0) A.status[traj] = (int8_t)st;
     __syncwarp();
   }

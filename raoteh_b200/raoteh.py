@@ -130,15 +130,51 @@ class RaoTehChains(object):
         self.dwell_sum.zero_()
         self.trans_sum.zero_()
 
+    def trajectory_log_likelihood(self, stats=False):
+        """log-likelihood of every trajectory under this MJP (_mjp.get_trajectory_log_likelihood,
+        raoteh/sampler/_mjp.py:186-250) -> fp64 [n_traj], computed on the device.  stats=True also
+        adds the sufficient statistics of the CURRENT histories to dwell_sum / trans_sum."""
+        import ctypes
+        A = _native.TmjpArgs()
+        A.S, A.n_parts, A.n_nodes = self.S, 0, self.sched.n
+        A.n_ops, A.n_slots, A.cap_p, A.cap_t = self.n_ops, self.n_slots, self.cap, 1
+        A.obs_kind = self.obs.kind
+        A.program, A.parent, A.length = _ptr(self.ops), _ptr(self.parent), _ptr(self.length)
+        A.B, A.rate_p, A.pi_p = _ptr(self.B), _ptr(self.rate), _ptr(self.root_distn)
+        A.omega_p = self.omega
+        A.obs, A.obs_stride = _ptr(self.obs.data), self.obs.stride
+        A.n_traj, A.n_sites, A.traj0 = self.n_traj, self.n_sites, self.traj0
+        A.p_node, A.p_cnt = _ptr(self.node_state), _ptr(self.ev_count)
+        A.pn_traj_stride, A.pn_node_stride = 1, self.stride
+        A.p_total, A.p_time, A.p_sb = _ptr(self.ev_total), _ptr(self.ev_time), _ptr(self.ev_sb)
+        A.status = _ptr(self.status)
+        A.mode = 4
+        if stats:
+            A.flags = 1
+            A.prim_dwell, A.prim_trans = _ptr(self.dwell_sum), _ptr(self.trans_sum)
+        out = torch.empty(self.n_traj, dtype=torch.float64, device=self.device)
+        A.traj_loglik = _ptr(out)
+        _native.check(_native.lib().rt_tmjp_run(ctypes.byref(A), _stream()), 'rt_tmjp_run')
+        return out
+
     _STATE = ('node_state', 'ev_count', 'ev_total', 'ev_time', 'ev_sb')
 
     def snapshot(self):
         """Copy of the trajectory state (for Metropolis-Hastings rejection)."""
         return dict((k, getattr(self, k).clone()) for k in self._STATE)
 
-    def restore(self, snap):
+    def restore(self, snap, reject=None):
+        """Put back the snapshot; with `reject` (bool [n_traj]) only those trajectories."""
         for k in self._STATE:
-            getattr(self, k).copy_(snap[k])
+            cur = getattr(self, k)
+            if reject is None:
+                cur.copy_(snap[k])
+            elif k in ('node_state', 'ev_count'):          # [n_nodes, n_traj]
+                torch.where(reject[None, :], snap[k], cur, out=cur)
+            elif k == 'ev_total':
+                torch.where(reject, snap[k], cur, out=cur)
+            else:                                          # [n_traj, cap]
+                torch.where(reject[:, None], snap[k], cur, out=cur)
 
     # -- host-side views --------------------------------------------------------
     def trajectory(self, t):

@@ -21,7 +21,7 @@ import torch
 from . import _native
 from .engine import OBS_CODES, OBS_MASK, _ptr, _stream
 
-MODE_INIT_PRIMARY, MODE_INIT_TOLERANCE, MODE_SWEEP, MODE_SUMMARY = 0, 1, 2, 3
+MODE_INIT_PRIMARY, MODE_INIT_TOLERANCE, MODE_SWEEP, MODE_SUMMARY, MODE_TRAJ_LOGLIK = 0, 1, 2, 3, 4
 F_STATS_PRIMARY, F_STATS_TOLERANCE, F_SUMMARY = 1, 2, 4
 F_SKIP_PRIMARY, F_SKIP_TOLERANCE = 8, 16
 
@@ -114,8 +114,10 @@ class ToleranceChains(object):
         self.tol_stats = z((NP, 4), torch.float64)
         self.summary_sum = z(8, torch.float64)
         self.summary_out = z((T, 8), torch.float64)
+        self.traj_loglik = z(T, torch.float64)
         self.sweeps_done = 0
         self.initialized = False
+        self._primary_src = None
 
     # -- the C-ABI call ------------------------------------------------------------
     def _args(self, mode, n_sweeps=1, init_k=0, flags=0):
@@ -127,13 +129,21 @@ class ToleranceChains(object):
         A.B, A.rate_p, A.pi_p = _ptr(self.B), _ptr(self.rate_p), _ptr(self.pi_p)
         A.part, A.absorb = _ptr(self.part), _ptr(self.absorb)
         A.rate_on, A.rate_off, A.omega_t = self.rate_on, self.rate_off, self.omega_t
+        A.omega_p = self.omega_p
         A.obs, A.obs_stride = _ptr(self.obs.data), self.obs.stride
         A.tol_obs, A.tol_obs_slot = _ptr(self.tol_obs), _ptr(self.tol_obs_slot)
         A.tol_obs_stride = 0 if self.tol_obs is None else int(self.tol_obs.shape[2])
         A.n_traj, A.n_sites, A.traj0 = self.n_traj, self.n_sites, self.traj0
-        A.p_node, A.p_cnt = _ptr(self.p_node), _ptr(self.p_cnt)
-        A.pn_traj_stride, A.pn_node_stride = self.sched.n, 1
-        A.p_total, A.p_time, A.p_sb = _ptr(self.p_total), _ptr(self.p_time), _ptr(self.p_sb)
+        src = self._primary_src
+        if src is None:
+            A.p_node, A.p_cnt = _ptr(self.p_node), _ptr(self.p_cnt)
+            A.pn_traj_stride, A.pn_node_stride = self.sched.n, 1
+            A.p_total, A.p_time, A.p_sb = _ptr(self.p_total), _ptr(self.p_time), _ptr(self.p_sb)
+        else:   # primary trajectories of a RaoTehChains (trajectory-minor node arrays)
+            A.cap_p = src.cap
+            A.p_node, A.p_cnt = _ptr(src.node_state), _ptr(src.ev_count)
+            A.pn_traj_stride, A.pn_node_stride = 1, src.stride
+            A.p_total, A.p_time, A.p_sb = _ptr(src.ev_total), _ptr(src.ev_time), _ptr(src.ev_sb)
         A.t_node, A.t_cnt = _ptr(self.t_node), _ptr(self.t_cnt)
         A.t_total, A.t_time = _ptr(self.t_total), _ptr(self.t_time)
         A.status = _ptr(self.status)
@@ -142,6 +152,7 @@ class ToleranceChains(object):
         A.prim_dwell, A.prim_trans = _ptr(self.prim_dwell), _ptr(self.prim_trans)
         A.tol_stats, A.summary_sum = _ptr(self.tol_stats), _ptr(self.summary_sum)
         A.summary_out = _ptr(self.summary_out)
+        A.traj_loglik = _ptr(self.traj_loglik)
         return A
 
     def _run(self, mode, **kw):
@@ -205,6 +216,28 @@ class ToleranceChains(object):
             raise NumericalZeroProb('the denominator is zero')
         self.check()
         return self.summary_out[:, :7]
+
+    def tolerance_log_likelihood(self):
+        """log-likelihood of every current primary trajectory under the compound process with
+        the tolerance histories integrated out (raoteh/sampler/_tmjp.py:406-492,
+        _tmjp_dense.py:407-505) -> [n_traj].  Runs the summary kernel."""
+        self.tolerance_summary()
+        return self.summary_out[:, 7]
+
+    def trajectory_log_likelihood(self):
+        """log-likelihood of every current primary trajectory under the primary process itself
+        (_mjp.get_trajectory_log_likelihood, raoteh/sampler/_mjp.py:186-250) -> [n_traj]."""
+        self._run(MODE_TRAJ_LOGLIK)
+        return self.traj_loglik
+
+    def attach_primary(self, chains):
+        """Use the primary trajectories of a raoteh_b200.raoteh.RaoTehChains (same tree, same
+        trajectory count) for the summary / log-likelihood modes: Rao-Blackwellisation and
+        importance weights for histories proposed under another rate matrix
+        (raoteh/sampler/tests/test_sample_tmjp.py:186-246)."""
+        if chains is not None and (chains.n_traj != self.n_traj or chains.sched.n != self.sched.n):
+            raise ValueError('the attached chains must have the same tree and trajectory count')
+        self._primary_src = chains
 
     def check(self):
         st = self.status

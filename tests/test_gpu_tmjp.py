@@ -106,6 +106,14 @@ def test_tolerance_summary_kernel_matches_reference_fixture():
         want = np.array([c['out'] for c in cases])
         # event times are stored in float32 on the device: 1e-6 relative on the inputs
         np.testing.assert_allclose(out, want, rtol=2e-6, atol=1e-7)
+        if cases[0]['disease'] is None:
+            # compound log-likelihood with the tolerance histories integrated out
+            # (_tmjp.get_tolerance_process_log_likelihood) and the plain trajectory log-likelihood
+            # (_mjp.get_trajectory_log_likelihood), both from the reference
+            got = ch.tolerance_log_likelihood().cpu().numpy()
+            np.testing.assert_allclose(got, [c['tol_ll'] for c in cases], rtol=2e-6)
+            got = ch.trajectory_log_likelihood().cpu().numpy()
+            np.testing.assert_allclose(got, [c['traj_ll'] for c in cases], rtol=2e-6)
 
 
 def test_tolerance_summary_kernel_matches_generic_path_fp64_times():
@@ -472,3 +480,100 @@ def test_gen_histories_sparse_generator():
         out = _tmjp.get_tolerance_summary(ctm, primary, 0)
         assert len(out) == 7 and abs(out[0] + out[1] - 3) < 1e-9
     assert n == 6
+
+
+def test_importance_weights_estimate_the_likelihood_ratio():
+    """raoteh/sampler/tests/test_sample_tmjp.py:186-246, :384-393: primary histories proposed by
+    plain Rao-Teh under the proposal rate matrix, weight = exp(compound log-likelihood with the
+    tolerance histories integrated out - proposal log-likelihood), everything on the device; the
+    mean weight estimates P_compound(data) / P_proposal(data), computed here in closed form on
+    the 48-state compound space.  |z| < 5."""
+    import torch
+    from raoteh_b200 import engine
+    from raoteh_b200.raoteh import RaoTehChains
+    from raoteh_b200.tmjp import ToleranceChains
+    from raoteh_b200.sampler import _tmjp_dense
+    Q, pi, part = toy_model()
+    sched = toy_tree()
+    rate_on, rate_off = 0.7, 1.3
+    ctm = _tmjp_dense.CompoundToleranceModel(Q, pi, dict(enumerate(int(p) for p in part)), rate_on, rate_off)
+    ctm.init_compound()
+    Qp = _tmjp_dense.get_primary_proposal_rate_matrix(Q, ctm.primary_to_part, ctm.tolerance_distn)
+    node_to_state = {3: 4, 4: 5, 5: 1}
+    leaves = np.array([3, 4, 5])
+    codes = np.array([[4], [5], [1]], dtype=np.uint8)
+    # closed-form marginal likelihoods of the leaf data
+    P = np_oracle.expm_edges(Qp, sched.length)
+    ll_prop, _ = np_oracle.log_likelihood(sched.parent, P, np_oracle.Obs('codes', 6, 1, leaf_nodes=leaves, codes=codes), pi)
+    nc = ctm.ncompound
+    lik = np.ones((sched.n, 1, nc))
+    for v, s in node_to_state.items():
+        lik[v, 0] = [1.0 if p == s else 0.0 for p in ctm.compound_to_primary]
+    Pc = np_oracle.expm_edges(ctm.Q_compound, sched.length)
+    ll_comp, _ = np_oracle.log_likelihood(sched.parent, Pc, np_oracle.Obs('dense', nc, 1, lik=lik, has=np.ones(sched.n, dtype=bool)),
+                                          ctm.compound_distn)
+    want = float(np.exp(ll_comp[0] - ll_prop[0]))
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaf_nodes=leaves)
+    groups, n_chains = 12, 4096
+    means = []
+    for g in range(groups):
+        prop = RaoTehChains(sched, Qp, obs, n_chains=n_chains, root_distn=pi, seed=600 + g, cap=64)
+        prop.sweep(60, stats=False)
+        tol = ToleranceChains(sched, Q, pi, ctm.primary_to_part, rate_on, rate_off, obs, n_chains=n_chains)
+        tol.attach_primary(prop)
+        w = torch.exp(tol.tolerance_log_likelihood() - prop.trajectory_log_likelihood())
+        means.append(float(w.mean()))
+    m, se = np.mean(means), np.std(means, ddof=1) / np.sqrt(groups)
+    assert abs(m - want) < 5 * se, (m, want, se)
+    assert se < 0.05 * want
+
+
+def test_device_metropolis_hastings_targets_the_compound_process():
+    """Rao-Teh proposals under the approximate primary process + MH correction with the
+    tolerance histories integrated out (raoteh/sampler/tests/test_sample_tmjp.py:248-276), all
+    trajectories at once on the device: the primary dwell times and transition counts must
+    match the exact posterior expectations of the 48-state compound process.  |z| < 5."""
+    from raoteh_b200 import engine
+    from raoteh_b200.mh import ToleranceMetropolisChains
+    from raoteh_b200.sampler import _tmjp_dense
+    Q, pi, part = toy_model()
+    sched = toy_tree()
+    rate_on, rate_off = 0.7, 1.3
+    ctm = _tmjp_dense.CompoundToleranceModel(Q, pi, dict(enumerate(int(p) for p in part)), rate_on, rate_off)
+    ctm.init_compound()
+    node_to_state = {3: 4, 4: 5, 5: 1}
+    leaves = np.array([3, 4, 5])
+    codes = np.array([[4], [5], [1]], dtype=np.uint8)
+    nc = ctm.ncompound
+    lik = np.ones((sched.n, 1, nc))
+    for v, s in node_to_state.items():
+        lik[v, 0] = [1.0 if p == s else 0.0 for p in ctm.compound_to_primary]
+    Pc = np_oracle.expm_edges(ctm.Q_compound, sched.length)
+    r = np_oracle.expected_history_statistics(
+        sched.parent, sched.length, ctm.Q_compound, Pc,
+        np_oracle.Obs('dense', nc, 1, lik=lik, has=np.ones(sched.n, dtype=bool)), ctm.compound_distn)
+    prim = np.array(ctm.compound_to_primary)
+    want_dwell = np.array([r['dwell'][prim == p].sum() for p in range(6)])
+    want_trans = np.zeros((6, 6))
+    for i in range(nc):
+        for j in range(nc):
+            if prim[i] != prim[j]:
+                want_trans[prim[i], prim[j]] += r['trans'][i, j]
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaf_nodes=leaves)
+    groups, n_chains, burn, n_steps = 12, 1024, 40, 60
+    dwell = np.zeros((groups, 6))
+    trans = np.zeros((groups, 36))
+    acc = []
+    for g in range(groups):
+        mh = ToleranceMetropolisChains(sched, Q, pi, ctm.primary_to_part, rate_on, rate_off, obs,
+                                       n_chains=n_chains, seed=900 + g, cap=64)
+        mh.step(burn, stats=False)
+        mh.step(n_steps)
+        dwell[g] = mh.dwell_sum.cpu().numpy() / (n_chains * n_steps)
+        trans[g] = mh.trans_sum.cpu().numpy().ravel() / (n_chains * n_steps)
+        acc.append(mh.n_accepted / mh.n_proposed)
+    assert 0.2 < np.mean(acc) < 0.999
+    np.testing.assert_allclose(dwell.sum(axis=1), sched.length.sum(), rtol=1e-5)
+    n_total = groups * n_chains * n_steps
+    _assert_z(dwell, want_dwell, n_total)
+    _assert_z(trans, want_trans.ravel(), n_total)
