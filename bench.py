@@ -39,6 +39,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 C2_SITES = 1_000_000
+E2E_CHUNKS = int(os.environ.get('RT_E2E_CHUNKS', '8'))
+DEV_CHUNKS = int(os.environ.get('RT_DEV_CHUNKS', '0'))     # device-resident arm: two-stream chunk overlap   # site chunks of the pipelined host-buffer call
 C2_LEAVES = 32
 
 
@@ -271,10 +273,13 @@ def run_gpu(args):
 
     def step(record=False):
         """New rate matrix -> expm + up + down + Frechet contraction (+ allreduce);
-        observations resident in HBM."""
+        observations resident in HBM.  record=True: one launch per kernel on the current
+        stream with CUDA events around the up and the down kernel (roofline accounting);
+        otherwise the production schedule (DEV_CHUNKS site chunks alternating between two
+        streams when > 1)."""
         mjp.events = sub if record else None
         mjp.set_rate_matrix(cfg['Q'])
-        r = mjp.expected_history_statistics(obs)
+        r = mjp.expected_history_statistics(obs, overlap_chunks=0 if record else DEV_CHUNKS)
         stats = rdist.pack_stats(r['loglik'].sum(), r['dwell'], r['trans'], r['root_post_sum'])
         rdist.allreduce_stats(stats)      # the path's only collective (NCCL, 1+S+S*S+S doubles)
         state['n_levels'] = r['n_levels']
@@ -286,7 +291,8 @@ def run_gpu(args):
         memory, D2H of per-site log-lik / status and of the statistics, all inside."""
         mjp.events = None
         mjp.set_rate_matrix(cfg['Q'])
-        r = mjp.expected_history_statistics_from_host(codes_pinned, cfg['leaves'], out_ll, out_st)
+        r = mjp.expected_history_statistics_from_host(codes_pinned, cfg['leaves'], out_ll, out_st,
+                                                      n_chunks=E2E_CHUNKS)
         stats = rdist.pack_stats(r['loglik_sum'], r['dwell'], r['trans'], r['root_post_sum'])
         rdist.allreduce_stats(stats)
         out_stats.copy_(stats, non_blocking=True)
@@ -321,7 +327,8 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms = timed(step, args.steps, args.warmup, record=True)
+    ms_plain = timed(step, args.steps, args.warmup, record=True)   # per-kernel events (roofline)
+    ms = timed(step, args.steps, args.warmup) if DEV_CHUNKS > 1 else ms_plain
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
 

@@ -214,9 +214,57 @@ class TreeMJP(object):
         return res
 
     # ---- K4 / K5 ------------------------------------------------------------
-    def posterior(self, obs, want_exponents=False, want_node_distn=True):
+    def _posterior_overlapped(self, obs, n_chunks):
+        """Up + down pass for S <= 8 with the site axis cut into chunks that alternate between
+        two streams: the kernels of different chunks are independent, so the write-heavy
+        pruning kernel of one chunk runs under the issue-bound walk of another and no kernel's
+        tail wave leaves SMs idle."""
+        lib = _native.lib()
+        S, n = self.S, self.sched.n
+        N, stride = obs.n_sites, obs.stride
+        dev = self.device
+        prog = self._programs(obs)
+        P = self.transition_matrices()
+        loglik = self._buf('ov_loglik', (N,), torch.float64)
+        status = self._buf('ov_status', (N,), torch.int8)
+        partials = self._buf('partials', (self.sched.n_store, S, stride), torch.float64)
+        W = self._buf('W', (n, S, S), torch.float64, zero=True)
+        rps = self._buf('root_post_sum', (S,), torch.float64, zero=True)
+        lp = prog['level_ptr']
+        esz = {OBS_CODES: 1, OBS_MASK: 8, OBS_DENSE: 8}[obs.kind]
+        cur = torch.cuda.current_stream()
+        if getattr(self, '_ov_streams', None) is None:
+            self._ov_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        chunk = _round_up((N + n_chunks - 1) // n_chunks, 256)
+        for cs in self._ov_streams:
+            cs.wait_stream(cur)
+        for k, lo in enumerate(range(0, N, chunk)):
+            hi = min(N, lo + chunk)
+            cs = self._ov_streams[k % 2]
+            rc = lib.rt_prune_loglik(
+                S, n, hi - lo, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'], _ptr(P),
+                _ptr(self.root_distn), obs.kind, obs.data.data_ptr() + esz * lo,
+                partials.data_ptr() + 8 * lo, None, loglik.data_ptr() + 8 * lo,
+                status.data_ptr() + lo, None, cs.cuda_stream)
+            _native.check(rc, 'rt_prune_loglik')
+            rc = lib.rt_posterior_stats(
+                S, n, hi - lo, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
+                _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1, _ptr(P), _ptr(self.root_distn),
+                obs.kind, obs.data.data_ptr() + esz * lo, partials.data_ptr() + 8 * lo,
+                status.data_ptr() + lo, None, _ptr(W), _ptr(rps), cs.cuda_stream)
+            _native.check(rc, 'rt_posterior_stats')
+        for cs in self._ov_streams:
+            cur.wait_stream(cs)
+        return dict(loglik=loglik, status=status, partials=partials, exponents=None, node_distn=None,
+                    W=W, root_post_sum=rps, n_levels=len(lp) - 1)
+
+    def posterior(self, obs, want_exponents=False, want_node_distn=True, overlap_chunks=0):
         """Up + down pass.  Returns loglik, status, partials, node_distn (internal
-        nodes, by store index), W[n,S,S] (site-summed J/P weights), root_post_sum[S]."""
+        nodes, by store index), W[n,S,S] (site-summed J/P weights), root_post_sum[S].
+        overlap_chunks > 1 (S <= 8, no node marginals / exponents wanted): chunked two-stream
+        schedule, see _posterior_overlapped."""
+        if overlap_chunks > 1 and self.S <= 8 and not want_node_distn and not want_exponents:
+            return self._posterior_overlapped(obs, int(overlap_chunks))
         up = self.log_likelihood(obs, keep_partials=True, want_exponents=want_exponents)
         prog = self._programs(obs)
         N, stride = obs.n_sites, obs.stride
@@ -305,9 +353,15 @@ class TreeMJP(object):
         cur = torch.cuda.current_stream()
         if getattr(self, '_copy_streams', None) is None:
             self._copy_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            # two compute streams, chunks alternate: the kernels of consecutive chunks are
+            # independent, so the tail wave of one chunk's kernel (a chunk is only ~1.3-1.7
+            # waves of CTAs) is filled with CTAs of the next chunk's kernels
+            self._compute_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         s_in, s_out = self._copy_streams
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
+        for cs in self._compute_streams:
+            cs.wait_stream(cur)
         chunk = _round_up((N + n_chunks - 1) // n_chunks, 128)
         bounds = [(lo, min(N, lo + chunk)) for lo in range(0, N, chunk)]
         ev_in = []
@@ -318,26 +372,29 @@ class TreeMJP(object):
             e = torch.cuda.Event()
             e.record(s_in)
             ev_in.append(e)
-        for (lo, hi), e in zip(bounds, ev_in):
-            cur.wait_event(e)
+        for k, ((lo, hi), e) in enumerate(zip(bounds, ev_in)):
+            cs = self._compute_streams[k % 2]
+            cs.wait_event(e)
             rc = lib.rt_prune_loglik(
                 S, n, hi - lo, N, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'], _ptr(P),
                 _ptr(self.root_distn), OBS_CODES, codes_dev.data_ptr() + lo,
                 partials.data_ptr() + 8 * lo, None, loglik.data_ptr() + 8 * lo,
-                status.data_ptr() + lo, _ptr(llsum), cur.cuda_stream)
+                status.data_ptr() + lo, _ptr(llsum), cs.cuda_stream)
             _native.check(rc, 'rt_prune_loglik')
             rc = lib.rt_posterior_stats(
                 S, n, hi - lo, N, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
                 _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1, _ptr(P), _ptr(self.root_distn),
                 OBS_CODES, codes_dev.data_ptr() + lo, partials.data_ptr() + 8 * lo,
-                status.data_ptr() + lo, None, _ptr(W), _ptr(rps), cur.cuda_stream)
+                status.data_ptr() + lo, None, _ptr(W), _ptr(rps), cs.cuda_stream)
             _native.check(rc, 'rt_posterior_stats')
             done = torch.cuda.Event()
-            done.record(cur)
+            done.record(cs)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)
                 out_loglik[lo:hi].copy_(loglik[lo:hi], non_blocking=True)
                 out_status[lo:hi].copy_(status[lo:hi], non_blocking=True)
+        for cs in self._compute_streams:
+            cur.wait_stream(cs)
         M = self.frechet_contract(W)
         M[0].zero_()
         if getattr(self, '_offdiag', None) is None:
@@ -357,14 +414,14 @@ class TreeMJP(object):
         _native.check(rc, 'rt_frechet_contract')
         return M
 
-    def expected_history_statistics(self, obs, want_node_distn=False):
+    def expected_history_statistics(self, obs, want_node_distn=False, overlap_chunks=0):
         """Site-summed expected dwell[S], transition counts[S,S], root posterior sum[S],
         per-site loglik, per-edge contraction matrices M_edges[n,S,S].
 
         dwell[c] = sum_b M_b[c,c]; trans[c,d] = Q_b[c,d] * M_b[c,d] summed over
         edges (raoteh/sampler/_mjp_dense.py:497-533 with one Frechet derivative per
         edge, the form of examples/code2x3/extras.py:108-129)."""
-        post = self.posterior(obs, want_node_distn=want_node_distn)
+        post = self.posterior(obs, want_node_distn=want_node_distn, overlap_chunks=overlap_chunks)
         M = self.frechet_contract(post['W'])
         M[0].zero_()
         S = self.S
