@@ -134,6 +134,26 @@ int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
                        double* node_distn, double* W, double* root_post_sum, void* stream);
 
 /*
+ * rt_posterior_stats plus, per SITE and BRANCH, the posterior expectation of a statistic
+ * given by one S x S kernel per edge:
+ *   branch_out[b][site] = sum_ac J_b[a,c] K_b[a,c] / P_b[a,c] = sum_ac G_b[a] K_b[a,c] L_b[c]
+ * K: [n_nodes][S][S] (slot 0 unused), branch_out: [n_nodes][site_stride] (row 0 not written).
+ * With K_b = L(t_b Q, t_b (E o Q)) (one rt_frechet_contract call) this is the expected number
+ * of E-type transitions on every branch for every site -- the per-branch tables of
+ * examples/code2x3/extras.py:19-132 (get_expected_ntransitions) and
+ * examples/p53/liwen-branch-expectation.py:176-356 (synonymous / non-synonymous counts per
+ * branch and codon column), which the reference computes one site and one branch at a time.
+ */
+int rt_posterior_branch_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                              const int32_t* program, int n_ops, int n_slots,
+                              const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
+                              const double* P, const double* root_distn,
+                              int obs_kind, const void* obs,
+                              const double* partials, const int8_t* status,
+                              double* node_distn, double* W, double* root_post_sum,
+                              const double* K, double* branch_out, void* stream);
+
+/*
  * Pitched host<->device copy on `stream` (cudaMemcpy2DAsync): moves a chunk of sites
  * [row][lo:hi] of a site-minor array between a pinned HOST array and the device
  * array without staging, so chunk k+1 can be copied under the kernels of chunk k.

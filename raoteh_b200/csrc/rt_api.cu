@@ -49,10 +49,12 @@ int rt_prune_dmma_dispatch(int, int, bool, int64_t, int64_t, const int32_t*, int
 int rt_posterior_small_dispatch(int, int, int64_t, int64_t, const int32_t*, int, int, int,
                                 const int32_t*, const int32_t*, int,
                                 const double*, const double*, const void*, const double*,
-                                const int8_t*, double*, double*, double*, cudaStream_t);
+                                const int8_t*, double*, double*, double*, const double*, double*,
+                                cudaStream_t);
 int rt_posterior_dmma_dispatch(int, int, int64_t, int64_t, const int32_t*, const int32_t*, int,
                                const double*, const double*, const void*, const double*,
-                               const int8_t*, double*, double*, double*, cudaStream_t);
+                               const int8_t*, double*, double*, double*, const double*, double*,
+                               cudaStream_t);
 
 int rt_raoteh_dispatch(int, int, int, int64_t, int64_t, int64_t, int64_t, const int32_t*, int, int,
                        const int32_t*, const double*, const double*, const double*, const double*,
@@ -131,30 +133,58 @@ int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
   return rc;
 }
 
-int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
-                       const int32_t* program, int n_ops, int n_slots,
-                       const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
-                       const double* P, const double* root_distn, int obs_kind, const void* obs,
-                       const double* partials, const int8_t* status, double* node_distn, double* W,
-                       double* root_post_sum, void* stream) {
+static int posterior_common(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                            const int32_t* program, int n_ops, int n_slots,
+                            const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
+                            const double* P, const double* root_distn, int obs_kind, const void* obs,
+                            const double* partials, const int8_t* status, double* node_distn, double* W,
+                            double* root_post_sum, const double* K, double* branch_out, void* stream) {
   if (!edges || !level_ptr_h || !P || !partials || !status || !W)
     return arg_error("null pointer");
   if (!node_distn && !(S >= 2 && S <= 8 && program))
     return arg_error("node_distn may be NULL only for S <= 8 with the upward program given");
   if (obs_kind < 0 || obs_kind > 2) return arg_error("obs_kind");
   if (site_stride < n_sites) return arg_error("site_stride < n_sites");
+  if ((K == nullptr) != (branch_out == nullptr)) return arg_error("K and branch_out go together");
   if (n_sites <= 0) return RT_OK;
-  (void)n_nodes;
+  int rc;
   if (S >= 2 && S <= 8)
-    return rt_posterior_small_dispatch(S, obs_kind, n_sites, site_stride, program, n_ops, n_slots,
-                                       n_nodes, edges, level_ptr_h, n_levels, P, root_distn, obs,
-                                       partials, status, node_distn, W, root_post_sum,
-                                       (cudaStream_t)stream);
-  if (S >= 1 && S <= 64)
-    return rt_posterior_dmma_dispatch(S, obs_kind, n_sites, site_stride, edges, level_ptr_h,
-                                      n_levels, P, root_distn, obs, partials, status, node_distn, W,
-                                      root_post_sum, (cudaStream_t)stream);
-  return unsupported("rt_posterior_stats needs 1 <= S <= 64");
+    rc = rt_posterior_small_dispatch(S, obs_kind, n_sites, site_stride, program, n_ops, n_slots,
+                                     n_nodes, edges, level_ptr_h, n_levels, P, root_distn, obs,
+                                     partials, status, node_distn, W, root_post_sum, K, branch_out,
+                                     (cudaStream_t)stream);
+  else if (S >= 1 && S <= 64)
+    rc = rt_posterior_dmma_dispatch(S, obs_kind, n_sites, site_stride, edges, level_ptr_h,
+                                    n_levels, P, root_distn, obs, partials, status, node_distn, W,
+                                    root_post_sum, K, branch_out, (cudaStream_t)stream);
+  else
+    return unsupported("rt_posterior_stats needs 1 <= S <= 64");
+  if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: shared-memory budget");
+  return rc;
+}
+
+int rt_posterior_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                       const int32_t* program, int n_ops, int n_slots,
+                       const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
+                       const double* P, const double* root_distn, int obs_kind, const void* obs,
+                       const double* partials, const int8_t* status, double* node_distn, double* W,
+                       double* root_post_sum, void* stream) {
+  return posterior_common(S, n_nodes, n_sites, site_stride, program, n_ops, n_slots, edges,
+                          level_ptr_h, n_levels, P, root_distn, obs_kind, obs, partials, status,
+                          node_distn, W, root_post_sum, nullptr, nullptr, stream);
+}
+
+int rt_posterior_branch_stats(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
+                              const int32_t* program, int n_ops, int n_slots,
+                              const int32_t* edges, const int32_t* level_ptr_h, int n_levels,
+                              const double* P, const double* root_distn, int obs_kind,
+                              const void* obs, const double* partials, const int8_t* status,
+                              double* node_distn, double* W, double* root_post_sum,
+                              const double* K, double* branch_out, void* stream) {
+  if (!K || !branch_out) return arg_error("null pointer");
+  return posterior_common(S, n_nodes, n_sites, site_stride, program, n_ops, n_slots, edges,
+                          level_ptr_h, n_levels, P, root_distn, obs_kind, obs, partials, status,
+                          node_distn, W, root_post_sum, K, branch_out, stream);
 }
 
 int rt_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,

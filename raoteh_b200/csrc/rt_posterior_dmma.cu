@@ -59,12 +59,17 @@ root_distn_generic_kernel(int S, int64_t n_sites, int64_t stride,
       if (rsum[s] != 0.0) atomicAdd(&root_post_sum[s], rsum[s]);
 }
 
-template <int MT, int OBS>
+// BR: a fourth contraction kl = K_b L_b and, per site, x = sum_a G_a kl_a: the posterior
+// expectation on this branch of the statistic with per-edge kernel K (e.g. expected number of
+// synonymous / non-synonymous substitutions, examples/code2x3/extras.py:19-132,
+// examples/p53/liwen-branch-expectation.py:176-356).  K is read through L1 (no shared memory left).
+template <int MT, int OBS, bool BR>
 __global__ void __launch_bounds__(kThreads, 1)
 down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict__ edges,
                  const double* __restrict__ P, const void* __restrict__ obs,
                  const double* __restrict__ partials, const int8_t* __restrict__ status,
-                 double* __restrict__ node_distn, double* __restrict__ W) {
+                 double* __restrict__ node_distn, double* __restrict__ W,
+                 const double* __restrict__ Kmat, double* __restrict__ branch_out) {
   constexpr int SP = 8 * MT;
   constexpr int LDP = SP + 4;
   constexpr int KS = SP / 4;
@@ -154,6 +159,31 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
         for (int j = 0; j < kNT; ++j) dmma884(m[i][j][0], m[i][j][1], a, bf[j]);
       }
     }
+    // ---- (BR) kl = K L, same shape as m ------------------------------------------------
+    double kl[BR ? MT : 1][kNT][2];
+    double xs[kNT][2];
+    if (BR) {
+      const double* Kb = Kmat + (size_t)b * S * S;
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) kl[BR ? i : 0][j][0] = kl[BR ? i : 0][j][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        double bf[kNT];
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) bf[j] = Lw[(4 * kk + t) * kLd + 8 * j + g];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const int r = 8 * i + g, cc = 4 * kk + t;
+          const double a = (r < S && cc < S) ? __ldg(&Kb[r * S + cc]) : 0.0;
+#pragma unroll
+          for (int j = 0; j < kNT; ++j) dmma884(kl[BR ? i : 0][j][0], kl[BR ? i : 0][j][1], a, bf[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kNT; ++j) xs[j][0] = xs[j][1] = 0.0;
+    }
     // ---- G = D_a / m (0 where D_a == 0), written to the warp's G tile ---------------
 #pragma unroll
     for (int i = 0; i < MT; ++i)
@@ -167,9 +197,24 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
           double d = 0.0;
           if (s < S && sg < n_sites) d = Dp[(int64_t)s * stride + sg];
           gv[h] = (d > 0.0 && m[i][j][h] > 0.0) ? d / m[i][j][h] : 0.0;
+          if (BR) xs[j][h] = fma(gv[h], kl[BR ? i : 0][j][h], xs[j][h]);
         }
         *reinterpret_cast<double2*>(&Gw[(8 * i + g) * kLd + 8 * j + 2 * t]) = make_double2(gv[0], gv[1]);
       }
+    if (BR) {
+      // sum over the 8 row groups g (lanes with equal t), then lane g == 0 writes its 2 sites
+#pragma unroll
+      for (int j = 0; j < kNT; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          double v = xs[j][h];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          const int64_t sg = site0 + 8 * j + 2 * t + h;
+          if (g == 0 && sg < n_sites) branch_out[(int64_t)b * stride + sg] = v;
+        }
+    }
     __syncwarp();
 
     // ---- D_b = L o (P^T G)  (rows = child states) ------------------------------------
@@ -240,7 +285,8 @@ template <int MT>
 int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edges_dev,
         const int32_t* level_ptr_h, int n_levels, const double* P, const double* root_distn,
         const void* obs, const double* partials, const int8_t* status, double* node_distn,
-        double* W, double* root_post_sum, cudaStream_t stream) {
+        double* W, double* root_post_sum, const double* Kmat, double* branch_out,
+        cudaStream_t stream) {
   constexpr int SP = 8 * MT;
   constexpr int LDP = SP + 4;
   int64_t gr = (n_sites + 255) / 256;
@@ -250,11 +296,16 @@ int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edg
   const int4* edges = reinterpret_cast<const int4*>(edges_dev);
   const unsigned gx = (unsigned)((n_sites + kTilesPerCta * kTileSites - 1) / (kTilesPerCta * kTileSites));
 #define RT_LAUNCH(OBSK)                                                                           \
-  {                                                                                               \
-    auto kern = down_dmma_kernel<MT, OBSK>;                                                       \
+  if (branch_out) {                                                                               \
+    auto kern = down_dmma_kernel<MT, OBSK, true>;                                                 \
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, kThreads, smem, stream>>>(S, n_sites, stride, edges + e0, P, obs, partials,     \
-                                           status, node_distn, W);                                \
+                                           status, node_distn, W, Kmat, branch_out);              \
+  } else {                                                                                        \
+    auto kern = down_dmma_kernel<MT, OBSK, false>;                                                \
+    RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kThreads, smem, stream>>>(S, n_sites, stride, edges + e0, P, obs, partials,     \
+                                           status, node_distn, W, nullptr, nullptr);              \
   }
   for (int l = 0; l < n_levels; ++l) {
     const int e0 = level_ptr_h[l], e1 = level_ptr_h[l + 1];
@@ -278,10 +329,11 @@ int rt_posterior_dmma_dispatch(int S, int obs_kind, int64_t n_sites, int64_t str
                                const int32_t* edges_dev, const int32_t* level_ptr_h, int n_levels,
                                const double* P, const double* root_distn, const void* obs,
                                const double* partials, const int8_t* status, double* node_distn,
-                               double* W, double* root_post_sum, cudaStream_t stream) {
+                               double* W, double* root_post_sum, const double* Kmat,
+                               double* branch_out, cudaStream_t stream) {
   const int MT = (S + 15) / 16 * 2;
 #define RT_ARGS S, obs_kind, n_sites, stride, edges_dev, level_ptr_h, n_levels, P, root_distn, obs, \
-                partials, status, node_distn, W, root_post_sum, stream
+                partials, status, node_distn, W, root_post_sum, Kmat, branch_out, stream
   switch (MT) {
     case 2: return run<2>(RT_ARGS);
     case 4: return run<4>(RT_ARGS);

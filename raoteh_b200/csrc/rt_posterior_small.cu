@@ -247,14 +247,18 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return r;
 }
 
-template <int S, int OBS>
+// BR: also write, per site and branch, x = sum_ab G_a K_b[a,c] L_c -- the posterior expectation
+// of the statistic whose per-edge kernel is K (e.g. K_b = L(t_b Q, t_b (E o Q)): expected number
+// of E-type transitions on the branch, examples/code2x3/extras.py:19-132).
+template <int S, int OBS, bool BR>
 __global__ void __launch_bounds__(kWalkBlock)
 down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ program, int n_ops,
                  int n_slots, int n_nodes, const double* __restrict__ P,
                  const double* __restrict__ root_distn, const void* __restrict__ obs,
                  const double* __restrict__ partials, const int8_t* __restrict__ status,
                  double* __restrict__ node_distn, double* __restrict__ W,
-                 double* __restrict__ root_post_sum) {
+                 double* __restrict__ root_post_sum, const double* __restrict__ Kmat,
+                 double* __restrict__ branch_out) {
   constexpr int V = WalkV<S>::value;
   constexpr int NS = WalkNS<S>::value;
   constexpr int SP1 = S + 1;
@@ -266,7 +270,8 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
   double* Pl_s = P_s + (size_t)n_nodes * S * S;        // [n_nodes][S][S+1]: columns + row sum (leaf edges)
   double* W_s = Pl_s + (size_t)n_nodes * S * SP1;      // [n_nodes][S*S] per-CTA accumulator
   double* rp_s = W_s + (size_t)n_nodes * S * S;        // [S]
-  double* stk = rp_s + S;                              // [n_slots][NS][S][kWalkBlock]
+  double* K_s = rp_s + S;                              // [n_nodes][S][S] (BR only)
+  double* stk = K_s + (BR ? (size_t)n_nodes * S * S : 0);   // [n_slots][NS][S][kWalkBlock]
 
   const int tid = threadIdx.x, lane = tid & 31;
   for (int i = tid; i < n_ops; i += kWalkBlock) {
@@ -280,6 +285,8 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
   }
   if (tid < S) { pi_s[tid] = root_distn ? root_distn[tid] : 1.0; rp_s[tid] = 0.0; }
   for (int i = tid; i < n_nodes * S * S; i += kWalkBlock) { P_s[i] = P[i]; W_s[i] = 0.0; }
+  if (BR)
+    for (int i = tid; i < n_nodes * S * S; i += kWalkBlock) K_s[i] = Kmat[i];
   for (int i = tid; i < n_nodes * S; i += kWalkBlock) {
     double t = 0.0;
 #pragma unroll
@@ -397,6 +404,17 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
             }
 #pragma unroll
             for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+            if (BR) {
+              double x = 0.0;
+#pragma unroll
+              for (int a = 0; a < S; ++a) {
+                double kl = 0.0;
+#pragma unroll
+                for (int b = 0; b < S; ++b) kl = fma(K_s[c * S * S + a * S + b], L[b], kl);
+                x = fma(G[a], kl, x);
+              }
+              if (site0 + q * kWalkBlock < n_sites) branch_out[(int64_t)c * stride + site0 + q * kWalkBlock] = x;
+            }
 #pragma unroll
             for (int b = 0; b < S; ++b) {
               if (fresh) cur[q][b] = t[b];
@@ -421,6 +439,17 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
             }
 #pragma unroll
             for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+            if (BR) {
+              double x = 0.0;
+#pragma unroll
+              for (int a = 0; a < S; ++a) {
+                double kl = 0.0;
+#pragma unroll
+                for (int b = 0; b < S; ++b) kl = fma(K_s[c * S * S + a * S + b], L[b], kl);
+                x = fma(G[a], kl, x);
+              }
+              if (site0 + q * kWalkBlock < n_sites) branch_out[(int64_t)c * stride + site0 + q * kWalkBlock] = x;
+            }
           }
         } else {
           // ---- leaf with a mask / dense emission row / no observation ----
@@ -453,6 +482,17 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
             }
 #pragma unroll
             for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
+            if (BR) {
+              double x = 0.0;
+#pragma unroll
+              for (int a = 0; a < S; ++a) {
+                double kl = 0.0;
+#pragma unroll
+                for (int b = 0; b < S; ++b) kl = fma(K_s[c * S * S + a * S + b], L[b], kl);
+                x = fma(G[a], kl, x);
+              }
+              if (site0 + q * kWalkBlock < n_sites) branch_out[(int64_t)c * stride + site0 + q * kWalkBlock] = x;
+            }
           }
         }
         // W_c += sum over the warp's 32*NS sites of G (x) L
@@ -494,15 +534,16 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
   if (root_post_sum && tid < S && rp_s[tid] != 0.0) atomicAdd(&root_post_sum[tid], rp_s[tid]);
 }
 
-template <int S, int OBS>
+template <int S, int OBS, bool BR>
 int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops, int n_slots,
                 int n_nodes, const double* P, const double* root_distn, const void* obs,
                 const double* partials, const int8_t* status, double* node_distn, double* W,
-                double* root_post_sum, cudaStream_t stream, bool* handled) {
+                double* root_post_sum, const double* Kmat, double* branch_out,
+                cudaStream_t stream, bool* handled) {
   constexpr int NS = WalkNS<S>::value;
-  auto kern = down_walk_kernel<S, OBS>;
+  auto kern = down_walk_kernel<S, OBS, BR>;
   const size_t smem = (sizeof(int4) + sizeof(long long)) * n_ops +
-                      sizeof(double) * (2 * S + (size_t)n_nodes * (2 * S * S + S * (S + 1))) +
+                      sizeof(double) * (2 * S + (size_t)n_nodes * ((BR ? 3 : 2) * S * S + S * (S + 1))) +
                       sizeof(double) * (size_t)n_slots * NS * S * kWalkBlock;
   *handled = false;
   if (smem > 100 * 1024) return RT_OK;        // fall back to the level-synchronous kernel
@@ -518,7 +559,7 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, kWalkBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots,
                                                      n_nodes, P, root_distn, obs, partials, status,
-                                                     node_distn, W, root_post_sum);
+                                                     node_distn, W, root_post_sum, Kmat, branch_out);
   RT_CUDA_CHECK(cudaGetLastError());
   *handled = true;
   return RT_OK;
@@ -529,20 +570,26 @@ int run(int obs_kind, int64_t n_sites, int64_t stride, const int32_t* program, i
         int n_slots, int n_nodes, const int32_t* edges_dev,
         const int32_t* level_ptr_h, int n_levels, const double* P, const double* root_distn,
         const void* obs, const double* partials, const int8_t* status, double* node_distn,
-        double* W, double* root_post_sum, cudaStream_t stream) {
+        double* W, double* root_post_sum, const double* Kmat, double* branch_out,
+        cudaStream_t stream) {
   if (program && n_ops > 0) {
     bool handled = false;
     const int4* prog = reinterpret_cast<const int4*>(program);
     int rc = RT_ERR_ARG;
-#define RT_WALK(OBSK) rc = launch_walk<S, OBSK>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P, \
+#define RT_WALK(OBSK)                                                                             \
+  rc = branch_out ? launch_walk<S, OBSK, true>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P,   \
+                                               root_distn, obs, partials, status, node_distn, W,    \
+                                               root_post_sum, Kmat, branch_out, stream, &handled)   \
+                  : launch_walk<S, OBSK, false>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P,  \
                                                 root_distn, obs, partials, status, node_distn, W,   \
-                                                root_post_sum, stream, &handled)
+                                                root_post_sum, nullptr, nullptr, stream, &handled)
     if (obs_kind == OBS_CODES) RT_WALK(OBS_CODES);
     else if (obs_kind == OBS_MASK) RT_WALK(OBS_MASK);
     else if (obs_kind == OBS_DENSE) RT_WALK(OBS_DENSE);
 #undef RT_WALK
     if (rc != RT_OK || handled) return rc;
   }
+  if (branch_out) return RT_ERR_UNSUPPORTED;   // per-branch output exists in the walk kernel only
   if (!node_distn) return RT_ERR_ARG;   // the level-synchronous kernel needs the marginals buffer
   int64_t gr = (n_sites + kBlock - 1) / kBlock;
   int grid_root = (int)(gr < 148 * 8 ? gr : 148 * 8);
@@ -581,9 +628,11 @@ int rt_posterior_small_dispatch(int S, int obs_kind, int64_t n_sites, int64_t st
                                 const int32_t* edges_dev, const int32_t* level_ptr_h, int n_levels,
                                 const double* P, const double* root_distn, const void* obs,
                                 const double* partials, const int8_t* status, double* node_distn,
-                                double* W, double* root_post_sum, cudaStream_t stream) {
+                                double* W, double* root_post_sum, const double* Kmat,
+                                double* branch_out, cudaStream_t stream) {
 #define RT_ARGS obs_kind, n_sites, stride, program, n_ops, n_slots, n_nodes, edges_dev, level_ptr_h, \
-                n_levels, P, root_distn, obs, partials, status, node_distn, W, root_post_sum, stream
+                n_levels, P, root_distn, obs, partials, status, node_distn, W, root_post_sum, Kmat,  \
+                branch_out, stream
   switch (S) {
     case 2: return run<2>(RT_ARGS);
     case 3: return run<3>(RT_ARGS);

@@ -287,6 +287,54 @@ class TreeMJP(object):
         up.update(node_distn=node_distn, W=W, root_post_sum=root_post_sum, n_levels=len(lp) - 1)
         return up
 
+    def transition_kernels(self, E=None):
+        """K_b = L(t_b Q_b, t_b (E o Q_b)) for every edge: K_b[a, c] = expected number of E-type
+        transitions on the branch jointly with the end state c, from the start state a
+        (the Frechet-derivative form of examples/code2x3/extras.py:108-129)."""
+        n, S = self.sched.n, self.S
+        Qe = self.Q[0].expand(n, S, S) if self.q_index is None else self.Q[self.q_index.long()]
+        off = 1.0 - torch.eye(S, dtype=torch.float64, device=self.device)
+        if E is None:
+            Et = off
+        else:
+            Et = torch.as_tensor(np.asarray(E, dtype=np.float64), device=self.device) * off
+        C = (Qe * Et).contiguous()
+        Qt = self.Q.transpose(1, 2).contiguous()
+        K = torch.empty((n, S, S), dtype=torch.float64, device=self.device)
+        rc = _native.lib().rt_frechet_contract(_ptr(Qt), _ptr(self.q_index), _ptr(self.length),
+                                               _ptr(C), n, S, _ptr(K), _stream())
+        _native.check(rc, 'rt_frechet_contract')
+        K[0].zero_()
+        return K
+
+    def branch_expectations(self, obs, E=None, K=None):
+        """Per SITE and BRANCH posterior expectation of the number of E-type transitions
+        (E: S x S 0/1 or weight mask, default all off-diagonal pairs) -> dict with
+        'branch' [n_nodes, n_sites] (row of the child node; root row zero), 'loglik', 'status'.
+        Batched form of examples/code2x3/extras.py:19-132 and of the per-branch tables of
+        examples/p53/liwen-branch-expectation.py:176-356."""
+        if K is None:
+            K = self.transition_kernels(E)
+        up = self.log_likelihood(obs, keep_partials=True)
+        prog = self._programs(obs)
+        N, stride = obs.n_sites, obs.stride
+        node_distn = None
+        if self.S > 8:
+            node_distn = self._buf('node_distn', (self.sched.n_store, self.S, stride), torch.float64)
+        W = self._buf('W', (self.sched.n, self.S, self.S), torch.float64, zero=True)
+        rps = self._buf('root_post_sum', (self.S,), torch.float64, zero=True)
+        branch = torch.zeros((self.sched.n, stride), dtype=torch.float64, device=self.device)
+        lp = prog['level_ptr']
+        rc = _native.lib().rt_posterior_branch_stats(
+            self.S, self.sched.n, N, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
+            _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1,
+            _ptr(self.transition_matrices()), _ptr(self.root_distn), obs.kind, _ptr(obs.data),
+            _ptr(up['partials']), _ptr(up['status']), _ptr(node_distn), _ptr(W), _ptr(rps),
+            _ptr(K), _ptr(branch), _stream())
+        _native.check(rc, 'rt_posterior_branch_stats')
+        return dict(branch=branch[:, :N], loglik=up['loglik'], status=up['status'], W=W,
+                    root_post_sum=rps, K=K)
+
     def posterior_given_partials(self, obs, partials, status=None):
         """Downward pass for caller-supplied partials of the internal nodes
         ([n_store, S, stride]; leaves come from `obs`): the batched form of

@@ -306,3 +306,39 @@ def test_host_buffer_pipeline_matches_resident_path(rt):
     np.testing.assert_allclose(r['dwell'].cpu().numpy(), ref['dwell'].cpu().numpy(), rtol=1e-12)
     np.testing.assert_allclose(r['trans'].cpu().numpy(), ref['trans'].cpu().numpy(), rtol=1e-12)
     np.testing.assert_allclose(float(r['loglik_sum']), float(ref['loglik'].sum()), rtol=1e-12)
+
+
+@pytest.mark.parametrize('S,n_leaves,n_sites', [(4, 9, 70), (6, 6, 33), (20, 5, 37), (61, 6, 150)])
+def test_branch_expectations_per_site(S, n_leaves, n_sites):
+    """rt_posterior_branch_stats: expected number of E-type transitions per site and branch vs
+    the oracle evaluated one site at a time (examples/code2x3/extras.py:19-132), relative 1e-9."""
+    from raoteh_b200 import synth, engine
+    from raoteh_b200.lowering import TreeSchedule
+    rng = np.random.default_rng(40 + S)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.2, rng)
+    if S == 61:
+        Q, pi, _ = synth.mg94()
+    else:
+        Q = rng.exponential(1.0, size=(S, S))
+        np.fill_diagonal(Q, 0)
+        Q -= np.diag(Q.sum(axis=1))
+        Q /= np.abs(np.diag(Q)).mean()
+        pi = rng.dirichlet(np.ones(S) * 3)
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.05)
+    E = (rng.random((S, S)) < 0.5).astype(float)
+    np.fill_diagonal(E, 0.0)        # a transition-type mask: pairs of distinct states
+    sched = TreeSchedule(parent, length)
+    mjp = engine.TreeMJP(sched, Q, root_distn=pi)
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaves)
+    got = mjp.branch_expectations(obs, E)['branch'].cpu().numpy()
+    P = np_oracle.expm_edges(Q, length)
+    oobs = np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes)
+    n_check = min(n_sites, 12 if S > 8 else n_sites)
+    for i in list(range(n_check - 1)) + [n_sites - 1]:
+        r = np_oracle._ehs_chunk(parent, length, Q, P, oobs, pi, None, i, i + 1)
+        want = np_oracle.edge_expected_ntransitions(Q, r['M_edges'], E)
+        np.testing.assert_allclose(got[:, i], want, rtol=1e-9, atol=1e-13)
+    # summed over sites and branches with E = all pairs it is the total expected transition count
+    tot = mjp.branch_expectations(obs)['branch'].sum()
+    ehs = mjp.expected_history_statistics(obs)
+    np.testing.assert_allclose(float(tot), float(ehs['trans'].sum()), rtol=1e-9)
