@@ -300,3 +300,48 @@ def test_tolerance_summary_matches_reference_fixture():
         contribs = _tmjp_dense.get_tolerance_ll_contribs(
             case['rate_on'], case['rate_off'], T_primary.size(weight='weight'), *out)
         assert all(np.isfinite(c) for c in contribs)
+
+
+def test_reader_pipeline_matches_per_column_calls():
+    """Text inputs (newick, codeml-style phylip, genetic code table) -> readers -> one batched
+    evaluation == the per-column loop of examples/p53/p53.py:76-100 over the mirrored
+    _mjp_dense.get_likelihood."""
+    import io as _io
+    from raoteh_b200 import io as rio, engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.sampler import _mjp_dense
+    code_txt = ''.join('%d\t%s\t%s\n' % (i, r, c) for i, (r, c) in enumerate(
+        # a connected set of codons (a 2 x 2 x 2 cube of single-nucleotide changes)
+        [('ala', 'gct'), ('ala', 'gcc'), ('val', 'gtt'), ('val', 'gtc'), ('thr', 'act'),
+         ('thr', 'acc'), ('ile', 'att'), ('ile', 'atc')])) + '8\tstop\ttaa\n'
+    code = rio.read_genetic_code(_io.StringIO(code_txt))
+    c2s, s2r, r2p, s2p = rio.codon_state_maps(code)
+    Q, distn, _, _ = rio.mg94_from_genetic_code(0.25, 0.3, 0.25, 0.2, 2.5, 0.4, code,
+                                                target_expected_rate=1.0)
+    T, root, leaves = rio.read_newick(_io.StringIO('((Has:0.3,Ptr:0.2):0.1,(Mmu:0.25,Rno:0.4):0.15,Bta:0.5);'))
+    rng = np.random.default_rng(3)
+    codons = [c for s, r, c in code]
+    names = [n for _, n in leaves]
+    n_cols = 40
+    seqs = {}
+    for nme in names:
+        col = [codons[k] for k in rng.integers(0, len(codons), n_cols)]
+        if nme == 'Bta':
+            col[5] = '---'
+        seqs[nme] = col
+    phy = '%d %d\n\n' % (len(names), 3 * n_cols) + ''.join('%s  %s\n\n' % (k, ''.join(v)) for k, v in seqs.items())
+    rows = list(rio.read_phylip(_io.StringIO(phy), ntaxa=5, ncodons=n_cols))
+    sched = TreeSchedule.from_nx(T, root)
+    codes, leaf_nodes = rio.alignment_to_codes(rows, leaves, sched, c2s)
+    mjp = engine.TreeMJP(sched, Q, root_distn=distn)
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaf_nodes)
+    ll = mjp.log_likelihood(obs)['loglik'].cpu().numpy()
+    name_to_leaf = dict((n, l) for l, n in leaves)
+    for j in (0, 5, 17, 39):
+        allowed = dict((v, set(range(8))) for v in T)
+        for nme in names:
+            cod = seqs[nme][j].upper()
+            if cod in c2s:
+                allowed[name_to_leaf[nme]] = {c2s[cod]}
+        lk = _mjp_dense.get_likelihood(T, allowed, root, 8, root_distn=distn, Q_default=Q)
+        assert_allclose(ll[j], np.log(lk), rtol=1e-10)
