@@ -195,6 +195,9 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
 // V/2 + V/4 + ... exchanges instead of V full reductions -- and then added to a per-CTA
 // accumulator in shared memory; one masked global atomicAdd per entry per CTA at the end.
 // ---------------------------------------------------------------------------------------
+#ifndef RT_WALK_DMMA_REDUCE
+#define RT_WALK_DMMA_REDUCE 0
+#endif
 #ifndef RT_WALK_PF
 #define RT_WALK_PF 0
 #endif
@@ -229,6 +232,41 @@ __device__ __forceinline__ void reduce_scatter_warp(double (&v)[V], int lane) {
 }
 
 template <int S> struct WalkV { static constexpr int value = (S <= 4) ? 16 : (S == 5 ? 32 : 64); };
+
+__device__ __forceinline__ void dmma884_acc(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Cross-lane reduction of the S*S per-lane weights on the FP64 tensor pipe.  One DMMA with the
+// lane's value as the B fragment (k = lane % 4, n = lane / 4) and a row selector as the A
+// fragment (a[m][k] = [m == r]) adds, for value r of the tile, the 4 lanes of every lane group n
+// into C[r][n]; 8 DMMAs fill an 8 x 8 tile (value x lane group), two adds and two shuffles
+// finish the sum over the groups.  16 DMMA + ~14 other instructions per edge and warp for
+// S = 4, against 30 SHFL + 60 FSEL + 15 DADD for the shuffle butterfly -- but MEASURED SLOWER
+// (C2 walk 0.749 ms vs 0.640 ms): on B200 the FP64 DMMA runs at the FP64 FMA rate (37.0 vs
+// 33.5 TFLOP/s measured), so 16 DMMAs cost the FP64 pipe as much as 128 DFMAs, far more than
+// the butterfly's 15 DADDs.  Kept behind RT_WALK_DMMA_REDUCE (0) as a recorded experiment.
+template <int S, int V>
+__device__ __forceinline__ void reduce_w_dmma(const double (&w)[V], const double (&sel)[8], int lane,
+                                              double* Wc) {
+  const int g = lane >> 2, t = lane & 3;
+  constexpr int NT = (S * S + 7) / 8;
+#pragma unroll
+  for (int tile = 0; tile < NT; ++tile) {
+    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = tile * 8 + r;
+      if (i < S * S) dmma884_acc(c0, c1, sel[r], w[i]);
+    }
+    double v = c0 + c1;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    const int idx = tile * 8 + g;
+    if (t == 0 && idx < S * S && v != 0.0) atomicAdd(&Wc[idx], v);
+  }
+}
 // sites per thread: more sites amortise the per-op work (program decode, P loads, the
 // cross-lane reduction of W) over more arithmetic; bounded by registers
 #ifndef RT_WALK_NS
@@ -295,6 +333,9 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
   }
   __syncthreads();
 
+  double sel[8];     // A-fragment row selectors of reduce_w_dmma
+#pragma unroll
+  for (int r = 0; r < 8; ++r) sel[r] = ((lane >> 2) == r) ? 1.0 : 0.0;
   const int64_t tile_sites = (int64_t)kWalkBlock * NS;
   const int64_t tiles = (n_sites + tile_sites - 1) / tile_sites;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -496,6 +537,9 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
           }
         }
         // W_c += sum over the warp's 32*NS sites of G (x) L
+        if (RT_WALK_DMMA_REDUCE) {
+          reduce_w_dmma<S, V>(w, sel, lane, W_s + c * S * S);
+        } else {
         reduce_scatter_warp<V>(w, lane);
         if (V == 16) {
           if ((lane & 1) == 0 && (lane >> 1) < S * S && w[0] != 0.0)
@@ -505,6 +549,7 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
         } else {
           if (2 * lane < S * S && w[0] != 0.0) atomicAdd(&W_s[c * S * S + 2 * lane], w[0]);
           if (2 * lane + 1 < S * S && w[1] != 0.0) atomicAdd(&W_s[c * S * S + 2 * lane + 1], w[1]);
+        }
         }
       }
     };
