@@ -348,7 +348,7 @@ def run_gpu(args):
     roofline = dict(bound='hbm', kernel='down_walk_kernel<4,codes> (1 launch/step, %.0f%% of the step)'
                     % (100 * down_ms / ms), achieved=down_gbs, peak=peaks['hbm_gbs'], unit='GB/s',
                     frac=down_gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
-                    traffic=ncu_traffic('down_walk_kernel<4, 0>'),
+                    traffic=ncu_traffic('down_walk_kernel<4, 0'),
                     algorithmic_bytes_per_launch=N * down_b, ms=down_ms,
                     note='S=4 walk is issue / FP64-pipe bound, not HBM bound (ncu, profiles/'
                          'r1_ncu_full_summary.json: issue active 53%, fp64 pipe 38%, dram 18%); it reads '

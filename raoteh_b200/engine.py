@@ -214,7 +214,7 @@ class TreeMJP(object):
         return res
 
     # ---- K4 / K5 ------------------------------------------------------------
-    def _posterior_overlapped(self, obs, n_chunks):
+    def _posterior_overlapped(self, obs, n_chunks, use_graph=True):
         """Up + down pass for S <= 8 with the site axis cut into chunks that alternate between
         two streams: the kernels of different chunks are independent, so the write-heavy
         pruning kernel of one chunk runs under the issue-bound walk of another and no kernel's
@@ -232,10 +232,40 @@ class TreeMJP(object):
         rps = self._buf('root_post_sum', (S,), torch.float64, zero=True)
         lp = prog['level_ptr']
         esz = {OBS_CODES: 1, OBS_MASK: 8, OBS_DENSE: 8}[obs.kind]
-        cur = torch.cuda.current_stream()
         if getattr(self, '_ov_streams', None) is None:
             self._ov_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            self._ov_graphs = {}
+        res = dict(loglik=loglik, status=status, partials=partials, exponents=None, node_distn=None,
+                   W=W, root_post_sum=rps, n_levels=len(lp) - 1)
+        # the chunk schedule is launch-bound on the host (2 launches per chunk), so it is
+        # captured once per (observations, chunking) into a CUDA graph and replayed
+        key = (obs.data.data_ptr(), N, stride, n_chunks, P.data_ptr(), partials.data_ptr(),
+               loglik.data_ptr(), W.data_ptr())
+        g = self._ov_graphs.get(key)
+        if g is not None:
+            g.replay()
+            return res
+        if use_graph:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._ov_launch(obs, prog, P, partials, loglik, status, W, rps, n_chunks)
+            self._ov_graphs[key] = g
+            g.replay()
+            return res
+        self._ov_launch(obs, prog, P, partials, loglik, status, W, rps, n_chunks)
+        return res
+
+    def _ov_launch(self, obs, prog, P, partials, loglik, status, W, rps, n_chunks):
+        lib = _native.lib()
+        S, n = self.S, self.sched.n
+        N, stride = obs.n_sites, obs.stride
+        lp = prog['level_ptr']
+        esz = {OBS_CODES: 1, OBS_MASK: 8, OBS_DENSE: 8}[obs.kind]
+        cur = torch.cuda.current_stream()
         chunk = _round_up((N + n_chunks - 1) // n_chunks, 256)
+        W.zero_()
+        rps.zero_()
         for cs in self._ov_streams:
             cs.wait_stream(cur)
         for k, lo in enumerate(range(0, N, chunk)):
@@ -255,8 +285,6 @@ class TreeMJP(object):
             _native.check(rc, 'rt_posterior_stats')
         for cs in self._ov_streams:
             cur.wait_stream(cs)
-        return dict(loglik=loglik, status=status, partials=partials, exponents=None, node_distn=None,
-                    W=W, root_post_sum=rps, n_levels=len(lp) - 1)
 
     def posterior(self, obs, want_exponents=False, want_node_distn=True, overlap_chunks=0):
         """Up + down pass.  Returns loglik, status, partials, node_distn (internal
