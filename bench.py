@@ -369,17 +369,17 @@ def run_gpu(args):
         except Exception as e:
             extra['c2_loglik_only'] = dict(error=repr(e))
         try:
-            from raoteh_b200 import raoteh_bench
+            import bench_legs as raoteh_bench
             extra['c4_raoteh_sweeps'] = raoteh_bench.bench_c4(dev, args)
         except Exception as e:
             extra['c4_raoteh_sweeps'] = dict(error=repr(e))
         try:
-            from raoteh_b200 import raoteh_bench
+            import bench_legs as raoteh_bench
             extra['c5_tolerance'] = raoteh_bench.bench_c5(dev, args)
         except Exception as e:
             extra['c5_tolerance'] = dict(error=repr(e))
         try:
-            from raoteh_b200 import raoteh_bench
+            import bench_legs as raoteh_bench
             extra['codon_raoteh_sweeps'] = raoteh_bench.bench_codon_raoteh(dev, args)
         except Exception as e:
             extra['codon_raoteh_sweeps'] = dict(error=repr(e))

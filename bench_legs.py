@@ -1,5 +1,6 @@
-"""C4 benchmark leg: Rao-Teh Gibbs sweeps, 4-state HKY on a 64-leaf tree
-(BASELINE.json configs[3]); used by bench.py `extra`."""
+"""Benchmark legs behind bench.py `extra`: C4 (Rao-Teh sweeps, BASELINE.json configs[3]), C5
+(tolerance model: likelihood, blocked Gibbs sampler, summary) and 61-state Rao-Teh.  Lives
+beside bench.py, not in the package: its CPU legs run the oracle port."""
 from __future__ import annotations
 
 import time
@@ -9,9 +10,9 @@ import torch
 
 
 def bench_c4(dev, args, n_chains=128, n_sites=10_000, sweeps_per_launch=25, launches=4):
-    from . import engine, synth
-    from .lowering import TreeSchedule
-    from .raoteh import RaoTehChains
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
     cfg = synth.config_c4(n_sites=n_sites)
     sched = TreeSchedule(cfg['parent'], cfg['length'])
     obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'], device=dev)
@@ -73,9 +74,9 @@ def bench_c5(dev, args, n_sites=100_000, sweeps_per_launch=5, launches=3, loglik
     """C5 legs: (a) 61-state pruning log-likelihood under the primary proposal model on the
     25-taxon tree, (b) blocked Gibbs sweeps of the compound tolerance process (61 codons x 20
     amino-acid classes) with the Rao-Blackwellised tolerance summary fused after every sweep."""
-    from . import engine, synth
-    from .lowering import TreeSchedule
-    from .tmjp import ToleranceChains
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.tmjp import ToleranceChains
     cfg = synth.config_c5(n_sites=max(n_sites, loglik_sites))
     sched = TreeSchedule(cfg['parent'], cfg['length'])
     out = dict(workload='C5: 61 codons x 20 tolerance classes, 25-taxon tree (48 edges x 0.1)')
@@ -156,9 +157,9 @@ def bench_c5(dev, args, n_sites=100_000, sweeps_per_launch=5, launches=3, loglik
 
 def bench_codon_raoteh(dev, args, n_sites=20_000, n_chains=4, sweeps_per_launch=5, launches=3):
     """Plain Rao-Teh sweeps of the 61-state codon model on the C3 tree (warp-per-trajectory)."""
-    from . import engine, synth
-    from .lowering import TreeSchedule
-    from .raoteh import RaoTehChains
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
     cfg = synth.config_c3(n_sites=n_sites)
     sched = TreeSchedule(cfg['parent'], cfg['length'])
     obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'], device=dev)

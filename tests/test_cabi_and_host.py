@@ -40,7 +40,7 @@ def test_product_never_imports_the_oracle():
     offenders = []
     for dp, dn, fn in os.walk(pkg):
         for f in fn:
-            if f.endswith('.py') and f != 'raoteh_bench.py':
+            if f.endswith('.py'):
                 text = open(os.path.join(dp, f)).read()
                 if re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M):
                     offenders.append(f)

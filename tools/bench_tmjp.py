@@ -1,7 +1,7 @@
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from raoteh_b200 import raoteh_bench
+import bench_legs as raoteh_bench
 dev = torch.device('cuda:0')
 which = sys.argv[1] if len(sys.argv) > 1 else 'all'
 if which in ('all', 'c5'):
