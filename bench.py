@@ -280,7 +280,8 @@ def run_gpu(args):
         mjp.events = sub if record else None
         mjp.set_rate_matrix(cfg['Q'])
         r = mjp.expected_history_statistics(obs, overlap_chunks=0 if record else DEV_CHUNKS)
-        stats = rdist.pack_stats(r['loglik'].sum(), r['dwell'], r['trans'], r['root_post_sum'])
+        ll_sum = r['loglik_sum'] if 'loglik_sum' in r else r['loglik'].sum()
+        stats = rdist.pack_stats(ll_sum, r['dwell'], r['trans'], r['root_post_sum'])
         rdist.allreduce_stats(stats)      # the path's only collective (NCCL, 1+S+S*S+S doubles)
         state['n_levels'] = r['n_levels']
         return r, stats

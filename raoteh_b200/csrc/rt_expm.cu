@@ -220,6 +220,157 @@ expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
   for (size_t i = tid; i < nn; i += kThreads) A[i] = R[i];
 }
 
+// ---------------------------------------------------------------------------------------
+// Small matrices (n <= 16: every S <= 16 transition matrix, the Frechet block form for S <= 8):
+// one WARP per matrix, all seven n x n work matrices in shared memory, lanes own elements, only
+// __syncwarp between the steps.  The generic kernel above spends ~25 us on a 4 x 4 matrix in
+// block-wide barriers around a 64 x 64 tile loop; this one is a dependent chain of ~40 short steps.
+// Same algorithm (Pade-13, scaling and squaring, LU with partial pivoting).
+// ---------------------------------------------------------------------------------------
+constexpr int kSmallMax = 16;
+constexpr int kSmallWarps = 4;
+
+__device__ __forceinline__ void mm_w(double* C, const double* A, const double* B, int n, int lane) {
+  for (int e = lane; e < n * n; e += 32) {
+    const int i = e / n, j = e % n;
+    double acc = 0.0;
+    for (int k = 0; k < n; ++k) acc = fma(A[i * n + k], B[k * n + j], acc);
+    C[e] = acc;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kSmallWarps * 32)
+expm_small_kernel(double* __restrict__ mats, int n, int n_mat) {
+  extern __shared__ double smw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * kSmallWarps + warp;
+  if (m >= n_mat) return;
+  const int nn = n * n;
+  double* A = smw + (size_t)warp * 8 * nn;
+  double *A2 = A + nn, *A4 = A + 2 * nn, *A6 = A + 3 * nn, *T1 = A + 4 * nn, *U = A + 5 * nn,
+         *V = A + 6 * nn, *T2 = A + 7 * nn;
+  double* G = mats + (size_t)m * nn;
+  for (int e = lane; e < nn; e += 32) A[e] = G[e];
+  __syncwarp();
+  // 1-norm
+  double cmax = 0.0;
+  for (int j = lane; j < n; j += 32) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += fabs(A[i * n + j]);
+    cmax = fmax(cmax, t);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+  int s = 0;
+  if (cmax > kTheta13) {
+    s = (int)ceil(log2(cmax / kTheta13));
+    if (s < 0) s = 0;
+    const double sc = ldexp(1.0, -s);
+    for (int e = lane; e < nn; e += 32) A[e] *= sc;
+  }
+  __syncwarp();
+  const double* b = kPade13;
+  mm_w(A2, A, A, n, lane);
+  mm_w(A4, A2, A2, n, lane);
+  mm_w(A6, A4, A2, n, lane);
+  for (int e = lane; e < nn; e += 32) {
+    const double a2 = A2[e], a4 = A4[e], a6 = A6[e];
+    T1[e] = b[13] * a6 + b[11] * a4 + b[9] * a2;
+    T2[e] = b[12] * a6 + b[10] * a4 + b[8] * a2;
+  }
+  __syncwarp();
+  mm_w(U, A6, T1, n, lane);
+  mm_w(V, A6, T2, n, lane);
+  for (int e = lane; e < nn; e += 32) {
+    const double a2 = A2[e], a4 = A4[e], a6 = A6[e];
+    const bool diag = (e / n) == (e % n);
+    T1[e] = U[e] + b[7] * a6 + b[5] * a4 + b[3] * a2 + (diag ? b[1] : 0.0);
+    V[e] = V[e] + b[6] * a6 + b[4] * a4 + b[2] * a2 + (diag ? b[0] : 0.0);
+  }
+  __syncwarp();
+  mm_w(U, A, T1, n, lane);
+  for (int e = lane; e < nn; e += 32) {
+    const double u = U[e], v = V[e];
+    T1[e] = v - u;     // M
+    T2[e] = v + u;     // B
+  }
+  __syncwarp();
+  double* M = T1;
+  double* B = T2;
+  for (int k = 0; k < n; ++k) {
+    // pivot: lanes k..n-1 hold |M[i][k]|
+    double best = (lane >= k && lane < n) ? fabs(M[lane * n + k]) : -1.0;
+    int bi = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const int p = bi;
+    if (p != k) {
+      for (int j = lane; j < 2 * n; j += 32) {
+        double* X = (j < n) ? M : B;
+        const int jj = (j < n) ? j : j - n;
+        const double t = X[k * n + jj];
+        X[k * n + jj] = X[p * n + jj];
+        X[p * n + jj] = t;
+      }
+    }
+    __syncwarp();
+    const double pinv = 1.0 / M[k * n + k];
+    const int rows = n - k - 1, cols = (n - k - 1) + n;
+    // multipliers first (column k is read by every element of its row)
+    double lmul = (lane > k && lane < n) ? M[lane * n + k] * pinv : 0.0;
+    __syncwarp();
+    for (int base = 0; base < rows * cols; base += 32) {     // warp-uniform trip count
+      const int idx = base + lane;
+      const bool on = idx < rows * cols;
+      const int i = on ? k + 1 + idx / cols : 0, c = on ? idx % cols : 0;
+      const double l = __shfl_sync(0xffffffffu, lmul, i);
+      if (on) {
+        if (c < n - k - 1) {
+          const int j = k + 1 + c;
+          M[i * n + j] = fma(-l, M[k * n + j], M[i * n + j]);
+        } else {
+          const int j = c - (n - k - 1);
+          B[i * n + j] = fma(-l, B[k * n + j], B[i * n + j]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  for (int j = lane; j < n; j += 32) {
+    for (int k = n - 1; k >= 0; --k) {
+      double v = B[k * n + j];
+      for (int c = k + 1; c < n; ++c) v = fma(-M[k * n + c], B[c * n + j], v);
+      B[k * n + j] = v / M[k * n + k];
+    }
+  }
+  __syncwarp();
+  double* R = B;
+  double* O = U;
+  for (int i = 0; i < s; ++i) {
+    mm_w(O, R, R, n, lane);
+    double* t = R; R = O; O = t;
+  }
+  for (int e = lane; e < nn; e += 32) G[e] = R[e];
+}
+
+static int launch_expm(double* mats, int n, int n_mat, double* scratch, cudaStream_t stream) {
+  if (n <= kSmallMax) {
+    const size_t smem = sizeof(double) * 8 * (size_t)n * n * kSmallWarps;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(expm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    expm_small_kernel<<<(n_mat + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, smem, stream>>>(
+        mats, n, n_mat);
+  } else {
+    expm_kernel<<<n_mat, kThreads, 0, stream>>>(mats, n, scratch);
+  }
+  return 0;
+}
+
 __global__ void build_scaled_kernel(const double* __restrict__ Q, const int32_t* __restrict__ q_index,
                                     const double* __restrict__ t, int S, double* __restrict__ out) {
   const int m = blockIdx.x;
@@ -284,7 +435,7 @@ int rt_expm_batched_impl(const double* Q, const int32_t* q_index, const double* 
   double* scratch = nullptr;
   RT_CUDA_CHECK(cudaMallocAsync(&scratch, sizeof(double) * 7 * (size_t)S * S * n_mat, stream));
   build_scaled_kernel<<<n_mat, 256, 0, stream>>>(Q, q_index, t, S, P);
-  expm_kernel<<<n_mat, kThreads, 0, stream>>>(P, S, scratch);
+  launch_expm(P, S, n_mat, scratch, stream);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(scratch, stream);
   RT_CUDA_CHECK(e);
@@ -304,7 +455,7 @@ int rt_frechet_contract_impl(const double* Q, const int32_t* q_index, const doub
   double* scratch = buf + nn * n_mat;
   double* scale = buf + 8 * nn * n_mat;
   build_frechet_kernel<<<n_mat, 256, 0, stream>>>(Q, q_index, t, W, S, blk, scale);
-  expm_kernel<<<n_mat, kThreads, 0, stream>>>(blk, n, scratch);
+  launch_expm(blk, n, n_mat, scratch, stream);
   extract_frechet_kernel<<<n_mat, 256, 0, stream>>>(blk, t, scale, S, M);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(buf, stream);

@@ -293,7 +293,10 @@ class TreeMJP(object):
         schedule, see _posterior_overlapped."""
         if overlap_chunks > 1 and self.S <= 8 and not want_node_distn and not want_exponents:
             return self._posterior_overlapped(obs, int(overlap_chunks))
-        up = self.log_likelihood(obs, keep_partials=True, want_exponents=want_exponents)
+        llsum = self._buf('loglik_sum', (1,), torch.float64, zero=True)
+        up = self.log_likelihood(obs, keep_partials=True, want_exponents=want_exponents,
+                                 loglik_sum=llsum)
+        up['loglik_sum'] = llsum[0]      # sum of the finite log-likelihoods, reduced by the kernel
         prog = self._programs(obs)
         N, stride = obs.n_sites, obs.stride
         dev = self.device
