@@ -108,6 +108,7 @@ def bench_c5(dev, args, n_sites=100_000, sweeps_per_launch=5, launches=3, loglik
                          tol_obs_nodes=cfg['tol_obs_nodes'], cap_p=96, cap_t=48, seed=20260205, device=dev)
     k = ch.initialize()
     ch.sweep(3, stats=False)
+    ch.sweep(1, stats=False, summary=True)    # warm-up of the summary path (scratch pool growth)
     torch.cuda.synchronize()
     res = {}
     for name, summary in (('sweep', False), ('sweep_plus_summary', True)):
