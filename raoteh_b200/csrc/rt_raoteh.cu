@@ -172,7 +172,9 @@ raoteh_kernel(SweepArgs A) {
           float pos = tc;                  // current position (moving toward 0)
           int init_left = 0;
           if (A.init_k >= 0) {
-            init_left = A.init_k;
+            // no events on a zero-length branch: its end states are equal (P(0) = I), and a jump
+            // at time 0 would be indistinguishable from 'no more jumps' in the sweeps
+            init_left = tc > 0.0f ? A.init_k : 0;
           } else {
             cur = ns_p[(int64_t)c * st];
             k_old = cnt_p[(int64_t)c * st];

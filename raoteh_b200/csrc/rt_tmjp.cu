@@ -214,7 +214,7 @@ __device__ int primary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
       float my_next = -1.0f;
       int my_k = 0;
       if (init) {
-        init_left = A.init_k;
+        init_left = tc > 0.0f ? A.init_k : 0;   // no events on a zero-length branch (P(0) = I)
       } else {
         cur = W.pn[c];
         k_old = W.pc[c];
@@ -478,7 +478,7 @@ __device__ int tol_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int la
           float cand;
           bool is_old = false, is_virtual = false, is_event = true;
           if (init) {
-            if (placed) {
+            if (placed || !(pos > bound)) {     // (no event inside a zero-length segment)
               is_event = false;
               cand = bound;
             } else {

@@ -342,3 +342,72 @@ def test_branch_expectations_per_site(S, n_leaves, n_sites):
     tot = mjp.branch_expectations(obs)['branch'].sum()
     ehs = mjp.expected_history_statistics(obs)
     np.testing.assert_allclose(float(tot), float(ehs['trans'].sum()), rtol=1e-9)
+
+
+def _tree(kind):
+    if kind == 'star':         # one polytomy: root with 7 leaves
+        return np.array([-1, 0, 0, 0, 0, 0, 0, 0], dtype=np.int32)
+    if kind == 'path':         # a chain of degree-2 nodes ending in one leaf
+        return np.array([-1, 0, 1, 2, 3, 4], dtype=np.int32)
+    if kind == 'edge':         # a single branch
+        return np.array([-1, 0], dtype=np.int32)
+    if kind == 'mixed':        # polytomy + degree-2 nodes + zero-length branch
+        return np.array([-1, 0, 1, 1, 1, 0, 5, 6, 6, 0], dtype=np.int32)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize('kind', ['star', 'path', 'edge', 'mixed'])
+@pytest.mark.parametrize('S', [2, 4, 7, 13, 64])
+def test_unusual_trees_and_extreme_state_counts(kind, S):
+    """Edge cases the reference's tests cover with hand-made trees (tests/test_mc.py:244-467,
+    test_mjp.py:52-89): polytomies, chains of degree-2 nodes, a single branch, a zero-length
+    branch, observed internal nodes, all-missing sites, 1 site, S = 2 and S = 64.
+    Log-likelihood and expectations vs the oracle, relative 1e-10."""
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+    rng = np.random.default_rng(S * 7 + len(kind))
+    parent = _tree(kind)
+    n = len(parent)
+    length = rng.uniform(0.05, 0.6, size=n)
+    length[0] = 0.0
+    if kind == 'mixed':
+        length[3] = 0.0
+    Q = rng.exponential(1.0, size=(S, S))
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    Q /= np.abs(np.diag(Q)).mean()
+    pi = rng.dirichlet(np.ones(S) * 2)
+    for n_sites in (1, 37):
+        full = np.uint64((1 << S) - 1) if S < 64 else np.uint64(0xFFFFFFFFFFFFFFFF)
+        mask = np.full((n, n_sites), full, dtype=np.uint64)
+        # a true history per site keeps every site feasible (also across the zero-length branch)
+        Pt = np_oracle.expm_edges(Q, length)
+        truth = np.zeros((n, n_sites), dtype=int)
+        truth[0] = rng.choice(S, size=n_sites, p=pi)
+        for v in range(1, n):
+            for i in range(n_sites):
+                p = np.maximum(Pt[v][truth[parent[v], i]], 0)
+                truth[v, i] = rng.choice(S, p=p / p.sum())
+        for v in range(n):
+            for i in range(n_sites):
+                r = rng.random()
+                if r < 0.5:                                  # a hard observation, also at internal nodes
+                    mask[v, i] = np.uint64(1) << np.uint64(truth[v, i])
+                elif r < 0.7:                                # a set of allowed states
+                    m = 1 << int(truth[v, i])
+                    for s in rng.choice(S, size=min(S, 3), replace=False):
+                        m |= 1 << int(s)
+                    mask[v, i] = np.uint64(m)
+        mask[:, 0] = full                                    # site 0: nothing observed anywhere
+        sched = TreeSchedule(parent, length)
+        mjp = engine.TreeMJP(sched, Q, root_distn=pi)
+        obs = engine.Observations.from_masks(sched, mask)
+        r = mjp.expected_history_statistics(obs)
+        P = np_oracle.expm_edges(Q, length)
+        o = np_oracle.expected_history_statistics(parent, length, Q, P, np_oracle.Obs('mask', S, n_sites, mask=mask), pi)
+        ll = r['loglik'].cpu().numpy()
+        np.testing.assert_allclose(ll, o['loglik'], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(ll[0], 0.0, atol=1e-12)   # no data: likelihood 1
+        np.testing.assert_allclose(r['dwell'].cpu().numpy(), o['dwell'], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(r['trans'].cpu().numpy(), o['trans'], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(float(r['dwell'].sum()), length.sum() * n_sites, rtol=1e-10)

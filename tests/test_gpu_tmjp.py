@@ -577,3 +577,61 @@ def test_device_metropolis_hastings_targets_the_compound_process():
     n_total = groups * n_chains * n_steps
     _assert_z(dwell, want_dwell, n_total)
     _assert_z(trans, want_trans.ravel(), n_total)
+
+
+def test_samplers_on_polytomies_chains_and_maximum_sizes():
+    """Structure of sampled histories on a tree with a polytomy, a chain of degree-2 nodes and a
+    zero-length branch, for the plain sampler with 64 states and the tolerance sampler with 64
+    primary states in 32 classes (the maxima of the warp kernels)."""
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
+    from raoteh_b200.tmjp import ToleranceChains
+    parent = np.array([-1, 0, 1, 1, 1, 0, 5, 6, 6, 0], dtype=np.int32)
+    rng = np.random.default_rng(12)
+    length = rng.uniform(0.1, 0.5, size=len(parent))
+    length[0] = 0.0
+    length[3] = 0.0
+    S = 64
+    Q = rng.exponential(1.0, size=(S, S)) * (rng.random((S, S)) < 0.2)
+    Q += np.roll(np.eye(S), 1, axis=1) + np.roll(np.eye(S), -1, axis=1)
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    Q /= np.abs(np.diag(Q)).mean()
+    pi = np.ones(S) / S
+    sched = TreeSchedule(parent, length)
+    leaves = sched.leaves
+    codes = rng.integers(0, S, size=(len(leaves), 3)).astype(np.uint8)
+    codes[0, 1] = 255
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaves)
+    ch = RaoTehChains(sched, Q, obs, n_chains=5, root_distn=pi, seed=2, cap=400)
+    ch.sweep(10)
+    for t in range(ch.n_traj):
+        ns, edges = ch.trajectory(t)
+        assert len(edges[3][0]) == 0 and ns[3] == ns[1]          # nothing happens on a zero-length branch
+        for c, (times, states) in edges.items():
+            assert states[0] == ns[parent[c]] and states[-1] == ns[c]
+            assert np.all(states[1:] != states[:-1])
+            for a, b in zip(states[:-1], states[1:]):
+                assert Q[a, b] > 0
+        for i, leaf in enumerate(leaves):
+            if codes[i, t % 3] != 255:
+                assert ns[leaf] == codes[i, t % 3]
+    part = dict((s, s % 32) for s in range(S))
+    tc = ToleranceChains(sched, Q, pi, part, 0.8, 1.1, obs, n_chains=4, cap_p=400, cap_t=64, seed=5)
+    tc.sweep(8, summary=True)
+    for t in range(0, tc.n_traj, 5):
+        ns, edges = tc.primary_trajectory(t)
+        for c, (times, states) in edges.items():
+            bounds = np.concatenate([[0.0], times, [length[c]]])
+            for i, s in enumerate(states):
+                bits, tedges = tc.tolerance_trajectory(t, part[int(s)])
+                tt, ts = tedges[c]
+                tb = np.concatenate([[0.0], tt, [length[c]]])
+                for j, on in enumerate(ts):
+                    if min(bounds[i + 1], tb[j + 1]) - max(bounds[i], tb[j]) > 1e-7:
+                        assert on == 1
+    out = tc.summary_out.cpu().numpy()
+    np.testing.assert_allclose(out[:, 0] + out[:, 1], 32.0, rtol=1e-12)
+    np.testing.assert_allclose(out[:, 2] + out[:, 3], 32.0 * length.sum(), rtol=1e-12)
+    assert np.isfinite(out).all()
