@@ -345,3 +345,46 @@ def test_reader_pipeline_matches_per_column_calls():
                 allowed[name_to_leaf[nme]] = {c2s[cod]}
         lk = _mjp_dense.get_likelihood(T, allowed, root, 8, root_distn=distn, Q_default=Q)
         assert_allclose(ll[j], np.log(lk), rtol=1e-10)
+
+
+def test_linalg_special_cases_match_scipy():
+    """raoteh/sampler/tests/test_expm.py:45-82 (the three restriction classes of the 3-state
+    tolerance matrix: w > 0; w = 0, a != r; w = 0, a == r) for sparse_expm, plus the matching
+    cases of simple_expm_frechet against scipy.linalg.expm_frechet, and the reachability pattern
+    of sparse_expm_naive."""
+    import scipy.linalg
+    from raoteh_b200.sampler import _linalg
+    from raoteh_b200.sampler._util import get_dense_rate_matrix
+    rs = np.random.RandomState(1234)
+    for t in np.logspace(-5, 5, 4, base=2):
+        for kind in 'abc':
+            a, w, r = rs.exponential(size=3)
+            Q = nx.DiGraph()
+            if kind == 'a':
+                Q.add_weighted_edges_from([(0, 1, a), (1, 0, w), (1, 2, r)])
+            elif kind == 'b':
+                Q.add_weighted_edges_from([(0, 1, a), (1, 2, r)])
+            else:
+                Q.add_weighted_edges_from([(0, 1, a), (1, 2, a)])
+            states, Qd = get_dense_rate_matrix(Q)
+            want = scipy.linalg.expm(Qd * t)
+            P = _linalg.sparse_expm(Q, t)
+            got = np.zeros_like(want)
+            for sa in states:
+                for sb in states:
+                    if P.has_edge(sa, sb):
+                        got[sa, sb] = P[sa][sb]['weight']
+            assert_allclose(got, want, rtol=1e-10, atol=1e-13)
+            assert _linalg.expm_frechet_is_simple(Q)
+            for (ai, bi, ci, di) in ((0, 0, 0, 0), (0, 1, 0, 1), (1, 1, 1, 1), (1, 0, 1, 0), (0, 1, 1, 1)):
+                E = np.zeros((3, 3))
+                E[ci, di] = 1.0
+                K = scipy.linalg.expm_frechet(t * Qd, t * E, compute_expm=False)
+                got = _linalg.simple_expm_frechet(Q, ai, bi, ci, di, t)
+                assert_allclose(got, K[ai, bi], rtol=1e-9, atol=1e-13)
+    # structural zeros of the generic path: 0 -> 1 -> 2, nothing leads back
+    Q = nx.DiGraph()
+    Q.add_weighted_edges_from([('x', 'y', 1.0), ('y', 'z', 2.0)])
+    P = _linalg.sparse_expm(Q, 0.7)
+    assert set(P.edges()) == {('x', 'x'), ('x', 'y'), ('x', 'z'), ('y', 'y'), ('y', 'z'), ('z', 'z')}
+    assert_allclose(sum(P['x'][s]['weight'] for s in P['x']), 1.0, rtol=1e-12)

@@ -145,7 +145,12 @@ def test_tolerance_summary_kernel_matches_generic_path_fp64_times():
             ns[t, c] = cur
             ej[c] = (list(times), sbs)
         jumps.append(ej)
-    for rate_on, rate_off in ((1.0, 1.0), (0.3, 2.0), (2.0, 0.0)):
+    # the last two: w = 0 for every segment, and rate_on EQUAL to one of the absorption rates
+    # (the reference's 'defective' case, raoteh/sampler/_linalg.py:116-118)
+    from raoteh_b200.tmjp import absorption_rates
+    a_eq = float(absorption_rates(Q, part, 3)[0, 1])
+    assert a_eq > 0
+    for rate_on, rate_off in ((1.0, 1.0), (0.3, 2.0), (2.0, 0.0), (a_eq, 0.0)):
         ch = _chains_for_fixture(sched, Q, part, rate_on, rate_off, n_traj, None)
         ch.load_primary_trajectories(ns, jumps)
         out = ch.tolerance_summary().cpu().numpy()
