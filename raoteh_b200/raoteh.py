@@ -23,11 +23,17 @@ class RaoTehChains(object):
     """
 
     def __init__(self, sched, Q, obs, n_chains=1, root_distn=None, uniformization_factor=2.0,
-                 cap=96, seed=0, device='cuda', traj0=0, n_traj=None):
+                 cap=96, seed=0, device='cuda', traj0=0, n_traj=None, chain_matrix=None):
+        """chain_matrix: instead of a rate matrix, a transition matrix B applied at every
+        candidate event, with no virtual events (Poisson rates 0): the discrete-time chain
+        samplers of raoteh/sampler/_sample_mcy.py / _sample_mcx.py are this special case."""
         if not torch.cuda.is_available():
             raise _native.NativeError('raoteh_b200 needs a CUDA device; there is no CPU fallback')
         if uniformization_factor <= 1:
             raise ValueError('the uniformization factor must be greater than 1')
+        if chain_matrix is not None:
+            Bc = np.asarray(chain_matrix, dtype=np.float64)
+            Q = Bc - np.eye(Bc.shape[0])          # placeholder generator with the same pattern
         Q = np.asarray(Q, dtype=np.float64)
         self.S = S = Q.shape[0]
         if not 2 <= S <= 64:
@@ -49,11 +55,16 @@ class RaoTehChains(object):
         q = -np.diag(Q)
         self.omega = float(uniformization_factor * q.max())
         if not self.omega > 0:
-            raise ValueError('the rate matrix is empty')
+            if chain_matrix is None:
+                raise ValueError('the rate matrix is empty')
+            self.omega = 1.0
         B = np.eye(S) + Q / self.omega
+        rate = self.omega - q
+        if chain_matrix is not None:
+            B, rate, self.omega = Bc, np.zeros(S), 1.0
         self.Q_host = Q
-        self.B = torch.from_numpy(B).to(dev)
-        self.rate = torch.from_numpy(self.omega - q).to(dev)
+        self.B = torch.from_numpy(np.ascontiguousarray(B)).to(dev)
+        self.rate = torch.from_numpy(np.ascontiguousarray(rate)).to(dev)
         self.root_distn = None if root_distn is None else torch.from_numpy(
             np.asarray(root_distn, dtype=np.float64).copy()).to(dev)
         ops, n_slots = sched.up_program(obs.obs_slot)
@@ -156,6 +167,34 @@ class RaoTehChains(object):
         A.traj_loglik = _ptr(out)
         _native.check(_native.lib().rt_tmjp_run(ctypes.byref(A), _stream()), 'rt_tmjp_run')
         return out
+
+    def load_events(self, edge_times):
+        """Install the same candidate events on every trajectory: edge_times[child node] = event
+        times from the parent end.  The next sweep runs FFBS over exactly these events (plus
+        virtual ones if the Poisson rates are positive)."""
+        n = self.sched.n
+        ops = self.ops.cpu().numpy()
+        order = [int(c) for code, c, a, b in ops if (code & 0xff) <= 2]
+        cnt = np.zeros(n, dtype=np.uint8)
+        tt = []
+        for c in order:
+            ts = sorted(float(x) for x in edge_times.get(c, ()))
+            cnt[c] = len(ts)
+            tt.extend(ts[::-1])                # child end first
+        k = len(tt)
+        if k > self.cap:
+            raise ValueError('more events than cap')
+        row = np.zeros(self.cap, dtype=np.float32)
+        if k:
+            row[self.cap - k:] = tt
+        dev = self.device
+        self.ev_time.copy_(torch.from_numpy(row).to(dev)[None, :].expand(self.n_traj, -1))
+        self.ev_sb.zero_()
+        self.ev_count.copy_(torch.from_numpy(cnt).to(dev)[:, None].expand(-1, self.n_traj))
+        self.ev_total.fill_(k)
+        self.node_state.zero_()
+        self.status.zero_()
+        self.initialized = True
 
     _STATE = ('node_state', 'ev_count', 'ev_total', 'ev_time', 'ev_sb')
 

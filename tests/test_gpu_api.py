@@ -388,3 +388,63 @@ def test_linalg_special_cases_match_scipy():
     P = _linalg.sparse_expm(Q, 0.7)
     assert set(P.edges()) == {('x', 'x'), ('x', 'y'), ('x', 'z'), ('y', 'y'), ('y', 'z'), ('z', 'z')}
     assert_allclose(sum(P['x'][s]['weight'] for s in P['x']), 1.0, rtol=1e-12)
+
+
+def _path_P(self_loops):
+    P = nx.DiGraph()
+    if self_loops:
+        P.add_weighted_edges_from([(0, 0, 0.5), (1, 1, 0.5), (2, 2, 0.5), (3, 3, 0.5), (0, 1, 0.5),
+                                   (1, 0, 0.25), (1, 2, 0.25), (2, 1, 0.25), (2, 3, 0.25), (3, 2, 0.5)])
+    else:
+        P.add_weighted_edges_from([(0, 1, 1.0), (1, 0, 0.5), (1, 2, 0.5), (2, 1, 0.5), (2, 3, 0.5),
+                                   (3, 2, 1.0)])
+    return P
+
+
+def test_chain_state_samplers_deterministic_answers():
+    """The known-answer tests of raoteh/sampler/tests/test_sample_mcx.py:21-149 (node states;
+    short path, infeasible chain, separated regions) and :154-235 (edge states with event
+    nodes): whenever only one assignment is feasible the sampler must return it, for every
+    choice of root."""
+    from raoteh_b200.sampler import _sample_mcx
+    from raoteh_b200.sampler._util import StructuralZeroProb
+    P = _path_P(False)
+    T = nx.Graph()
+    T.add_edges_from([(0, 1), (1, 2)])
+    for root in T:
+        with pytest.raises(StructuralZeroProb):
+            _sample_mcx.resample_states(T, root, {0: 0, 2: 3}, P_default=P)
+    uniform = {0: 0.25, 1: 0.25, 2: 0.25, 3: 0.25}
+    for root in T:
+        assert _sample_mcx.resample_states(T, root, {0: 0, 2: 2}, root_distn=uniform,
+                                           P_default=P) == {0: 0, 1: 1, 2: 2}
+        assert _sample_mcx.resample_states(T, root, {0: 3, 2: 1},
+                                           root_distn={0: 0.1, 1: 0.2, 2: 0.3, 3: 0.4},
+                                           P_default=P) == {0: 3, 1: 2, 2: 1}
+        with pytest.raises(StructuralZeroProb):       # no transitions allowed at all
+            _sample_mcx.resample_states(T, root, {0: 0, 2: 2}, root_distn=uniform,
+                                        P_default=nx.DiGraph())
+    T = nx.Graph()
+    T.add_edges_from([(0, 10), (0, 20), (0, 30), (10, 11), (20, 21), (30, 31), (31, 32)])
+    for root in T:
+        got = _sample_mcx.resample_states(T, root, {0: 0, 11: 2, 21: 2, 32: 3}, root_distn=uniform,
+                                          P_default=P)
+        assert got == {0: 0, 10: 1, 11: 2, 20: 1, 21: 2, 30: 1, 31: 2, 32: 3}
+    # edge states with event nodes (:154-235)
+    P = _path_P(True)
+    T = nx.Graph()
+    T.add_weighted_edges_from([(0, 10, 1.0), (0, 20, 1.0), (0, 30, 1.0), (10, 11, 2.0), (11, 12, 2.0),
+                               (12, 13, 2.0), (13, 14, 2.0), (14, 15, 2.0), (15, 16, 2.0),
+                               (20, 21, 1.0), (21, 22, 1.0), (30, 31, 1.0), (31, 32, 1.0), (32, 33, 1.0)])
+    node_to_state = {0: 0, 16: 0, 22: 2, 33: 3}
+    event_nodes = {10, 20, 21, 30, 31, 32}
+    for root in set(T) - event_nodes:
+        T_aug = _sample_mcx.resample_edge_states(T, root, event_nodes, node_to_state=node_to_state,
+                                                 root_distn=uniform, P_default=P)
+        assert T.size() == T_aug.size()
+        assert_allclose(T.size(weight='weight'), T_aug.size(weight='weight'))
+        long_path = (10, 11, 12, 13, 14, 15, 16)
+        for a, b in zip(long_path[:-1], long_path[1:]):
+            assert T_aug[a][b]['state'] == 0
+        assert [T_aug[a][b]['state'] for a, b in ((0, 20), (20, 21), (21, 22))] == [0, 1, 2]
+        assert [T_aug[a][b]['state'] for a, b in ((0, 30), (30, 31), (31, 32), (32, 33))] == [0, 1, 2, 3]
