@@ -205,7 +205,9 @@ int rt_joint_distn(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
  * (nullable) += the sufficient statistics of every sampled history
  * (_mjp.get_history_statistics, raoteh/sampler/_mjp.py:150).
  * Trajectories whose status != 0 are skipped; status 3 = more than `cap`
- * candidate events in one sweep (trajectory left at its last completed sweep).
+ * candidate events in one sweep, or more than 255 on one branch (the per-branch
+ * counts are uint8; expected candidates per branch = omega * length) -- the
+ * trajectory is left at its last completed sweep.
  */
 int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, int64_t n_sites,
                      int64_t traj0, const int32_t* program, int n_ops, int n_slots,

@@ -182,6 +182,48 @@ class TreeSchedule(object):
                 np.asarray(level_ptr, dtype=np.int32))
 
 
+def subdivide_long_branches(sched, max_length):
+    """Split every branch longer than max_length into equal pieces joined by new degree-two
+    nodes (appended labels: None).  Returns (new TreeSchedule, pieces) where pieces[c] lists, for
+    the original child node c, the new-schedule nodes of its pieces from the parent end to the
+    child end (the last one is the image of c), and image[v] is the new index of old node v.
+    The per-branch event counts of the sampling kernels are uint8, so a branch must not expect
+    more than ~255 candidate events (omega * length); this keeps long branches usable."""
+    n = sched.n
+    if not (max_length > 0):
+        raise ValueError('max_length must be positive')
+    kpieces = np.ones(n, dtype=np.int64)
+    for c in range(1, n):
+        kpieces[c] = max(1, int(np.ceil(sched.length[c] / max_length)))
+    if int(kpieces.max()) == 1:
+        return sched, dict((c, [c]) for c in range(1, n)), np.arange(n)
+    # preorder of the subdivided tree: walk the old preorder, inserting the chain before each node
+    parent, length, nodes = [], [], []
+    image = np.zeros(n, dtype=np.int64)
+    pieces = {}
+    for v in range(n):
+        if v == 0:
+            parent.append(-1)
+            length.append(0.0)
+            nodes.append(sched.nodes[0])
+            image[0] = 0
+            continue
+        k = int(kpieces[v])
+        prev = int(image[sched.parent[v]])
+        chain = []
+        for i in range(k):
+            parent.append(prev)
+            length.append(sched.length[v] / k)
+            nodes.append(sched.nodes[v] if i == k - 1 else ('__piece__', sched.nodes[v], i))
+            prev = len(parent) - 1
+            chain.append(prev)
+        image[v] = prev
+        pieces[v] = chain
+    # the old preorder with chains inserted keeps parent < child only if children follow their
+    # parent's image, which holds because image[parent] was assigned before v was visited
+    return TreeSchedule(np.asarray(parent, dtype=np.int32), np.asarray(length), nodes), pieces, image
+
+
 # ---------------------------------------------------------------------------
 # rate matrices
 # ---------------------------------------------------------------------------

@@ -127,15 +127,22 @@ class RaoTehChains(object):
             self.initialize()
         self._call(int(n_sweeps), -1, stats)
         self.sweeps_done += int(n_sweeps)
+        self.check()
 
     def check(self):
         bad = int((self.status != 0).sum())
+        if bad and int((self.status == 1).sum()):
+            raise _native.NativeError('no feasible history (structural zero) for %d trajectories'
+                                      % int((self.status == 1).sum()))
         if bad and int((self.status == 4).sum()):
             raise _native.NativeError('initial history has more than cap=%d real jumps' % self.cap)
         if bad:
             raise _native.NativeError(
-                '%d trajectories exceeded the event capacity cap=%d in one sweep '
-                '(status 3); re-create the sampler with a larger cap' % (bad, self.cap))
+                '%d trajectories exceeded the event capacity in one sweep (status 3): more than '
+                'cap=%d candidate events in the trajectory, or more than 255 on one branch '
+                '(expected per branch: omega * length, here up to %.0f); re-create the sampler '
+                'with a larger cap, or subdivide long branches with degree-two nodes'
+                % (bad, self.cap, self.omega * float(self.sched.length.max())))
 
     def reset_statistics(self):
         self.dwell_sum.zero_()

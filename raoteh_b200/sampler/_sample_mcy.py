@@ -58,7 +58,7 @@ def _run(sched, states, index, B, node_to_allowed_states, root_distn, edge_times
                          seed=int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else seed,
                          chain_matrix=B)
     chain.load_events(edge_times)
-    chain.sweep(1, stats=False)
+    chain._call(1, -1, False)          # one FFBS pass over the loaded events; status handled here
     st = int(chain.status[0])
     if st == 1:
         raise StructuralZeroProb('no assignment of states is feasible')

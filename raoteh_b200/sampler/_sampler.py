@@ -21,10 +21,32 @@ import numpy as np
 from . import _mjp, _sparse
 from ._util import get_first_element
 from .. import engine
-from ..lowering import TreeSchedule
+from ..lowering import TreeSchedule, subdivide_long_branches
 from ..raoteh import RaoTehChains
 
 __all__ = []
+
+
+def _merged_trajectory(chain):
+    """Trajectory 0 of the chain on the ORIGINAL tree: pieces of subdivided branches joined."""
+    ns, edges = chain.trajectory(0)
+    sched0, pieces = chain.merge
+    ns0 = np.zeros(sched0.n, dtype=int)
+    ns0[0] = ns[0]
+    edges0 = {}
+    for c in range(1, sched0.n):
+        times, seg_states, offset = [], None, 0.0
+        for node in pieces[c]:
+            tt, ss = edges[node]
+            if seg_states is None:
+                seg_states = [int(ss[0])]
+            for tau, s_after in zip(tt, ss[1:]):
+                times.append(offset + float(tau))
+                seg_states.append(int(s_after))
+            offset += float(chain.sched.length[node])
+        ns0[c] = seg_states[-1]
+        edges0[c] = (np.asarray(times, dtype=float), np.asarray(seg_states, dtype=int))
+    return ns0, edges0
 
 
 def _trajectory_to_graph(sched, states, ns, edges, next_node):
@@ -64,7 +86,12 @@ def _make_chain(T, Q, node_to_allowed_states, root, root_distn, uniformization_f
     S = len(states)
     Qd = _sparse.dense_matrix(Q, states, index)
     Qd -= np.diag(Qd.sum(axis=1))
-    sched = TreeSchedule.from_nx(T, root)
+    sched0 = TreeSchedule.from_nx(T, root)
+    # long branches are cut into pieces (new unobserved degree-two nodes) so that no branch
+    # expects more than ~100 candidate events per sweep; the pieces are merged again when a
+    # history is converted to the reference's graph type
+    omega = uniformization_factor * np.max(-np.diag(Qd))
+    sched, pieces, image = subdivide_long_branches(sched0, 100.0 / omega if omega > 0 else np.inf)
     full = (1 << S) - 1
     mask = np.full((sched.n, 1), full, dtype=np.uint64)
     for v, allowed in node_to_allowed_states.items():
@@ -72,7 +99,7 @@ def _make_chain(T, Q, node_to_allowed_states, root, root_distn, uniformization_f
         for s in allowed:
             if s in index:
                 m |= 1 << index[s]
-        mask[sched.node_index[v], 0] = m
+        mask[image[sched0.node_index[v]], 0] = m
     prior = None
     if root_distn is not None:
         prior = np.array([root_distn.get(s, 0.0) for s in states], dtype=float)
@@ -80,7 +107,6 @@ def _make_chain(T, Q, node_to_allowed_states, root, root_distn, uniformization_f
     if seed is None:
         seed = int(np.random.randint(0, 2 ** 31 - 1))
     if cap is None:
-        omega = uniformization_factor * np.max(-np.diag(Qd))
         mean = omega * sched.length.sum()
         cap = int(max(256, (sched.n - 1) * (S + 1), 4 * mean + 64))
     chain = RaoTehChains(sched, Qd, obs, n_chains=1, root_distn=prior,
@@ -89,7 +115,8 @@ def _make_chain(T, Q, node_to_allowed_states, root, root_distn, uniformization_f
         chain.initialize()
     except RuntimeError:
         raise Exception('failed to find a feasible history')
-    return chain, sched, states
+    chain.merge = (sched0, pieces)
+    return chain, sched0, states
 
 
 def gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=None,
@@ -99,7 +126,7 @@ def gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=None
                                        uniformization_factor, seed, cap)
     next_node = max(T) + 1
     for i in itertools.count():
-        ns, edges = chain.trajectory(0)
+        ns, edges = _merged_trajectory(chain)
         yield _trajectory_to_graph(sched, states, ns, edges, next_node)
         if nhistories is not None and i + 1 >= nhistories:
             return
@@ -127,7 +154,7 @@ def gen_mh_histories(T, Q, node_to_allowed_states, target_log_likelihood_callbac
     saved = None
     ll_biased_prev = ll_target_prev = None
     for i in itertools.count():
-        ns, edges = chain.trajectory(0)
+        ns, edges = _merged_trajectory(chain)
         T_cur = _trajectory_to_graph(sched, states, ns, edges, next_node)
         if T_prev is None:
             accept_flag = True

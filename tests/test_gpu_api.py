@@ -448,3 +448,39 @@ def test_chain_state_samplers_deterministic_answers():
             assert T_aug[a][b]['state'] == 0
         assert [T_aug[a][b]['state'] for a, b in ((0, 20), (20, 21), (21, 22))] == [0, 1, 2]
         assert [T_aug[a][b]['state'] for a, b in ((0, 30), (30, 31), (31, 32), (32, 33))] == [0, 1, 2, 3]
+
+
+def test_gen_histories_long_branch_birth_death():
+    """raoteh/sampler/tests/test_sample_mjp.py:29-112 at the reference's own size: elapsed time
+    2.0 with rates up to ~120 (about 490 candidate events on the single branch per sweep, above
+    the 255 a branch holds on the device): the generator cuts the branch into pieces and joins
+    them again.  Every history has an even number of excess events and keeps the tree length."""
+    from raoteh_b200.sampler import _sampler
+    from raoteh_b200.lowering import TreeSchedule, subdivide_long_branches
+    T = nx.Graph()
+    T.add_edge(0, 1, weight=2.0)
+    Q = nx.DiGraph()
+    for state in range(1, 51):
+        if state - 1:
+            Q.add_edge(state, state - 1, weight=(state - 1) * 1.5)
+        if state < 50:
+            Q.add_edge(state, state + 1, weight=state * 1.0)
+    n = 0
+    for traj in _sampler.gen_histories(T, Q, {0: 3, 1: 7}, root=0, root_distn=None, nhistories=25, seed=4):
+        n += 1
+        ntransitions = len(traj) - 2
+        excess = ntransitions - (7 - 3)
+        assert excess >= 0 and excess % 2 == 0
+        assert_allclose(traj.size(weight='weight'), 2.0, rtol=1e-5)
+        path = nx.shortest_path(traj, 0, 1)
+        seq = [traj[a][b]['state'] for a, b in zip(path[:-1], path[1:])]
+        assert seq[0] == 3 and seq[-1] == 7
+        assert all(abs(x - y) == 1 for x, y in zip(seq[:-1], seq[1:]))
+    assert n == 25
+    # the subdivision itself
+    s0 = TreeSchedule(np.array([-1, 0, 0, 2], dtype=np.int32), np.array([0.0, 1.0, 0.2, 2.5]))
+    s1, pieces, image = subdivide_long_branches(s0, 1.0)
+    assert s1.n == 4 + 0 + 0 + 2 and [len(pieces[c]) for c in (1, 2, 3)] == [1, 1, 3]
+    assert_allclose(s1.length.sum(), s0.length.sum())
+    assert (s1.parent[1:] < np.arange(1, s1.n)).all()
+    assert_allclose(sum(s1.length[v] for v in pieces[3]), 2.5)

@@ -194,3 +194,54 @@ def test_mh_histories_with_exact_target_always_accepts_and_biased_target_rejects
     plain = [ntrans(h) for h in _sampler.gen_restricted_histories(T, Q, allowed, 0, root_distn=distn,
                                                                    nhistories=300, seed=3)]
     assert np.mean(counts[50:]) < np.mean(plain[50:])
+
+
+def test_birth_death_indel_bridge():
+    """raoteh/sampler/tests/test_sample_mjp.py:29-112 (a print-only, disabled test in the
+    reference): sequence-length birth-death process with 50 states on one branch, end states
+    3 and 7.  Every sampled history has an even number of excess events, and the mean number
+    of transitions matches the closed-form posterior expectation (|z| < 5)."""
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
+    S, t = 50, 0.5      # (the reference uses t = 2; here omega * t stays below the 255 events per branch)
+    Q = np.zeros((S, S))                      # state index i = sequence length i + 1
+    for i in range(S):
+        if i > 0:
+            Q[i, i - 1] = i * 1.5
+        if i < S - 1:
+            Q[i, i + 1] = (i + 1) * 1.0
+    Q -= np.diag(Q.sum(axis=1))
+    a, b = 3 - 1, 7 - 1
+    parent = np.array([-1, 0], dtype=np.int32)
+    length = np.array([0.0, t])
+    sched = TreeSchedule(parent, length)
+    mask = np.array([[1 << a], [1 << b]], dtype=np.uint64)
+    obs = engine.Observations.from_masks(sched, mask)
+    P = np_oracle.expm_edges(Q, length)
+    o = np_oracle.expected_history_statistics(parent, length, Q, P, np_oracle.Obs('mask', S, 1, mask=mask), None)
+    want = o['trans'].sum()
+    groups, n_chains, n_sweeps = 12, 512, 60
+    means = []
+    for g in range(groups):
+        ch = RaoTehChains(sched, Q, obs, n_chains=n_chains, seed=70 + g, cap=400)
+        ch.sweep(60, stats=False)
+        ch.sweep(n_sweeps)
+        means.append(float(ch.trans_sum.sum()) / (n_chains * n_sweeps))
+        tot = ch.ev_total.cpu().numpy()
+        assert np.all((tot - (b - a)) % 2 == 0) and np.all(tot >= b - a)
+    m, se = np.mean(means), np.std(means, ddof=1) / np.sqrt(groups)
+    assert abs(m - want) < 5 * se, (m, want, se)
+
+
+def test_event_capacity_overflow_is_loud():
+    """More candidate events than a branch can hold (255) must raise, not return stale histories."""
+    from raoteh_b200 import engine, _native
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
+    Q = np.array([[-200.0, 200.0], [200.0, -200.0]])
+    sched = TreeSchedule(np.array([-1, 0], dtype=np.int32), np.array([0.0, 2.0]))
+    obs = engine.Observations.from_masks(sched, np.array([[1], [1]], dtype=np.uint64))
+    ch = RaoTehChains(sched, Q, obs, n_chains=4, seed=1, cap=4000)
+    with pytest.raises(_native.NativeError):
+        ch.sweep(2)
