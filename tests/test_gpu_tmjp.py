@@ -640,3 +640,66 @@ def test_samplers_on_polytomies_chains_and_maximum_sizes():
     np.testing.assert_allclose(out[:, 0] + out[:, 1], 32.0, rtol=1e-12)
     np.testing.assert_allclose(out[:, 2] + out[:, 3], 32.0 * length.sum(), rtol=1e-12)
     assert np.isfinite(out).all()
+
+
+def test_codon_tolerance_gibbs_matches_cpu_port():
+    """61 codons x 20 amino-acid classes (two states per lane, 20 of 32 class lanes): the closed
+    form is out of reach (61 * 2^20 compound states), so the GPU sampler is compared with the CPU
+    restatement of the same sweep (oracle/np_tmjp.py, itself checked against the closed form on
+    the toy model).  Aggregate statistics, |z| < 5 with batch-means standard errors."""
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.tmjp import ToleranceChains
+    rng = np.random.default_rng(77)
+    parent, length, leaves = synth.random_binary_tree(5, 0.15, rng)
+    Q, pi, residues = synth.mg94(omega=1.0)
+    aas = sorted(set(residues))
+    part = np.array([aas.index(r) for r in residues])
+    rate_on, rate_off = 0.21925, 0.78075
+    Qp = synth.tolerance_proposal(Q, part, rate_on)
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Qp, pi, 1, rng, 0.0)
+    sched = TreeSchedule(parent, length)
+    node_to_state = dict((int(v), int(codes[i, 0])) for i, v in enumerate(leaves))
+    human = int(leaves[0])
+    dd = [dict() for _ in range(20)]
+    tol_obs = np.full((1, 20, 1), 2, dtype=np.uint8)
+    for c in (3, 7, 11):
+        if c != part[codes[0, 0]]:
+            dd[c][human] = {0}
+            tol_obs[0, c, 0] = 1
+    for c in range(20):
+        dd[c].setdefault(human, {1})
+
+    def summarise(dwell, trans, tol):
+        same = part[:, None] == part[None, :]
+        return np.array([trans[same].sum(), trans[~same].sum(), tol[:, 0].sum(), tol[:, 1].sum(),
+                         tol[:, 2].sum(), tol[:, 3].sum(), (dwell * (-np.diag(Q))).sum()])
+    # CPU port: one long chain, batch means
+    crng = np.random.default_rng(5)
+    margs = (parent, length, Q, part, 20, pi, rate_on, rate_off, node_to_state, dd)
+    prim, tols = np_tmjp.gibbs_init(*margs, crng)
+    burn, nb, per = 100, 20, 60
+    rows = []
+    for i in range(burn + nb * per):
+        prim, tols = np_tmjp.gibbs_sweep(*margs, prim, tols, crng)
+        if i >= burn:
+            rows.append(summarise(*np_tmjp.sampled_statistics(parent, length, prim, tols, 61, 20)))
+    rows = np.array(rows).reshape(nb, per, -1).mean(axis=1)
+    cpu_mean, cpu_se = rows.mean(axis=0), rows.std(axis=0, ddof=1) / np.sqrt(nb)
+    # GPU: independent groups of chains
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaves)
+    groups, n_chains, n_sweeps = 12, 256, 60
+    g = []
+    for k in range(groups):
+        ch = ToleranceChains(sched, Q, pi, dict(enumerate(int(p) for p in part)), rate_on, rate_off, obs,
+                             n_chains=n_chains, tol_obs=tol_obs, tol_obs_nodes=[human], cap_p=96,
+                             cap_t=48, seed=300 + k)
+        ch.sweep(80, stats=False)
+        ch.sweep(n_sweeps)
+        norm = n_chains * n_sweeps
+        g.append(summarise(ch.prim_dwell.cpu().numpy() / norm, ch.prim_trans.cpu().numpy() / norm,
+                           ch.tol_stats.cpu().numpy() / norm))
+    g = np.array(g)
+    gpu_mean, gpu_se = g.mean(axis=0), g.std(axis=0, ddof=1) / np.sqrt(groups)
+    for a, sa, b, sb in zip(gpu_mean, gpu_se, cpu_mean, cpu_se):
+        assert abs(a - b) < 5 * np.hypot(sa, sb) + 1e-9, (a, sa, b, sb)
