@@ -40,6 +40,7 @@ if ROOT not in sys.path:
 
 C2_SITES = 1_000_000
 E2E_CHUNKS = int(os.environ.get('RT_E2E_CHUNKS', '8'))
+E2E_PACKED = os.environ.get('RT_E2E_PACKED', '1') != '0'         # 4-bit leaf codes on the host side
 DEV_CHUNKS = int(os.environ.get('RT_DEV_CHUNKS', '0'))     # device-resident arm: two-stream chunk overlap   # site chunks of the pipelined host-buffer call
 C2_LEAVES = 32
 
@@ -252,12 +253,26 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
+    if world > 1:
+        # one rank per GPU on a multi-socket host: keep the rank (and the pinned buffers it is
+        # about to allocate) on the CPU cores local to its GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
     cfg = c2_workload(rank)
     S = cfg['S']
     sched = TreeSchedule(cfg['parent'], cfg['length'])
     n_edges = sched.n_edges
     N = cfg['codes'].shape[1]
     codes_pinned = torch.from_numpy(cfg['codes']).pin_memory()
+    codes4_pinned = torch.from_numpy(engine.pack_codes4(cfg['codes'])).pin_memory()   # RT_OBS_CODES4
     codes_dev = codes_pinned.to(dev)
     obs_slot = np.full(sched.n, -1, dtype=np.int32)
     obs_slot[cfg['leaves']] = np.arange(len(cfg['leaves']), dtype=np.int32)
@@ -287,13 +302,15 @@ def run_gpu(args):
         return r, stats
     sub = {}
 
-    def step_e2e():
+    def step_e2e(packed=E2E_PACKED):
         """Same step through the public host-buffer API: H2D of the leaf codes from pinned
-        memory, D2H of per-site log-lik / status and of the statistics, all inside."""
+        memory (two 4-bit codes per byte by default, one byte per code with packed=False),
+        D2H of per-site log-lik / status and of the statistics, all inside."""
         mjp.events = None
         mjp.set_rate_matrix(cfg['Q'])
-        r = mjp.expected_history_statistics_from_host(codes_pinned, cfg['leaves'], out_ll, out_st,
-                                                      n_chunks=E2E_CHUNKS)
+        r = mjp.expected_history_statistics_from_host(
+            codes4_pinned if packed else codes_pinned, cfg['leaves'], out_ll, out_st,
+            n_chunks=E2E_CHUNKS, packed=packed)
         stats = rdist.pack_stats(r['loglik_sum'], r['dwell'], r['trans'], r['root_post_sum'])
         rdist.allreduce_stats(stats)
         out_stats.copy_(stats, non_blocking=True)
@@ -332,6 +349,7 @@ def run_gpu(args):
     ms = timed(step, args.steps, args.warmup) if DEV_CHUNKS > 1 else ms_plain
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_u8 = timed(lambda: step_e2e(False), args.steps, args.warmup) if E2E_PACKED else ms_e2e
 
     total_sites = N * world
     value = total_sites * n_edges / (ms * 1e-3)
@@ -414,7 +432,10 @@ def run_gpu(args):
                         parallelism='site-sharded x%d, one allreduce of %d doubles' % (world, 1 + 2 * S + S * S),
                         l2='256 MiB flush buffer written between timed iterations'),
             e2e=dict(value=e2e_value, unit='messages/s', ms_per_step=ms_e2e,
-                     h2d_bytes_per_step=int(codes_pinned.numel()),
+                     input='leaf codes, %s' % ('4 bits each (RT_OBS_CODES4)' if E2E_PACKED else 'uint8'),
+                     h2d_bytes_per_step=int((codes4_pinned if E2E_PACKED else codes_pinned).numel()),
+                     uint8_codes=dict(ms_per_step=ms_e2e_u8, value=total_sites * n_edges / (ms_e2e_u8 * 1e-3),
+                                      h2d_bytes_per_step=int(codes_pinned.numel())),
                      d2h_bytes_per_step=int(out_ll.numel() * 8 + out_st.numel() + out_stats.numel() * 8)),
             gpu_launches=launches_per_step * args.steps,
             roofline=roofline, cpu_baseline=cpu_baseline, clocks=clocks, extra=extra)

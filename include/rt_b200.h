@@ -42,6 +42,9 @@ extern "C" {
 #define RT_OBS_CODES 0 /* uint8  [n_obs][site_stride]     hard state, 255 = unobserved */
 #define RT_OBS_MASK 1  /* uint64 [n_obs][site_stride]     bitmask of allowed states     */
 #define RT_OBS_DENSE 2 /* double [n_obs][S][site_stride]  emission likelihoods          */
+#define RT_OBS_CODES4 3 /* uint8 [n_obs][(site_stride+1)/2] two hard states per byte (site i in
+                           nibble i & 1 of byte i >> 1), 15 = unobserved; S <= 8, rt_prune_loglik and
+                           rt_posterior_stats only: halves the host-to-device bytes of nucleotide data */
 
 int rt_version(void);
 const char* rt_last_error_string(void);

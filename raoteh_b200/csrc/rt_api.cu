@@ -112,7 +112,8 @@ int rt_prune_loglik(int S, int n_nodes, int64_t n_sites, int64_t site_stride,
                     int32_t* exponents, double* loglik, int8_t* status, double* loglik_sum,
                     void* stream) {
   if (!program || !P || !loglik || !status) return arg_error("null pointer");
-  if (obs_kind < 0 || obs_kind > 2) return arg_error("obs_kind");
+  if (obs_kind < 0 || obs_kind > 3) return arg_error("obs_kind");
+  if (obs_kind == 3 && !(S >= 2 && S <= 8)) return unsupported("RT_OBS_CODES4 needs 2 <= S <= 8");
   if (site_stride < n_sites) return arg_error("site_stride < n_sites");
   if (n_sites <= 0) return RT_OK;
   if (n_ops <= 0 || n_slots <= 0 || n_nodes <= 1) return arg_error("empty program");
@@ -143,7 +144,8 @@ static int posterior_common(int S, int n_nodes, int64_t n_sites, int64_t site_st
     return arg_error("null pointer");
   if (!node_distn && !(S >= 2 && S <= 8 && program))
     return arg_error("node_distn may be NULL only for S <= 8 with the upward program given");
-  if (obs_kind < 0 || obs_kind > 2) return arg_error("obs_kind");
+  if (obs_kind < 0 || obs_kind > 3) return arg_error("obs_kind");
+  if (obs_kind == 3 && !(S >= 2 && S <= 8 && program)) return unsupported("RT_OBS_CODES4 needs 2 <= S <= 8");
   if (site_stride < n_sites) return arg_error("site_stride < n_sites");
   if ((K == nullptr) != (branch_out == nullptr)) return arg_error("K and branch_out go together");
   if (n_sites <= 0) return RT_OK;

@@ -296,7 +296,7 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
                  const double* __restrict__ partials, const int8_t* __restrict__ status,
                  double* __restrict__ node_distn, double* __restrict__ W,
                  double* __restrict__ root_post_sum, const double* __restrict__ Kmat,
-                 double* __restrict__ branch_out) {
+                 double* __restrict__ branch_out, int obs_packed) {
   constexpr int V = WalkV<S>::value;
   constexpr int NS = WalkNS<S>::value;
   constexpr int SP1 = S + 1;
@@ -318,7 +318,9 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
     const int code = op.x & 0xff;
     long long off = 0;
     if (code == OP_MSG_SLOT || code == OP_ROOT) off = (long long)op.w * S * stride;
-    else if (code == OP_MSG_OBS) off = (OBS == OBS_DENSE) ? (long long)op.z * S * stride : (long long)op.z * stride;
+    else if (code == OP_MSG_OBS)
+      off = (OBS == OBS_DENSE) ? (long long)op.z * S * stride
+                               : (long long)op.z * (obs_packed ? ((stride + 1) >> 1) : stride);
     off_s[i] = off;
   }
   if (tid < S) { pi_s[tid] = root_distn ? root_distn[tid] : 1.0; rp_s[tid] = 0.0; }
@@ -367,9 +369,21 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
           for (int s = 0; s < S; ++s)
             Lb[q][s] = live[q] ? __ldcs(&src[(int64_t)s * stride + q * kWalkBlock]) : 0.0;
       } else if (ncode == OP_MSG_OBS && OBS == OBS_CODES) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(obs) + off_s[j] + site0;
+        const uint8_t* row = reinterpret_cast<const uint8_t*>(obs) + off_s[j];
 #pragma unroll
-        for (int q = 0; q < NS; ++q) kb[q] = live[q] ? src[q * kWalkBlock] : 0;
+        for (int q = 0; q < NS; ++q) {
+          const int64_t sg = site0 + q * kWalkBlock;
+          int k = 0;
+          if (live[q]) {
+            if (obs_packed) {      // RT_OBS_CODES4: nibble sg & 1 of byte sg >> 1, 15 = unobserved
+              k = (row[sg >> 1] >> ((int)(sg & 1) * 4)) & 15;
+              if (k == 15) k = RT_MISSING;
+            } else {
+              k = row[sg];
+            }
+          }
+          kb[q] = k;
+        }
       }
     };
     auto do_op = [&](int ip, const double (&Lb)[NS][S], const int (&kb)[NS]) {
@@ -584,7 +598,7 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
                 int n_nodes, const double* P, const double* root_distn, const void* obs,
                 const double* partials, const int8_t* status, double* node_distn, double* W,
                 double* root_post_sum, const double* Kmat, double* branch_out,
-                cudaStream_t stream, bool* handled) {
+                cudaStream_t stream, bool* handled, int packed = 0) {
   constexpr int NS = WalkNS<S>::value;
   auto kern = down_walk_kernel<S, OBS, BR>;
   const size_t smem = (sizeof(int4) + sizeof(long long)) * n_ops +
@@ -604,7 +618,7 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, kWalkBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots,
                                                      n_nodes, P, root_distn, obs, partials, status,
-                                                     node_distn, W, root_post_sum, Kmat, branch_out);
+                                                     node_distn, W, root_post_sum, Kmat, branch_out, packed);
   RT_CUDA_CHECK(cudaGetLastError());
   *handled = true;
   return RT_OK;
@@ -621,20 +635,23 @@ int run(int obs_kind, int64_t n_sites, int64_t stride, const int32_t* program, i
     bool handled = false;
     const int4* prog = reinterpret_cast<const int4*>(program);
     int rc = RT_ERR_ARG;
-#define RT_WALK(OBSK)                                                                             \
+#define RT_WALK(OBSK, PACKED)                                                                     \
   rc = branch_out ? launch_walk<S, OBSK, true>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P,   \
                                                root_distn, obs, partials, status, node_distn, W,    \
-                                               root_post_sum, Kmat, branch_out, stream, &handled)   \
+                                               root_post_sum, Kmat, branch_out, stream, &handled,   \
+                                               PACKED)                                              \
                   : launch_walk<S, OBSK, false>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P,  \
                                                 root_distn, obs, partials, status, node_distn, W,   \
-                                                root_post_sum, nullptr, nullptr, stream, &handled)
-    if (obs_kind == OBS_CODES) RT_WALK(OBS_CODES);
-    else if (obs_kind == OBS_MASK) RT_WALK(OBS_MASK);
-    else if (obs_kind == OBS_DENSE) RT_WALK(OBS_DENSE);
+                                                root_post_sum, nullptr, nullptr, stream, &handled,  \
+                                                PACKED)
+    if (obs_kind == OBS_CODES) RT_WALK(OBS_CODES, 0);
+    else if (obs_kind == 3) RT_WALK(OBS_CODES, 1);
+    else if (obs_kind == OBS_MASK) RT_WALK(OBS_MASK, 0);
+    else if (obs_kind == OBS_DENSE) RT_WALK(OBS_DENSE, 0);
 #undef RT_WALK
     if (rc != RT_OK || handled) return rc;
   }
-  if (branch_out) return RT_ERR_UNSUPPORTED;   // per-branch output exists in the walk kernel only
+  if (branch_out || obs_kind == 3) return RT_ERR_UNSUPPORTED;   // walk-kernel-only features
   if (!node_distn) return RT_ERR_ARG;   // the level-synchronous kernel needs the marginals buffer
   int64_t gr = (n_sites + kBlock - 1) / kBlock;
   int grid_root = (int)(gr < 148 * 8 ? gr : 148 * 8);

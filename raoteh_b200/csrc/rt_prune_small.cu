@@ -27,8 +27,17 @@ template <int S, int OBS> struct ObsVal;
 template <int S> struct ObsVal<S, OBS_CODES> {
   int k;
   __device__ __forceinline__ void init() { k = RT_MISSING; }
-  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site) {
-    if (row >= 0) k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * stride + site];
+  // packed: two codes per byte (RT_OBS_CODES4), site i in nibble i & 1 of byte i >> 1, 15 = unobserved
+  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site,
+                                        int packed) {
+    if (row < 0) return;
+    if (packed) {
+      const int b = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * ((stride + 1) >> 1) + (site >> 1)];
+      k = (b >> ((int)(site & 1) * 4)) & 15;
+      if (k == 15) k = RT_MISSING;
+    } else {
+      k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * stride + site];
+    }
   }
   __device__ __forceinline__ double get(int b) const { return (k == RT_MISSING || k == b) ? 1.0 : 0.0; }
 };
@@ -36,7 +45,8 @@ template <int S> struct ObsVal<S, OBS_CODES> {
 template <int S> struct ObsVal<S, OBS_MASK> {
   unsigned long long mk;
   __device__ __forceinline__ void init() { mk = ~0ull; }
-  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site) {
+  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site,
+                                        int) {
     if (row >= 0) mk = reinterpret_cast<const unsigned long long*>(obs)[(int64_t)row * stride + site];
   }
   __device__ __forceinline__ double get(int b) const { return ((mk >> b) & 1ull) ? 1.0 : 0.0; }
@@ -48,7 +58,8 @@ template <int S> struct ObsVal<S, OBS_DENSE> {
 #pragma unroll
     for (int s = 0; s < S; ++s) d[s] = 1.0;
   }
-  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site) {
+  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site,
+                                        int) {
     if (row < 0) return;
     const double* p = reinterpret_cast<const double*>(obs) + (int64_t)row * S * stride + site;
 #pragma unroll
@@ -92,7 +103,7 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
                    const void* __restrict__ obs,
                    double* __restrict__ partials, int32_t* __restrict__ exponents,
                    double* __restrict__ loglik, int8_t* __restrict__ status,
-                   double* __restrict__ loglik_sum) {
+                   double* __restrict__ loglik_sum, int obs_packed) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // carve: decoded program | prefetch rows | pi | rowsum | P (optional) | stack | stack exponents
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
@@ -169,7 +180,7 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
       esum[q] = 0;
       nxt[q].init();
       cur[q].init();
-      if (!(OBS == OBS_DENSE && kRing > 0)) nxt[q].fetch(obs, pre_s[n_ops], stride, site[q]);
+      if (!(OBS == OBS_DENSE && kRing > 0)) nxt[q].fetch(obs, pre_s[n_ops], stride, site[q], obs_packed);
     }
     int jobs = 0;                    // index of the next obs-consuming op (dense ring)
     auto ring_issue = [&](int j) {   // start the copy of the j-th obs row into its ring slot
@@ -208,7 +219,7 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
 #pragma unroll
           for (int q = 0; q < NS; ++q) {
             cur[q] = nxt[q];
-            nxt[q].fetch(obs, row, stride, site[q]);
+            nxt[q].fetch(obs, row, stride, site[q], obs_packed);
           }
         }
       }
@@ -357,7 +368,7 @@ template <int S, int OBS, bool STORE>
 int launch_t(int64_t n_sites, int64_t stride, const int4* program, int n_ops, int n_slots,
              int n_nodes, const double* P, const double* root_distn, const void* obs,
              double* partials, int32_t* exponents, double* loglik, int8_t* status,
-             double* loglik_sum, cudaStream_t stream) {
+             double* loglik_sum, cudaStream_t stream, int packed = 0) {
   constexpr int NS = (S <= 4) ? 2 : 1;      // sites per thread
   size_t base = (size_t)n_ops * sizeof(int4) + sizeof(int) * (((size_t)n_ops + 4) & ~(size_t)3) +
                 sizeof(double) * (S + (size_t)n_nodes * S);
@@ -376,13 +387,13 @@ int launch_t(int64_t n_sites, int64_t stride, const int4* program, int n_ops, in
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
                                                   P, root_distn, obs, partials, exponents, loglik,
-                                                  status, loglik_sum);
+                                                  status, loglik_sum, packed);
   } else {
     auto kern = prune_small_kernel<S, OBS, STORE, false, NS>;
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, kBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots, n_nodes,
                                                   P, root_distn, obs, partials, exponents, loglik,
-                                                  status, loglik_sum);
+                                                  status, loglik_sum, packed);
   }
   RT_CUDA_CHECK(cudaGetLastError());
   return RT_OK;
@@ -399,6 +410,8 @@ int launch_s(int obs_kind, bool store, int64_t n_sites, int64_t stride, const in
     case OBS_CODES: return store ? launch_t<S, OBS_CODES, true>(RT_ARGS) : launch_t<S, OBS_CODES, false>(RT_ARGS);
     case OBS_MASK:  return store ? launch_t<S, OBS_MASK, true>(RT_ARGS)  : launch_t<S, OBS_MASK, false>(RT_ARGS);
     case OBS_DENSE: return store ? launch_t<S, OBS_DENSE, true>(RT_ARGS) : launch_t<S, OBS_DENSE, false>(RT_ARGS);
+    case 3:   // RT_OBS_CODES4: the codes kernels with the nibble decoder
+      return store ? launch_t<S, OBS_CODES, true>(RT_ARGS, 1) : launch_t<S, OBS_CODES, false>(RT_ARGS, 1);
   }
 #undef RT_ARGS
   return RT_ERR_ARG;

@@ -19,7 +19,7 @@ import torch
 from . import _native
 from .lowering import TreeSchedule, MISSING
 
-OBS_CODES, OBS_MASK, OBS_DENSE = 0, 1, 2
+OBS_CODES, OBS_MASK, OBS_DENSE, OBS_CODES4 = 0, 1, 2, 3
 
 
 def _ptr(t):
@@ -28,6 +28,19 @@ def _ptr(t):
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def pack_codes4(codes):
+    """uint8 codes [n_obs, n_sites] (255 = unobserved) -> RT_OBS_CODES4: two codes per byte, site i in
+    nibble i & 1 of byte i >> 1, 15 = unobserved.  For state spaces of at most 8 states (nucleotides):
+    halves the bytes that cross PCIe."""
+    c = np.ascontiguousarray(codes, dtype=np.uint8)
+    if ((c > 14) & (c != MISSING)).any():
+        raise ValueError('4-bit codes hold states 0..14')
+    c = np.where(c == MISSING, 15, c).astype(np.uint8)
+    if c.shape[1] % 2:
+        c = np.concatenate([c, np.full((c.shape[0], 1), 15, dtype=np.uint8)], axis=1)
+    return np.ascontiguousarray(c[:, 0::2] | (c[:, 1::2] << 4))
 
 
 def _round_up(x, m):
@@ -48,7 +61,8 @@ class Observations(object):
         self.data = data
         self.obs_slot = np.asarray(obs_slot, dtype=np.int32)
         self.n_sites = int(n_sites)
-        self.stride = int(data.shape[-1])
+        # site stride of the per-site arrays that go with these observations
+        self.stride = int(data.shape[-1]) * (2 if kind == OBS_CODES4 else 1)
 
     @classmethod
     def from_leaf_codes(cls, sched, codes, leaf_nodes=None, device='cuda', pinned=None):
@@ -62,6 +76,16 @@ class Observations(object):
         else:
             data = codes.to(device=device, dtype=torch.uint8).contiguous()
         return cls(OBS_CODES, data, obs_slot, data.shape[1])
+
+    @classmethod
+    def from_leaf_codes4(cls, sched, codes, leaf_nodes=None, device='cuda'):
+        """Hard leaf codes stored two per byte (RT_OBS_CODES4, S <= 8)."""
+        leaf_nodes = sched.leaves if leaf_nodes is None else np.asarray(leaf_nodes)
+        obs_slot = np.full(sched.n, -1, dtype=np.int32)
+        obs_slot[leaf_nodes] = np.arange(len(leaf_nodes), dtype=np.int32)
+        n_sites = codes.shape[1]
+        data = torch.from_numpy(pack_codes4(codes)).to(device)
+        return cls(OBS_CODES4, data, obs_slot, n_sites)
 
     @classmethod
     def from_masks(cls, sched, mask, device='cuda'):
@@ -231,7 +255,7 @@ class TreeMJP(object):
         W = self._buf('W', (n, S, S), torch.float64, zero=True)
         rps = self._buf('root_post_sum', (S,), torch.float64, zero=True)
         lp = prog['level_ptr']
-        esz = {OBS_CODES: 1, OBS_MASK: 8, OBS_DENSE: 8}[obs.kind]
+        esz = {OBS_CODES: 1, OBS_MASK: 8, OBS_DENSE: 8, OBS_CODES4: 0.5}[obs.kind]
         if getattr(self, '_ov_streams', None) is None:
             self._ov_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
             self._ov_graphs = {}
@@ -261,7 +285,7 @@ class TreeMJP(object):
         S, n = self.S, self.sched.n
         N, stride = obs.n_sites, obs.stride
         lp = prog['level_ptr']
-        esz = {OBS_CODES: 1, OBS_MASK: 8, OBS_DENSE: 8}[obs.kind]
+        esz = {OBS_CODES: 1, OBS_MASK: 8, OBS_DENSE: 8, OBS_CODES4: 0.5}[obs.kind]
         cur = torch.cuda.current_stream()
         chunk = _round_up((N + n_chunks - 1) // n_chunks, 256)
         W.zero_()
@@ -273,14 +297,14 @@ class TreeMJP(object):
             cs = self._ov_streams[k % 2]
             rc = lib.rt_prune_loglik(
                 S, n, hi - lo, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'], _ptr(P),
-                _ptr(self.root_distn), obs.kind, obs.data.data_ptr() + esz * lo,
+                _ptr(self.root_distn), obs.kind, obs.data.data_ptr() + int(esz * lo),
                 partials.data_ptr() + 8 * lo, None, loglik.data_ptr() + 8 * lo,
                 status.data_ptr() + lo, None, cs.cuda_stream)
             _native.check(rc, 'rt_prune_loglik')
             rc = lib.rt_posterior_stats(
                 S, n, hi - lo, stride, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
                 _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1, _ptr(P), _ptr(self.root_distn),
-                obs.kind, obs.data.data_ptr() + esz * lo, partials.data_ptr() + 8 * lo,
+                obs.kind, obs.data.data_ptr() + int(esz * lo), partials.data_ptr() + 8 * lo,
                 status.data_ptr() + lo, None, _ptr(W), _ptr(rps), cs.cuda_stream)
             _native.check(rc, 'rt_posterior_stats')
         for cs in self._ov_streams:
@@ -405,27 +429,31 @@ class TreeMJP(object):
 
     # ---- host-buffer entry point (pipelined) ----------------------------------------
     def expected_history_statistics_from_host(self, codes_pinned, leaf_nodes, out_loglik,
-                                              out_status, n_chunks=4):
+                                              out_status, n_chunks=4, packed=False):
         """The C2 evaluation from HOST buffers: uint8 leaf codes [n_leaves, n_sites] in
         pinned memory in, per-site log-likelihoods / status into pinned `out_*`, summed
         statistics returned.  The site axis is cut into `n_chunks` chunks; the H2D copy
         of chunk k+1 and the D2H copy of chunk k-1 run on their own streams under the
         kernels of chunk k (sites are independent, W only accumulates)."""
         lib = _native.lib()
-        L, N = codes_pinned.shape
+        L, NB = codes_pinned.shape
+        # packed=True: codes_pinned is RT_OBS_CODES4 (pack_codes4), N = len(out_loglik) sites
+        N = int(out_loglik.shape[0]) if packed else NB
+        kind = OBS_CODES4 if packed else OBS_CODES
+        bps = 2 if packed else 1                      # sites per byte of the code rows
         S, n = self.S, self.sched.n
         dev = self.device
         leaf_nodes = self.sched.leaves if leaf_nodes is None else np.asarray(leaf_nodes)
         obs_slot = np.full(n, -1, dtype=np.int32)
         obs_slot[leaf_nodes] = np.arange(len(leaf_nodes), dtype=np.int32)
-        codes_dev = self._buf('h_codes', (L, N), torch.uint8)
+        codes_dev = self._buf('h_codes%d' % bps, (L, NB), torch.uint8)
         loglik = self._buf('h_loglik', (N,), torch.float64)
         status = self._buf('h_status', (N,), torch.int8)
         partials = self._buf('partials', (self.sched.n_store, S, N), torch.float64)
         W = self._buf('W', (n, S, S), torch.float64, zero=True)
         rps = self._buf('root_post_sum', (S,), torch.float64, zero=True)
         llsum = self._buf('h_llsum', (1,), torch.float64, zero=True)
-        obs = Observations(OBS_CODES, codes_dev, obs_slot, N)
+        obs = Observations(kind, codes_dev, obs_slot, N)
         prog = self._programs(obs)
         lp = prog['level_ptr']
         P = self.transition_matrices()
@@ -445,8 +473,9 @@ class TreeMJP(object):
         bounds = [(lo, min(N, lo + chunk)) for lo in range(0, N, chunk)]
         ev_in = []
         for lo, hi in bounds:
-            rc = lib.rt_copy2d_async(codes_dev.data_ptr() + lo, N, codes_pinned.data_ptr() + lo, N,
-                                     hi - lo, L, 1, s_in.cuda_stream)
+            rc = lib.rt_copy2d_async(codes_dev.data_ptr() + lo // bps, NB,
+                                     codes_pinned.data_ptr() + lo // bps, NB,
+                                     (hi - lo + bps - 1) // bps, L, 1, s_in.cuda_stream)
             _native.check(rc, 'rt_copy2d_async')
             e = torch.cuda.Event()
             e.record(s_in)
@@ -456,14 +485,14 @@ class TreeMJP(object):
             cs.wait_event(e)
             rc = lib.rt_prune_loglik(
                 S, n, hi - lo, N, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'], _ptr(P),
-                _ptr(self.root_distn), OBS_CODES, codes_dev.data_ptr() + lo,
+                _ptr(self.root_distn), kind, codes_dev.data_ptr() + lo // bps,
                 partials.data_ptr() + 8 * lo, None, loglik.data_ptr() + 8 * lo,
                 status.data_ptr() + lo, _ptr(llsum), cs.cuda_stream)
             _native.check(rc, 'rt_prune_loglik')
             rc = lib.rt_posterior_stats(
                 S, n, hi - lo, N, _ptr(prog['ops']), prog['n_ops'], prog['n_slots'],
                 _ptr(prog['edges']), lp.ctypes.data, len(lp) - 1, _ptr(P), _ptr(self.root_distn),
-                OBS_CODES, codes_dev.data_ptr() + lo, partials.data_ptr() + 8 * lo,
+                kind, codes_dev.data_ptr() + lo // bps, partials.data_ptr() + 8 * lo,
                 status.data_ptr() + lo, None, _ptr(W), _ptr(rps), cs.cuda_stream)
             _native.check(rc, 'rt_posterior_stats')
             done = torch.cuda.Event()

@@ -411,3 +411,36 @@ def test_unusual_trees_and_extreme_state_counts(kind, S):
         np.testing.assert_allclose(r['dwell'].cpu().numpy(), o['dwell'], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(r['trans'].cpu().numpy(), o['trans'], rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(float(r['dwell'].sum()), length.sum() * n_sites, rtol=1e-10)
+
+
+@pytest.mark.parametrize('S,n_sites', [(4, 3001), (8, 515), (2, 64)])
+def test_packed_codes4_are_bit_identical_to_uint8_codes(S, n_sites):
+    """RT_OBS_CODES4 (two leaf codes per byte) is only another encoding of the same observations:
+    log-likelihoods, statuses and statistics must be bit-identical, also through the pipelined
+    host-buffer entry point (odd site counts, missing cells)."""
+    import torch
+    from raoteh_b200 import synth, engine
+    from raoteh_b200.lowering import TreeSchedule
+    rng = np.random.default_rng(S + n_sites)
+    parent, length, leaves = synth.random_binary_tree(12, 0.15, rng)
+    Q = rng.exponential(1.0, size=(S, S))
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    pi = rng.dirichlet(np.ones(S) * 3)
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.07)
+    sched = TreeSchedule(parent, length)
+    mjp = engine.TreeMJP(sched, Q, root_distn=pi)
+    a = mjp.expected_history_statistics(engine.Observations.from_leaf_codes(sched, codes, leaves))
+    a = dict((k, a[k].clone()) for k in ('loglik', 'status', 'dwell', 'trans', 'root_post_sum'))
+    b = mjp.expected_history_statistics(engine.Observations.from_leaf_codes4(sched, codes, leaves))
+    assert torch.equal(a['loglik'], b['loglik']) and torch.equal(a['status'], b['status'])
+    for k in ('dwell', 'trans', 'root_post_sum'):
+        np.testing.assert_allclose(b[k].cpu().numpy(), a[k].cpu().numpy(), rtol=1e-13)
+    packed = torch.from_numpy(engine.pack_codes4(codes)).pin_memory()
+    out_ll = torch.empty(n_sites, dtype=torch.float64).pin_memory()
+    out_st = torch.empty(n_sites, dtype=torch.int8).pin_memory()
+    r = mjp.expected_history_statistics_from_host(packed, leaves, out_ll, out_st, n_chunks=3, packed=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out_ll, a['loglik'].cpu()) and torch.equal(out_st, a['status'].cpu())
+    np.testing.assert_allclose(r['dwell'].cpu().numpy(), a['dwell'].cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(r['trans'].cpu().numpy(), a['trans'].cpu().numpy(), rtol=1e-12)
