@@ -198,9 +198,6 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
 #ifndef RT_WALK_DMMA_REDUCE
 #define RT_WALK_DMMA_REDUCE 0
 #endif
-#ifndef RT_WALK_PF
-#define RT_WALK_PF 0
-#endif
 #ifndef RT_WALK_BLOCK
 #define RT_WALK_BLOCK 128
 #endif
