@@ -120,14 +120,38 @@ class RaoTehChains(object):
         self.initialized = True
         return k
 
-    def sweep(self, n_sweeps=1, stats=True):
+    def sweep(self, n_sweeps=1, stats=True, auto_grow=False):
         """n_sweeps Rao-Teh sweeps of every trajectory; raises if any trajectory needed
         more than `cap` candidate events in one sweep."""
         if not self.initialized:
             self.initialize()
         self._call(int(n_sweeps), -1, stats)
         self.sweeps_done += int(n_sweeps)
+        if auto_grow:
+            # a trajectory that ran out of event capacity stopped at its last completed sweep
+            # (a valid history); double the pools and carry on -- it is a few sweeps behind
+            tries = 0
+            while bool((self.status == 3).any()) and self.omega * float(self.sched.length.max()) < 200 \
+                    and tries < 4:
+                self.grow(2 * self.cap)
+                self._call(1, -1, stats)
+                self.sweeps_done += 1
+                tries += 1
         self.check()
+
+    def grow(self, cap):
+        """Re-allocate the jump pools with a larger capacity (contents stay right-aligned) and
+        clear the capacity flags; flagged trajectories continue from their last completed sweep."""
+        cap = int(cap)
+        if cap <= self.cap:
+            return
+        T, dev = self.n_traj, self.device
+        for name, dt in (('ev_time', torch.float32), ('ev_sb', torch.uint8)):
+            new = torch.zeros((T, cap), dtype=dt, device=dev)
+            new[:, cap - self.cap:] = getattr(self, name)
+            setattr(self, name, new)
+        self.cap = cap
+        self.status[self.status == 3] = 0
 
     def check(self):
         bad = int((self.status != 0).sum())

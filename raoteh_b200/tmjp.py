@@ -239,6 +239,24 @@ class ToleranceChains(object):
             raise ValueError('the attached chains must have the same tree and trajectory count')
         self._primary_src = chains
 
+    def grow(self, cap_p=None, cap_t=None):
+        """Re-allocate the jump / toggle pools with larger capacities (contents stay
+        right-aligned) and clear the capacity flags."""
+        T, dev, NP = self.n_traj, self.device, self.n_parts
+        if cap_p is not None and int(cap_p) > self.cap_p:
+            cap_p = int(cap_p)
+            for name, dt in (('p_time', torch.float32), ('p_sb', torch.uint8)):
+                new = torch.zeros((T, cap_p), dtype=dt, device=dev)
+                new[:, cap_p - self.cap_p:] = getattr(self, name)
+                setattr(self, name, new)
+            self.cap_p = cap_p
+        if cap_t is not None and int(cap_t) > self.cap_t:
+            cap_t = min(255, int(cap_t))
+            new = torch.zeros((T, NP, cap_t), dtype=torch.float32, device=dev)
+            new[:, :, cap_t - self.cap_t:] = self.t_time
+            self.t_time, self.cap_t = new, cap_t
+        self.status[self.status == 3] = 0
+
     def check(self):
         st = self.status
         if int((st == 2).sum()):

@@ -245,3 +245,27 @@ def test_event_capacity_overflow_is_loud():
     ch = RaoTehChains(sched, Q, obs, n_chains=4, seed=1, cap=4000)
     with pytest.raises(_native.NativeError):
         ch.sweep(2)
+
+
+def test_capacity_growth_keeps_histories():
+    """grow(): larger pools, same histories; auto_grow continues after an overflow."""
+    import torch
+    from raoteh_b200.raoteh import RaoTehChains
+    parent, length, leaves, Q, pi, codes, sched, obs = _setup(4, 10, 4, 21)
+    a = RaoTehChains(sched, Q, obs, n_chains=8, root_distn=pi, seed=3, cap=96)
+    b = RaoTehChains(sched, Q, obs, n_chains=8, root_distn=pi, seed=3, cap=96)
+    a.sweep(5)
+    b.sweep(5)
+    b.grow(160)
+    a.sweep(4)
+    b.sweep(4)
+    assert torch.equal(a.node_state, b.node_state) and torch.equal(a.ev_total, b.ev_total)
+    for t in (0, 7, 31):
+        ea, eb = a.trajectory(t)[1], b.trajectory(t)[1]
+        for c in ea:
+            np.testing.assert_array_equal(ea[c][0], eb[c][0])
+            np.testing.assert_array_equal(ea[c][1], eb[c][1])
+    tiny = RaoTehChains(sched, Q, obs, n_chains=8, root_distn=pi, seed=3, cap=12)
+    tiny.initialize()
+    tiny.sweep(3, auto_grow=True)
+    assert tiny.cap > 12 and int((tiny.status != 0).sum()) == 0
