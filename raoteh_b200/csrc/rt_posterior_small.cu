@@ -285,7 +285,7 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // BR: also write, per site and branch, x = sum_ab G_a K_b[a,c] L_c -- the posterior expectation
 // of the statistic whose per-edge kernel is K (e.g. K_b = L(t_b Q, t_b (E o Q)): expected number
 // of E-type transitions on the branch, examples/code2x3/extras.py:19-132).
-template <int S, int OBS, bool BR>
+template <int S, int OBS, bool BR, bool PACKED>
 __global__ void __launch_bounds__(kWalkBlock)
 down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ program, int n_ops,
                  int n_slots, int n_nodes, const double* __restrict__ P,
@@ -293,7 +293,8 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
                  const double* __restrict__ partials, const int8_t* __restrict__ status,
                  double* __restrict__ node_distn, double* __restrict__ W,
                  double* __restrict__ root_post_sum, const double* __restrict__ Kmat,
-                 double* __restrict__ branch_out, int obs_packed) {
+                 double* __restrict__ branch_out) {
+  constexpr int obs_packed = PACKED ? 1 : 0;   // RT_OBS_CODES4 decoded at compile time
   constexpr int V = WalkV<S>::value;
   constexpr int NS = WalkNS<S>::value;
   constexpr int SP1 = S + 1;
@@ -590,14 +591,14 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
   if (root_post_sum && tid < S && rp_s[tid] != 0.0) atomicAdd(&root_post_sum[tid], rp_s[tid]);
 }
 
-template <int S, int OBS, bool BR>
+template <int S, int OBS, bool BR, bool PACKED = false>
 int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops, int n_slots,
                 int n_nodes, const double* P, const double* root_distn, const void* obs,
                 const double* partials, const int8_t* status, double* node_distn, double* W,
                 double* root_post_sum, const double* Kmat, double* branch_out,
-                cudaStream_t stream, bool* handled, int packed = 0) {
+                cudaStream_t stream, bool* handled) {
   constexpr int NS = WalkNS<S>::value;
-  auto kern = down_walk_kernel<S, OBS, BR>;
+  auto kern = down_walk_kernel<S, OBS, BR, PACKED>;
   const size_t smem = (sizeof(int4) + sizeof(long long)) * n_ops +
                       sizeof(double) * (2 * S + (size_t)n_nodes * ((BR ? 3 : 2) * S * S + S * (S + 1))) +
                       sizeof(double) * (size_t)n_slots * NS * S * kWalkBlock;
@@ -615,7 +616,7 @@ int launch_walk(int64_t n_sites, int64_t stride, const int4* program, int n_ops,
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, kWalkBlock, smem, stream>>>(n_sites, stride, program, n_ops, n_slots,
                                                      n_nodes, P, root_distn, obs, partials, status,
-                                                     node_distn, W, root_post_sum, Kmat, branch_out, packed);
+                                                     node_distn, W, root_post_sum, Kmat, branch_out);
   RT_CUDA_CHECK(cudaGetLastError());
   *handled = true;
   return RT_OK;
@@ -633,18 +634,18 @@ int run(int obs_kind, int64_t n_sites, int64_t stride, const int32_t* program, i
     const int4* prog = reinterpret_cast<const int4*>(program);
     int rc = RT_ERR_ARG;
 #define RT_WALK(OBSK, PACKED)                                                                     \
-  rc = branch_out ? launch_walk<S, OBSK, true>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P,   \
-                                               root_distn, obs, partials, status, node_distn, W,    \
-                                               root_post_sum, Kmat, branch_out, stream, &handled,   \
-                                               PACKED)                                              \
-                  : launch_walk<S, OBSK, false>(n_sites, stride, prog, n_ops, n_slots, n_nodes, P,  \
-                                                root_distn, obs, partials, status, node_distn, W,   \
-                                                root_post_sum, nullptr, nullptr, stream, &handled,  \
-                                                PACKED)
-    if (obs_kind == OBS_CODES) RT_WALK(OBS_CODES, 0);
-    else if (obs_kind == 3) RT_WALK(OBS_CODES, 1);
-    else if (obs_kind == OBS_MASK) RT_WALK(OBS_MASK, 0);
-    else if (obs_kind == OBS_DENSE) RT_WALK(OBS_DENSE, 0);
+  rc = branch_out ? launch_walk<S, OBSK, true, PACKED>(n_sites, stride, prog, n_ops, n_slots,       \
+                                                       n_nodes, P, root_distn, obs, partials,       \
+                                                       status, node_distn, W, root_post_sum, Kmat,  \
+                                                       branch_out, stream, &handled)                \
+                  : launch_walk<S, OBSK, false, PACKED>(n_sites, stride, prog, n_ops, n_slots,      \
+                                                        n_nodes, P, root_distn, obs, partials,      \
+                                                        status, node_distn, W, root_post_sum,       \
+                                                        nullptr, nullptr, stream, &handled)
+    if (obs_kind == OBS_CODES) RT_WALK(OBS_CODES, false);
+    else if (obs_kind == 3) RT_WALK(OBS_CODES, true);
+    else if (obs_kind == OBS_MASK) RT_WALK(OBS_MASK, false);
+    else if (obs_kind == OBS_DENSE) RT_WALK(OBS_DENSE, false);
 #undef RT_WALK
     if (rc != RT_OK || handled) return rc;
   }
