@@ -217,3 +217,34 @@ def get_restricted_feasible_history(T, P, node_to_allowed_states, root, root_dis
     gen = gen_restricted_histories(T, Q, node_to_allowed_states, root, root_distn=root_distn,
                                    nhistories=1)
     return next(gen)
+
+
+def get_forward_sample(T, Q, root, root_distn):
+    """raoteh/sampler/_sampler.py:163-235: unconditional forward simulation of one history
+    (host-side data generation, jump by jump with numpy's global RNG like the reference; it is
+    not on the accelerated path).  Returns the augmented tree with `state` and `weight`."""
+    total_rates = _mjp.get_total_rates(Q)
+    P = _mjp.get_conditional_transition_matrix(Q, total_rates)
+    next_node = max(T) + 1
+    states, probs = zip(*root_distn.items())
+    node_to_state = {root: states[int(np.random.choice(len(states), p=probs))]}
+    T_out = nx.Graph()
+    for a, b in nx.bfs_edges(T, root):
+        state = node_to_state[a]
+        weight = T[a][b]['weight']
+        prev_node, total_dwell = a, 0.0
+        while state in total_rates and total_rates[state] > 0:
+            dwell = np.random.exponential(scale=1.0 / total_rates[state])
+            if total_dwell + dwell > weight:
+                break
+            total_dwell += dwell
+            mid_node = next_node
+            next_node += 1
+            T_out.add_edge(prev_node, mid_node, state=state, weight=dwell)
+            prev_node = mid_node
+            nxt = list(P[state])
+            state = nxt[int(np.random.choice(len(nxt), p=[P[state][s]['weight'] for s in nxt]))]
+            node_to_state[prev_node] = state
+        node_to_state[b] = state
+        T_out.add_edge(prev_node, b, state=state, weight=weight - total_dwell)
+    return T_out

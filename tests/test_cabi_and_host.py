@@ -156,3 +156,33 @@ def test_compound_tolerance_model_matches_reference():
     np.testing.assert_allclose(
         _tmjp_dense.get_primary_proposal_rate_matrix(Q, part, b.tolerance_distn),
         ref.get_primary_proposal_rate_matrix(Q, part, a.tolerance_distn), rtol=1e-14)
+
+
+def test_forward_sample_invariants():
+    """_sampler.get_forward_sample (raoteh/sampler/_sampler.py:163-235): tree length preserved,
+    every jump follows an edge of Q, long-run dwell fractions approach the stationary distribution."""
+    import networkx as nx
+    import numpy as np
+    from raoteh_b200.sampler import _sampler, _mjp
+    np.random.seed(3)
+    Q = nx.DiGraph()
+    Q.add_weighted_edges_from([(0, 1, 1.0), (1, 0, 2.0), (1, 2, 1.0), (2, 1, 0.5)])
+    T = nx.Graph()
+    T.add_weighted_edges_from([(0, 1, 40.0), (1, 2, 30.0), (1, 3, 30.0)])
+    dwell = {0: 0.0, 1: 0.0, 2: 0.0}
+    for rep in range(20):
+        H = _sampler.get_forward_sample(T, Q, 0, {0: 0.5, 1: 0.25, 2: 0.25})
+        np.testing.assert_allclose(H.size(weight='weight'), 100.0)
+        assert set(T) <= set(H)
+        for a, b in nx.bfs_edges(H, 0):
+            dwell[H[a][b]['state']] += H[a][b]['weight']
+        for v in H:
+            if v not in T:
+                (x, y) = list(H[v])
+                sa, sb = H[v][x]['state'], H[v][y]['state']
+                assert sa != sb and (Q.has_edge(sa, sb) or Q.has_edge(sb, sa))
+        d, root_state, trans = _mjp.get_history_statistics(H, root=0)
+        assert abs(sum(d.values()) - 100.0) < 1e-9
+    tot = sum(dwell.values())
+    # stationary distribution of this chain: pi = (2, 1, 2) / 5
+    np.testing.assert_allclose([dwell[s] / tot for s in (0, 1, 2)], [0.4, 0.2, 0.4], atol=0.05)
