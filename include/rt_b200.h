@@ -329,6 +329,9 @@ typedef struct rt_tmjp_args {
   double* summary_sum;
   double* summary_out;
   double* traj_loglik;         /* [n_traj], mode RT_TMJP_TRAJ_LOGLIK */
+  const double* p_time64;      /* nullable [n_traj][cap_p]: fp64 jump times of caller-loaded primary
+                                  trajectories (same layout as p_time); modes SUMMARY / TRAJ_LOGLIK then
+                                  use them, and the fp64 branch lengths, instead of the float32 state */
 } rt_tmjp_args;
 
 int rt_tmjp_run(const rt_tmjp_args* args, void* stream);

@@ -69,7 +69,7 @@ class TmjpArgs(ctypes.Structure):
         ('n_sweeps', ctypes.c_int32), ('mode', ctypes.c_int32), ('init_k', ctypes.c_int32),
         ('flags', ctypes.c_int32),
         ('prim_dwell', c_void_p), ('prim_trans', c_void_p), ('tol_stats', c_void_p),
-        ('summary_sum', c_void_p), ('summary_out', c_void_p), ('traj_loglik', c_void_p),
+        ('summary_sum', c_void_p), ('summary_out', c_void_p), ('traj_loglik', c_void_p), ('p_time64', c_void_p),
     ]
 
 

@@ -740,7 +740,8 @@ __device__ __forceinline__ void seg_setup(double a, double w, double r, double l
 template <int SP>
 __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, int lane, int64_t site,
                             int p_total, double2* scr_seg, int n_seg_cap, double total_len,
-                            double (&out7)[8]) {
+                            double (&out7)[8], const double* pt64) {
+  const double* len64 = pt64 ? A.length : nullptr;   // fp64 branch lengths go with fp64 jump times
   const int NP = A.n_parts;
   const bool tl = lane < NP;
   const double a = A.rate_on;
@@ -777,9 +778,9 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
       if (tl) {
         int pstate = W.pn[c];
         int pk = pk0, pr = prd;
-        double pos = (double)C.len[c];
+        double pos = len64 ? len64[c] : (double)C.len[c];
         while (true) {
-          const double bound = pk > 0 ? (double)W.pt[pr] : 0.0;
+          const double bound = pk > 0 ? (pt64 ? pt64[pr] : (double)W.pt[pr]) : 0.0;
           const bool same = C.part[pstate] == lane;
           const double w = same ? 0.0 : A.rate_off;
           const double* ct = C.absorb + (size_t)(pstate * NP + lane) * 3;   // (lam1, sq, r)
@@ -878,8 +879,8 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
       for (int i = 0; i <= k; ++i) {
         int st;
         double tend;
-        if (i < k) { st = W.psb[pr - i]; tend = (double)W.pt[pr - i]; }
-        else { st = W.pn[c]; tend = (double)C.len[c]; }
+        if (i < k) { st = W.psb[pr - i]; tend = pt64 ? pt64[pr - i] : (double)W.pt[pr - i]; }
+        else { st = W.pn[c]; tend = len64 ? len64[c] : (double)C.len[c]; }
         --sg;
         const double2 l = l_next;
         if (sg > 0) l_next = scr_seg[(size_t)(sg - 1) * 32 + lane];   // next record meanwhile
@@ -943,7 +944,8 @@ __device__ int summary_pass(const rt_tmjp_args& A, const Cta& C, const Wp& W, in
 // the offset of an edge's jumps in the pool is a warp prefix sum over the program order.
 template <int SP>
 __device__ double trajectory_loglik(const rt_tmjp_args& A, const Cta& C, const Wp& W, int lane,
-                                    int p_total, bool stats) {
+                                    int p_total, bool stats, const double* pt64) {
+  const double* len64 = pt64 ? A.length : nullptr;
   constexpr int SPAD = SP * 32;
   double ll = 0.0;
   int base = A.cap_p - p_total;
@@ -965,9 +967,9 @@ __device__ double trajectory_loglik(const rt_tmjp_args& A, const Cta& C, const W
     if (c >= 0) {
       // jumps of the edge, child end first: (time from the parent end, parent-side state)
       int below = W.pn[c];
-      double pos = (double)C.len[c];
+      double pos = len64 ? len64[c] : (double)C.len[c];
       for (int i = 0; i < k; ++i) {
-        const double tau = (double)W.pt[start + i];
+        const double tau = pt64 ? pt64[start + i] : (double)W.pt[start + i];
         const int above = W.psb[start + i];
         ll -= (pos - tau) * (A.omega_p - A.rate_p[below]);
         ll += log(C.Bt[below * SPAD + above] * A.omega_p);
@@ -1138,6 +1140,9 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
     if (NP > 0)
       for (int i = lane; i < A.n_nodes * NP; i += 32) W.tc[i] = A.t_cnt[(size_t)traj * A.n_nodes * NP + i];
     int p_total = A.p_total[traj];
+    // optional fp64 copy of the jump times (caller-loaded trajectories): used by the summary and
+    // log-likelihood modes instead of the float32 sampler state
+    const double* pt64 = (A.p_time64 && A.mode >= RT_TMJP_SUMMARY) ? A.p_time64 + (size_t)traj * A.cap_p : nullptr;
     __syncwarp();
     int st = 0;
     bool primary_dirty = false, tol_dirty = false;
@@ -1166,7 +1171,7 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
           if (st == 0 || st == 4) tol_dirty = true;
           if (st) break;
           if (A.flags & RT_TMJP_F_SUMMARY) {
-            st = summary_pass<SP>(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7);
+            st = summary_pass<SP>(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7, pt64);
             if (st) break;
             have7 = true;
             if (lane < 7) atomicAdd(&C.sum_acc[lane], out7[lane]);
@@ -1175,10 +1180,10 @@ tmjp_kernel(rt_tmjp_args A, Scratch X) {
         }
       }
     } else if (A.mode == RT_TMJP_TRAJ_LOGLIK) {
-      const double ll = trajectory_loglik<SP>(A, C, W, lane, p_total, stats_p);
+      const double ll = trajectory_loglik<SP>(A, C, W, lane, p_total, stats_p, pt64);
       if (lane == 0 && A.traj_loglik) A.traj_loglik[traj] = ll;
     } else {   // RT_TMJP_SUMMARY
-      st = summary_pass<SP>(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7);
+      st = summary_pass<SP>(A, C, W, lane, site, p_total, scr_seg, X.n_seg, total_len, out7, pt64);
       if (st == 0) {
         have7 = true;
         if (lane < 7) atomicAdd(&C.sum_acc[lane], out7[lane]);

@@ -118,6 +118,7 @@ class ToleranceChains(object):
         self.sweeps_done = 0
         self.initialized = False
         self._primary_src = None
+        self.p_time64 = None      # fp64 jump times of caller-loaded trajectories (load_primary_trajectories)
 
     # -- the C-ABI call ------------------------------------------------------------
     def _args(self, mode, n_sweeps=1, init_k=0, flags=0):
@@ -153,6 +154,7 @@ class ToleranceChains(object):
         A.tol_stats, A.summary_sum = _ptr(self.tol_stats), _ptr(self.summary_sum)
         A.summary_out = _ptr(self.summary_out)
         A.traj_loglik = _ptr(self.traj_loglik)
+        A.p_time64 = _ptr(self.p_time64) if self._primary_src is None else None
         return A
 
     def _run(self, mode, **kw):
@@ -194,6 +196,7 @@ class ToleranceChains(object):
         """n_sweeps blocked Gibbs sweeps of every trajectory."""
         if not self.initialized:
             self.initialize()
+        self.p_time64 = None          # the sampler state is float32 from here on
         flags = (F_STATS_PRIMARY | F_STATS_TOLERANCE if stats else 0)
         if summary:
             # the summary runs as its own launch after every sweep: with all warps of an SM in
@@ -324,7 +327,7 @@ class ToleranceChains(object):
         T, n = self.n_traj, self.sched.n
         order = self._edge_order()
         p_cnt = np.zeros((T, n), dtype=np.uint8)
-        p_time = np.zeros((T, self.cap_p), dtype=np.float32)
+        p_time = np.zeros((T, self.cap_p), dtype=np.float64)
         p_sb = np.zeros((T, self.cap_p), dtype=np.uint8)
         p_total = np.zeros(T, dtype=np.int32)
         for t in range(T):
@@ -344,7 +347,8 @@ class ToleranceChains(object):
         dev = self.device
         self.p_node.copy_(torch.from_numpy(np.asarray(node_states, dtype=np.uint8)).to(dev))
         self.p_cnt.copy_(torch.from_numpy(p_cnt).to(dev))
-        self.p_time.copy_(torch.from_numpy(p_time).to(dev))
+        self.p_time.copy_(torch.from_numpy(p_time.astype(np.float32)).to(dev))
+        self.p_time64 = torch.from_numpy(p_time).to(dev)      # the summary uses the exact times
         self.p_sb.copy_(torch.from_numpy(p_sb).to(dev))
         self.p_total.copy_(torch.from_numpy(p_total).to(dev))
         self.status.zero_()

@@ -104,16 +104,16 @@ def test_tolerance_summary_kernel_matches_reference_fixture():
         ch.load_primary_trajectories(np.array([t[0] for t in trajs]), [t[1] for t in trajs])
         out = ch.tolerance_summary().cpu().numpy()
         want = np.array([c['out'] for c in cases])
-        # event times are stored in float32 on the device: 1e-6 relative on the inputs
-        np.testing.assert_allclose(out, want, rtol=2e-6, atol=1e-7)
+        # caller-loaded trajectories keep their fp64 times for the summary: relative 1e-9
+        np.testing.assert_allclose(out, want, rtol=1e-9, atol=1e-12)
         if cases[0]['disease'] is None:
             # compound log-likelihood with the tolerance histories integrated out
             # (_tmjp.get_tolerance_process_log_likelihood) and the plain trajectory log-likelihood
             # (_mjp.get_trajectory_log_likelihood), both from the reference
             got = ch.tolerance_log_likelihood().cpu().numpy()
-            np.testing.assert_allclose(got, [c['tol_ll'] for c in cases], rtol=2e-6)
+            np.testing.assert_allclose(got, [c['tol_ll'] for c in cases], rtol=1e-9)
             got = ch.trajectory_log_likelihood().cpu().numpy()
-            np.testing.assert_allclose(got, [c['traj_ll'] for c in cases], rtol=2e-6)
+            np.testing.assert_allclose(got, [c['traj_ll'] for c in cases], rtol=1e-9)
 
 
 def test_tolerance_summary_kernel_matches_generic_path_fp64_times():
