@@ -24,7 +24,8 @@ from .tmjp import ToleranceChains
 
 class ToleranceMetropolisChains(object):
     def __init__(self, sched, Q_primary, primary_distn, primary_to_part, rate_on, rate_off, obs,
-                 n_chains=1, uniformization_factor=2.0, cap=96, seed=0, device='cuda'):
+                 n_chains=1, uniformization_factor=2.0, cap=96, seed=0, device='cuda',
+                 tol_obs=None, tol_obs_nodes=None):
         from .sampler._tmjp_dense import get_primary_proposal_rate_matrix, get_two_state_tolerance_distn
         self.S = S = int(np.asarray(Q_primary).shape[0])
         part = dict((s, int(primary_to_part[s])) for s in range(S))
@@ -34,7 +35,8 @@ class ToleranceMetropolisChains(object):
                                      root_distn=primary_distn, cap=cap, seed=seed,
                                      uniformization_factor=uniformization_factor, device=device)
         self.target = ToleranceChains(sched, Q_primary, primary_distn, part, rate_on, rate_off, obs,
-                                      n_chains=n_chains, cap_p=cap, cap_t=8, seed=seed, device=device)
+                                      n_chains=n_chains, cap_p=cap, cap_t=8, seed=seed, device=device,
+                                      tol_obs=tol_obs, tol_obs_nodes=tol_obs_nodes)
         self.target.attach_primary(self.proposal)
         self.gen = torch.Generator(device=self.proposal.device)
         self.gen.manual_seed(int(seed) + 12345)
@@ -42,6 +44,10 @@ class ToleranceMetropolisChains(object):
         self.ll_biased = self.ll_target = None
         self.n_accepted = 0
         self.n_proposed = 0
+        # Rao-Blackwellised tolerance summary (get_tolerance_summary, 7 values) of the CURRENT
+        # history of every chain, and its sum over chains and steps
+        self.cur_summary = None
+        self.summary_acc = torch.zeros(7, dtype=torch.float64, device=self.proposal.device)
 
     @property
     def dwell_sum(self):
@@ -55,6 +61,7 @@ class ToleranceMetropolisChains(object):
         self.proposal.initialize()
         self.ll_biased = self.proposal.trajectory_log_likelihood().clone()
         self.ll_target = self.target.tolerance_log_likelihood().clone()
+        self.cur_summary = self.target.summary_out[:, :7].clone()
 
     def step(self, n_steps=1, stats=True):
         """n_steps proposals per trajectory; with stats=True the statistics of the CURRENT
@@ -72,7 +79,9 @@ class ToleranceMetropolisChains(object):
             self.proposal.restore(saved, reject=~accept)
             self.ll_biased = torch.where(accept, ll_b, self.ll_biased)
             self.ll_target = torch.where(accept, ll_t, self.ll_target)
+            self.cur_summary = torch.where(accept[:, None], self.target.summary_out[:, :7], self.cur_summary)
             self.n_accepted += int(accept.sum())
             self.n_proposed += self.n_traj
             if stats:
                 self.proposal.trajectory_log_likelihood(stats=True)
+                self.summary_acc += self.cur_summary.sum(dim=0)

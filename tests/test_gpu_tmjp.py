@@ -703,3 +703,54 @@ def test_codon_tolerance_gibbs_matches_cpu_port():
     gpu_mean, gpu_se = g.mean(axis=0), g.std(axis=0, ddof=1) / np.sqrt(groups)
     for a, sa, b, sb in zip(gpu_mean, gpu_se, cpu_mean, cpu_se):
         assert abs(a - b) < 5 * np.hypot(sa, sb) + 1e-9, (a, sa, b, sb)
+
+
+@pytest.mark.parametrize('level', ['L1', 'L2'])
+def test_code2x3_blinking_model_golden_values_by_sampling(level):
+    """The published numbers of the blinking model of examples/code2x3
+    (full-description.tex:305-370; inputs run.py:520-614): expected synonymous / non-synonymous
+    primary transitions and tolerance gains / losses summed over the five branches, with
+    alignment data only (L1) and with disease data at the root as well (L2).  Reproduced here by
+    SAMPLING: Rao-Teh proposals under the approximate primary process, Metropolis-Hastings
+    correction with the tolerance histories integrated out, Rao-Blackwellised tolerance summary
+    of every current history -- all on the device.  |z| < 5."""
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.mh import ToleranceMetropolisChains
+    Q, pi, part = toy_model()            # the 6-state code of run.py:524-540, classes {0,1},{2,3},{4,5}
+    parent = np.array([-1, 0, 1, 2, 2, 1], dtype=np.int32)       # run.py:557-559
+    sched = TreeSchedule(parent, np.array([0.0, 0.5, 0.5, 0.5, 0.5, 0.5]))
+    obs_nodes = np.array([0, 3, 4, 5])                            # run.py:578-585
+    codes = np.array([[0], [4], [5], [1]], dtype=np.uint8)
+    obs = engine.Observations.from_leaf_codes(sched, codes, leaf_nodes=obs_nodes)
+    golden = dict(     # per-branch values of the tex file, summed over the branches
+        L1=dict(syn=4 * 0.530243839876 + 0.214285714286, nonsyn=4 * 0.214361006829 + 1.63974144573,
+                gain=0.679310052688 + 0.540928083993 + 3 * 0.316402335024,
+                loss=0.316402335024 + 0.540928083993 + 3 * 0.679310052688),
+        L2=dict(syn=4 * 0.530243839876 + 0.214285714286,
+                nonsyn=0.115905720866 + 1.71225589525 + 2 * 0.22303974637 + 0.128868804275,
+                gain=0.880141827661 + 0.563730372337 + 2 * 0.307552791569 + 0.315487814895,
+                loss=0.30799029452 + 0.524525848196 + 2 * 0.685431320483 + 0.681655127317))[level]
+    tol_obs = tol_nodes = None
+    if level == 'L2':                                             # run.py:603-611: root (0,0):{1}, (0,1):{0}, (0,2):{1}
+        tol_nodes = [0]
+        tol_obs = np.array([[[2], [1], [2]]], dtype=np.uint8)
+    same = part[:, None] == part[None, :]
+    groups, n_chains, burn, n_steps = 12, 2048, 40, 50
+    rows = []
+    for g in range(groups):
+        mh = ToleranceMetropolisChains(sched, Q, pi, dict(enumerate(int(p) for p in part)), 1.0, 1.0, obs,
+                                       n_chains=n_chains, seed=1200 + g, cap=64, tol_obs=tol_obs,
+                                       tol_obs_nodes=tol_nodes)
+        mh.step(burn, stats=False)
+        mh.step(n_steps)
+        norm = n_chains * n_steps
+        tr = mh.trans_sum.cpu().numpy() / norm
+        sm = mh.summary_acc.cpu().numpy() / norm
+        rows.append([tr[same].sum(), tr[~same].sum(), sm[5], sm[6]])
+    rows = np.array(rows)
+    m, se = rows.mean(axis=0), rows.std(axis=0, ddof=1) / np.sqrt(groups)
+    want = np.array([golden['syn'], golden['nonsyn'], golden['gain'], golden['loss']])
+    for a, s, w in zip(m, se, want):
+        assert abs(a - w) < 5 * s, (level, m, se, want)
+    assert (se < 0.02 * want).all()
