@@ -402,6 +402,11 @@ def run_gpu(args):
             extra['codon_raoteh_sweeps'] = raoteh_bench.bench_codon_raoteh(dev, args)
         except Exception as e:
             extra['codon_raoteh_sweeps'] = dict(error=repr(e))
+        try:
+            import bench_legs as raoteh_bench
+            extra['next_rows'] = raoteh_bench.bench_next_rows(dev, args)
+        except Exception as e:
+            extra['next_rows'] = dict(error=repr(e))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:

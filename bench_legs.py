@@ -186,3 +186,54 @@ def bench_codon_raoteh(dev, args, n_sites=20_000, n_chains=4, sweeps_per_launch=
                 sweeps_per_sec=ch.n_traj * sweeps_per_launch / (ms * 1e-3),
                 mean_real_jumps_per_trajectory=float(ch.ev_total.double().mean()),
                 expected_candidate_events_per_sweep=float(omega * cfg['length'].sum()))
+
+
+def bench_next_rows(dev, args):
+    """Measurements for the rows SURVEY.md 8(f) marks 'next': per-site per-branch expectations
+    (f2) at C2 and C3 size, and the device-side Metropolis-Hastings pipeline (f1) at C5 size."""
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.mh import ToleranceMetropolisChains
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    out = {}
+    for name, cfg in (('c2', synth.config_c2(n_sites=1_000_000)), ('c3', synth.config_c3(n_sites=100_000))):
+        sched = TreeSchedule(cfg['parent'], cfg['length'])
+        mjp = engine.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'], device=dev)
+        obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'], device=dev)
+        K = mjp.transition_kernels(None)
+        for _ in range(2):
+            r = mjp.branch_expectations(obs, K=K)
+        ts = []
+        for _ in range(3):
+            a, b = ev(), ev()
+            a.record()
+            r = mjp.branch_expectations(obs, K=K)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.mean(ts))
+        out['branch_expectations_' + name] = dict(
+            workload='%s: up pass + down pass with one expected count per site and branch '
+                     '([n_nodes, n_sites] fp64 out)' % name.upper(),
+            ms=ms, messages_per_sec=obs.n_sites * sched.n_edges / (ms * 1e-3),
+            out_bytes=int(r['branch'].numel() * 8))
+        del mjp, obs, r
+    cfg = synth.config_c5(n_sites=20_000)
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'], device=dev)
+    mh = ToleranceMetropolisChains(sched, cfg['Q'], cfg['pi'], dict(enumerate(int(p) for p in cfg['part'])),
+                                   cfg['rate_on'], cfg['rate_off'], obs, n_chains=1, cap=192,
+                                   seed=20260205, device=dev)
+    mh.step(3, stats=False)
+    torch.cuda.synchronize()
+    a, b = ev(), ev()
+    a.record()
+    mh.step(5)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / 5
+    out['mh_c5'] = dict(workload='C5: Rao-Teh proposal under the approximate primary process + both '
+                                 'log-likelihoods + tolerance summary + accept/reject, 2e4 trajectories',
+                        ms_per_step=ms, steps_per_sec=mh.n_traj / (ms * 1e-3),
+                        acceptance=mh.n_accepted / max(1, mh.n_proposed))
+    return out
