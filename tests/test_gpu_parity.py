@@ -207,16 +207,20 @@ def test_loglik_mask_and_dense_match_oracle(rt, S, n_leaves, n_sites):
     np.testing.assert_allclose(r['loglik'].cpu().numpy(), ll, rtol=RTOL)
 
 
-@pytest.mark.parametrize('S,n_leaves,n_sites', [(4, 32, 5000), (3, 6, 100)])
+@pytest.mark.parametrize('S,n_leaves,n_sites', [(4, 32, 5000), (3, 6, 100), (20, 9, 300), (61, 12, 333)])
 def test_expectations_match_oracle(rt, S, n_leaves, n_sites):
     from raoteh_b200.lowering import TreeSchedule
     from raoteh_b200 import synth
     rng = np.random.default_rng(5 + S)
     parent, length, leaves = synth.random_binary_tree(n_leaves, 0.1, rng)
-    Q = rng.exponential(1.0, size=(S, S))
-    np.fill_diagonal(Q, 0)
-    Q -= np.diag(Q.sum(axis=1))
-    pi = rng.dirichlet(np.ones(S))
+    if S == 61:
+        Q, pi, _ = synth.mg94()            # sparse codon matrix: structural zeros in P for short branches
+    else:
+        Q = rng.exponential(1.0, size=(S, S))
+        np.fill_diagonal(Q, 0)
+        Q -= np.diag(Q.sum(axis=1))
+        Q /= np.abs(np.diag(Q)).mean()
+        pi = rng.dirichlet(np.ones(S))
     codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.02)
     sched = TreeSchedule(parent, length)
     mjp = rt.TreeMJP(sched, Q, root_distn=pi)
