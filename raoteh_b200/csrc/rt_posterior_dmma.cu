@@ -59,10 +59,27 @@ root_distn_generic_kernel(int S, int64_t n_sites, int64_t stride,
       if (rsum[s] != 0.0) atomicAdd(&root_post_sum[s], rsum[s]);
 }
 
+// 1/x to ~1 ulp: hardware seed (rcp.approx.ftz.f64) plus two Newton steps; no slow-path
+// branch, so the scheduler can keep loads and DMMAs in flight around it.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = r * fma(-x, r, 2.0);
+  r = r * fma(-x, r, 2.0);
+  return r;
+}
+
 // BR: a fourth contraction kl = K_b L_b and, per site, x = sum_a G_a kl_a: the posterior
 // expectation on this branch of the statistic with per-edge kernel K (e.g. expected number of
 // synonymous / non-synonymous substitutions, examples/code2x3/extras.py:19-132,
 // examples/p53/liwen-branch-expectation.py:176-356).  K is read through L1 (no shared memory left).
+//
+// Latency hiding (ncu, profiles/r1_ncu_full_summary.json: the first version spent 34 % of its
+// warp samples on the scoreboard of the D_a and L_b loads): the D_a values of a tile are loaded
+// into registers BEFORE the m contraction and the L_b rows (or code bytes) of the NEXT tile
+// before the W contraction, so both global latencies run under 256 DMMAs per warp.
+// Leaf edges with hard codes skip the m contraction: P L is a column gather from the staged
+// P_b (the row sum for an unobserved site).
 template <int MT, int OBS, bool BR>
 __global__ void __launch_bounds__(kThreads, 1)
 down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict__ edges,
@@ -73,10 +90,12 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
   constexpr int SP = 8 * MT;
   constexpr int LDP = SP + 4;
   constexpr int KS = SP / 4;
+  constexpr int NL = SP / 2;          // L rows per lane in the staging layout
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ps = reinterpret_cast<double*>(smem_raw);          // [SP][LDP]
   double* Lall = Ps + SP * LDP;                              // [kWarps][SP][kLd]
   double* Gall = Lall + (size_t)kWarps * SP * kLd;           // [kWarps][SP][kLd]
+  double* rs_s = Gall + (size_t)kWarps * SP * kLd;           // [SP] row sums of P_b
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -91,72 +110,125 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
   const double* Dp = node_distn + (int64_t)e.y * S * stride;
   const double* Lc = e.z >= 0 ? partials + (int64_t)e.z * S * stride : nullptr;
   double* Dc = e.z >= 0 ? node_distn + (int64_t)e.z * S * stride : nullptr;
+  // 0: stored partial of an internal child, 1: no observation (ones), 2: leaf observation
+  const int kind = Lc ? 0 : (e.w < 0 ? 1 : 2);
+  const bool gather = (OBS == OBS_CODES) && kind == 2;
 
   // W rows [8*warp, 8*warp+8) x all columns, accumulated over the whole chunk
   double Wacc[MT][2];
 #pragma unroll
   for (int j = 0; j < MT; ++j) Wacc[j][0] = Wacc[j][1] = 0.0;
   __syncthreads();
+  if (tid < SP) {
+    double sum = 0.0;
+    for (int c = 0; c < S; ++c) sum += Ps[tid * LDP + c];
+    rs_s[tid] = sum;
+  }
+
+  // ---- staging layout of L_b^T: lane owns site column lane & 15, rows r0 + (lane >> 4) ------
+  const int sc = lane & 15, rh = lane >> 4;
+  double lpre[NL];
+  int kpre = -1;
+  unsigned long long mpre = 0ull;
+  bool live_pre = false;
+  auto prefetch = [&](int tile) {
+    const int64_t tile0 = ((int64_t)blockIdx.x * kTilesPerCta + tile) * kTileSites;
+    const int64_t sg = tile0 + warp * kWarpSites + sc;
+    live_pre = tile < kTilesPerCta && sg < n_sites && status[sg] == RT_SITE_OK;
+    if (!live_pre) return;
+    if (kind == 0) {
+      const double* src = Lc + (int64_t)rh * stride + sg;
+#pragma unroll
+      for (int i = 0; i < NL; ++i) lpre[i] = (2 * i + rh < S) ? __ldcs(src + (int64_t)(2 * i) * stride) : 0.0;
+    } else if (kind == 2) {
+      if (OBS == OBS_CODES) {
+        kpre = reinterpret_cast<const uint8_t*>(obs)[(int64_t)e.w * stride + sg];
+      } else if (OBS == OBS_MASK) {
+        mpre = reinterpret_cast<const unsigned long long*>(obs)[(int64_t)e.w * stride + sg];
+      } else {
+        const double* src = reinterpret_cast<const double*>(obs) + ((int64_t)e.w * S + rh) * stride + sg;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) lpre[i] = (2 * i + rh < S) ? __ldcs(src + (int64_t)(2 * i) * stride) : 0.0;
+      }
+    }
+  };
+  prefetch(0);
+  __syncthreads();     // rs_s complete
 
   for (int tile = 0; tile < kTilesPerCta; ++tile) {
     const int64_t tile0 = ((int64_t)blockIdx.x * kTilesPerCta + tile) * kTileSites;
     if (tile0 >= n_sites) break;
     const int64_t site0 = tile0 + warp * kWarpSites;
 
-    // ---- L_b^T tile of this warp: [SP][16 sites] --------------------------------
+    // ---- stage the prefetched L_b^T tile of this warp: [SP][16 sites] ----------------------
+    const int kcur = live_pre ? kpre : -1;          // code of site column sc (gather edges)
     {
-      const int c = lane & 15;
-      const int64_t sg = site0 + c;
-      const bool live = sg < n_sites && status[sg] == RT_SITE_OK;
-      if (Lc) {
-        for (int r0 = 0; r0 < SP; r0 += 2) {
-          const int r = r0 + (lane >> 4);
-          Lw[r * kLd + c] = (r < S && live) ? Lc[(int64_t)r * stride + sg] : 0.0;
-        }
-      } else if (e.w < 0) {
-        for (int r0 = 0; r0 < SP; r0 += 2) {
-          const int r = r0 + (lane >> 4);
-          Lw[r * kLd + c] = (r < S && live) ? 1.0 : 0.0;
-        }
+      double* dst = Lw + rh * kLd + sc;
+      if (kind == 0 || (kind == 2 && OBS == OBS_DENSE)) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) dst[2 * i * kLd] = live_pre ? lpre[i] : 0.0;
+      } else if (kind == 1) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) dst[2 * i * kLd] = (live_pre && 2 * i + rh < S) ? 1.0 : 0.0;
       } else if (OBS == OBS_CODES) {
-        const int k = live ? reinterpret_cast<const uint8_t*>(obs)[(int64_t)e.w * stride + sg] : -1;
-        for (int r0 = 0; r0 < SP; r0 += 2) {
-          const int r = r0 + (lane >> 4);
-          Lw[r * kLd + c] = (r < S && live && (k == RT_MISSING || k == r)) ? 1.0 : 0.0;
-        }
-      } else if (OBS == OBS_MASK) {
-        const unsigned long long mk =
-            live ? reinterpret_cast<const unsigned long long*>(obs)[(int64_t)e.w * stride + sg] : 0ull;
-        for (int r0 = 0; r0 < SP; r0 += 2) {
-          const int r = r0 + (lane >> 4);
-          Lw[r * kLd + c] = (r < S && ((mk >> r) & 1ull)) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+          const int r = 2 * i + rh;
+          dst[2 * i * kLd] = (live_pre && r < S && (kcur == RT_MISSING || kcur == r)) ? 1.0 : 0.0;
         }
       } else {
-        const double* d = reinterpret_cast<const double*>(obs) + (int64_t)e.w * S * stride;
-        for (int r0 = 0; r0 < SP; r0 += 2) {
-          const int r = r0 + (lane >> 4);
-          Lw[r * kLd + c] = (r < S && live) ? d[(int64_t)r * stride + sg] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+          const int r = 2 * i + rh;
+          dst[2 * i * kLd] = (live_pre && r < S && ((mpre >> r) & 1ull)) ? 1.0 : 0.0;
         }
       }
     }
-    __syncwarp();
-
-    // ---- m = P L  (rows = parent states, cols = sites) -----------------------------
-    double m[MT][kNT][2];
+    // ---- D_a of this tile into registers (C-fragment layout), in flight under the m phase ----
+    double dpre[MT][kNT][2];
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
-      for (int j = 0; j < kNT; ++j) m[i][j][0] = m[i][j][1] = 0.0;
+      for (int j = 0; j < kNT; ++j)
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) {
-      double bf[kNT];
+        for (int h = 0; h < 2; ++h) {
+          const int s = 8 * i + g;
+          const int64_t sg = site0 + 8 * j + 2 * t + h;
+          dpre[i][j][h] = (s < S && sg < n_sites) ? Dp[(int64_t)s * stride + sg] : 0.0;
+        }
+    __syncwarp();
+
+    double m[MT][kNT][2];
+    if (gather) {
+      // ---- hard codes at a leaf: m = column k of P_b (row sum when unobserved) --------------
 #pragma unroll
-      for (int j = 0; j < kNT; ++j) bf[j] = Lw[(4 * kk + t) * kLd + 8 * j + g];
+      for (int j = 0; j < kNT; ++j)
 #pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const double a = Ps[(8 * i + g) * LDP + 4 * kk + t];
+        for (int h = 0; h < 2; ++h) {
+          const int k = __shfl_sync(0xffffffffu, kcur, 8 * j + 2 * t + h);
 #pragma unroll
-        for (int j = 0; j < kNT; ++j) dmma884(m[i][j][0], m[i][j][1], a, bf[j]);
+          for (int i = 0; i < MT; ++i) {
+            const int r = 8 * i + g;
+            m[i][j][h] = (k == RT_MISSING) ? rs_s[r] : ((k >= 0 && k < S) ? Ps[r * LDP + k] : 0.0);
+          }
+        }
+    } else {
+      // ---- m = P L  (rows = parent states, cols = sites) -----------------------------------
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) m[i][j][0] = m[i][j][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < KS; ++kk) {
+        double bf[kNT];
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) bf[j] = Lw[(4 * kk + t) * kLd + 8 * j + g];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const double a = Ps[(8 * i + g) * LDP + 4 * kk + t];
+#pragma unroll
+          for (int j = 0; j < kNT; ++j) dmma884(m[i][j][0], m[i][j][1], a, bf[j]);
+        }
       }
     }
     // ---- (BR) kl = K L, same shape as m ------------------------------------------------
@@ -192,11 +264,8 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
         double gv[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int s = 8 * i + g;
-          const int64_t sg = site0 + 8 * j + 2 * t + h;
-          double d = 0.0;
-          if (s < S && sg < n_sites) d = Dp[(int64_t)s * stride + sg];
-          gv[h] = (d > 0.0 && m[i][j][h] > 0.0) ? d / m[i][j][h] : 0.0;
+          const double d = dpre[i][j][h];
+          gv[h] = (d > 0.0 && m[i][j][h] > 0.0) ? d * fast_rcp(m[i][j][h]) : 0.0;
           if (BR) xs[j][h] = fma(gv[h], kl[BR ? i : 0][j][h], xs[j][h]);
         }
         *reinterpret_cast<double2*>(&Gw[(8 * i + g) * kLd + 8 * j + 2 * t]) = make_double2(gv[0], gv[1]);
@@ -250,6 +319,9 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
     }
     __syncthreads();   // every warp's L and G tiles are complete
 
+    // next tile's L rows / codes: in flight under the W contraction
+    prefetch(tile + 1);
+
     // ---- W[8*warp.., :] += G L^T over the 128 sites of the tile ------------------------
     if (warp < MT) {
 #pragma unroll 4
@@ -292,7 +364,7 @@ int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edg
   int64_t gr = (n_sites + 255) / 256;
   root_distn_generic_kernel<<<(int)(gr < 1184 ? gr : 1184), 256, sizeof(double) * S, stream>>>(
       S, n_sites, stride, root_distn, partials, status, node_distn, root_post_sum);
-  const size_t smem = sizeof(double) * ((size_t)SP * LDP + 2 * (size_t)kWarps * SP * kLd);
+  const size_t smem = sizeof(double) * ((size_t)SP * LDP + 2 * (size_t)kWarps * SP * kLd + SP);
   const int4* edges = reinterpret_cast<const int4*>(edges_dev);
   const unsigned gx = (unsigned)((n_sites + kTilesPerCta * kTileSites - 1) / (kTilesPerCta * kTileSites));
 #define RT_LAUNCH(OBSK)                                                                           \

@@ -22,34 +22,50 @@ constexpr int kBlock = 128;
 
 // One observation row of one site, fetched one obs-consuming op ahead of its use
 // (one specialisation per encoding so that only the live member occupies registers).
+// The row's element offset is precomputed per op in shared memory (row_off) and the thread
+// keeps one base pointer per site (base), so a fetch is a 64-bit add plus the loads.
 template <int S, int OBS> struct ObsVal;
 
 template <int S> struct ObsVal<S, OBS_CODES> {
   int k;
   __device__ __forceinline__ void init() { k = RT_MISSING; }
   // packed: two codes per byte (RT_OBS_CODES4), site i in nibble i & 1 of byte i >> 1, 15 = unobserved
-  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site,
-                                        int packed) {
-    if (row < 0) return;
-    if (packed) {
-      const int b = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * ((stride + 1) >> 1) + (site >> 1)];
-      k = (b >> ((int)(site & 1) * 4)) & 15;
-      if (k == 15) k = RT_MISSING;
-    } else {
-      k = reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * stride + site];
-    }
+  static __device__ __forceinline__ long long row_off(int row, int64_t stride, int packed) {
+    return (long long)row * (packed ? ((stride + 1) >> 1) : stride);
   }
-  __device__ __forceinline__ double get(int b) const { return (k == RT_MISSING || k == b) ? 1.0 : 0.0; }
+  static __device__ __forceinline__ const void* base(const void* obs, int64_t site, int packed) {
+    return reinterpret_cast<const uint8_t*>(obs) + (packed ? (site >> 1) : site);
+  }
+  // the raw byte is kept and decoded at its use one op later (decoding here would make the
+  // thread wait for the load it has just issued)
+  __device__ __forceinline__ void fetch(const void* __restrict__ tb, long long off, int64_t) {
+    if (off >= 0) k = reinterpret_cast<const uint8_t*>(tb)[off];
+  }
+  // nib < 0: one code per byte; else the shift of this site's nibble (byte 255 = both unobserved)
+  __device__ __forceinline__ int code(int nib) const {
+    if (nib < 0) return k;
+    const int c = (k >> nib) & 15;
+    return c == 15 ? RT_MISSING : c;
+  }
+  __device__ __forceinline__ double get(int b, int nib) const {
+    const int c = code(nib);
+    return (c == RT_MISSING || c == b) ? 1.0 : 0.0;
+  }
 };
 
 template <int S> struct ObsVal<S, OBS_MASK> {
   unsigned long long mk;
   __device__ __forceinline__ void init() { mk = ~0ull; }
-  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site,
-                                        int) {
-    if (row >= 0) mk = reinterpret_cast<const unsigned long long*>(obs)[(int64_t)row * stride + site];
+  static __device__ __forceinline__ long long row_off(int row, int64_t stride, int) {
+    return (long long)row * stride;
   }
-  __device__ __forceinline__ double get(int b) const { return ((mk >> b) & 1ull) ? 1.0 : 0.0; }
+  static __device__ __forceinline__ const void* base(const void* obs, int64_t site, int) {
+    return reinterpret_cast<const unsigned long long*>(obs) + site;
+  }
+  __device__ __forceinline__ void fetch(const void* __restrict__ tb, long long off, int64_t) {
+    if (off >= 0) mk = reinterpret_cast<const unsigned long long*>(tb)[off];
+  }
+  __device__ __forceinline__ double get(int b, int) const { return ((mk >> b) & 1ull) ? 1.0 : 0.0; }
 };
 
 template <int S> struct ObsVal<S, OBS_DENSE> {
@@ -58,34 +74,35 @@ template <int S> struct ObsVal<S, OBS_DENSE> {
 #pragma unroll
     for (int s = 0; s < S; ++s) d[s] = 1.0;
   }
-  __device__ __forceinline__ void fetch(const void* __restrict__ obs, int row, int64_t stride, int64_t site,
-                                        int) {
-    if (row < 0) return;
-    const double* p = reinterpret_cast<const double*>(obs) + (int64_t)row * S * stride + site;
+  static __device__ __forceinline__ long long row_off(int row, int64_t stride, int) {
+    return (long long)row * S * stride;
+  }
+  static __device__ __forceinline__ const void* base(const void* obs, int64_t site, int) {
+    return reinterpret_cast<const double*>(obs) + site;
+  }
+  __device__ __forceinline__ void fetch(const void* __restrict__ tb, long long off, int64_t stride) {
+    if (off < 0) return;
+    const double* p = reinterpret_cast<const double*>(tb) + off;
 #pragma unroll
     for (int s = 0; s < S; ++s) d[s] = __ldcs(p + (int64_t)s * stride);
   }
-  __device__ __forceinline__ double get(int b) const { return d[b]; }
+  __device__ __forceinline__ double get(int b, int) const { return d[b]; }
 };
 
-// Optional: dense emission rows streamed through a per-thread ring in shared memory with
-// cp.async (RT_DENSE_RING rows in flight per site).  MEASURED SLOWER on B200 than the
-// one-row register prefetch (C2, 1e6 sites: ring 0/1/2/4 -> 0.287/0.360/0.392/0.524 ms): the
-// ring's shared memory costs more occupancy than the extra bytes in flight buy, and the
-// kernel's floor is its instruction issue (0.262 ms with 1-byte codes), so it is off (0).
-#ifndef RT_DENSE_RING
-#define RT_DENSE_RING 0
-#endif
-constexpr int kRing = RT_DENSE_RING;            // rows in flight
-constexpr int kRingSlots = kRing + 1;
+// Recorded experiment (removed from the source, numbers in profiles/r1_dense_ring_sweep.log):
+// dense emission rows streamed through a per-thread cp.async ring in shared memory were
+// SLOWER on B200 than the one-row register prefetch (C2, 1e6 sites: ring 0/1/2/4 rows ->
+// 0.287/0.360/0.392/0.524 ms): the ring's shared memory costs more occupancy than the extra
+// bytes in flight buy, and the kernel's floor is its instruction issue.
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+// exponent field of the largest of S non-negative doubles via an integer max of their high
+// words (one VIMNMX per state instead of the ~7-instruction IEEE fmax); 0 for zeros/subnormals
+template <int S>
+__device__ __forceinline__ int max_hiword(const double (&a)[S]) {
+  int h = __double2hiint(a[0]);
+#pragma unroll
+  for (int s = 1; s < S; ++s) h = max(h, __double2hiint(a[s]));
+  return h;
 }
 
 // decoded op in shared memory: x = opcode, y = P offset in doubles (node*S*S),
@@ -107,16 +124,13 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // carve: decoded program | prefetch rows | pi | rowsum | P (optional) | stack | stack exponents
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
-  int* pre_s = reinterpret_cast<int*>(prog_s + n_ops);
-  double* pi_s = reinterpret_cast<double*>(pre_s + ((n_ops + 4) & ~3));
-  double* rowsum_s = pi_s + S;
-  double* P_s = rowsum_s + n_nodes * S;
+  long long* pre_s = reinterpret_cast<long long*>(prog_s + n_ops);     // [n_ops + 1], padded to even
+  double* pi_s = reinterpret_cast<double*>(pre_s + ((n_ops + 2) & ~1));
+  double* zero_s = pi_s + S;                     // [2], zeros
+  double* rowsum_s = zero_s + 2;
+  double* P_s = rowsum_s + n_nodes * S;          // 16-byte aligned for even S
   double* stk = P_s + (P_SMEM ? n_nodes * S * S : 0);
   int* estk = reinterpret_cast<int*>(stk + n_slots * NS * S * kBlock);
-  // dense emissions only: ring [slot][site q][state][thread] and the obs rows in order of use
-  double* ring = reinterpret_cast<double*>(
-      (reinterpret_cast<uintptr_t>(estk + n_slots * NS * kBlock) + 7) & ~(uintptr_t)7);
-  int* orow_s = reinterpret_cast<int*>(ring + ((OBS == OBS_DENSE && kRing > 0) ? kRingSlots * NS * S * kBlock : 0));
 
   const int tid = threadIdx.x;
   for (int i = tid; i < n_ops; i += kBlock) {
@@ -131,24 +145,17 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
   }
   __syncthreads();
   if (tid == 0) {
-    // pre_s[ip]: row consumed by the next obs-consuming op after ip
-    int nxt = -1;
+    // pre_s[ip]: element offset of the row consumed by the next obs-consuming op after ip
+    long long nxt = -1;
     for (int i = n_ops - 1; i >= 0; --i) {
       pre_s[i] = nxt;
       const int code = prog_s[i].x;
-      if (code == OP_MSG_OBS || code == OP_APPLY_OBS) nxt = prog_s[i].z;
+      if (code == OP_MSG_OBS || code == OP_APPLY_OBS) nxt = ObsVal<S, OBS>::row_off(prog_s[i].z, stride, obs_packed);
     }
     pre_s[n_ops] = nxt;     // first row of the program
-    if (OBS == OBS_DENSE && kRing > 0) {
-      int j = 0;
-      for (int i = 0; i < n_ops; ++i) {
-        const int code = prog_s[i].x;
-        if (code == OP_MSG_OBS || code == OP_APPLY_OBS) orow_s[j++] = prog_s[i].z;
-      }
-      for (int d = 0; d < kRing; ++d) orow_s[j++] = -1;
-    }
   }
   if (tid < S) pi_s[tid] = root_distn ? root_distn[tid] : 1.0;
+  if (tid < 2) zero_s[tid] = 0.0;
   for (int i = tid; i < n_nodes * S; i += kBlock) {
     double r = 0.0;
 #pragma unroll
@@ -172,57 +179,52 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
   {
     double acc[NS][S];
     int esum[NS];
-    ObsVal<S, OBS> cur[NS], nxt[NS];
+    // cur[q] holds the row of the NEXT obs-consuming op: an obs op computes from it and then
+    // fetches its successor into the same registers (no second buffer, no copies)
+    ObsVal<S, OBS> cur[NS];
+    const void* obs_q[NS];
+    int nib[NS];
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
 #pragma unroll
       for (int a = 0; a < S; ++a) acc[q][a] = 1.0;
       esum[q] = 0;
-      nxt[q].init();
+      obs_q[q] = ObsVal<S, OBS>::base(obs, site[q], obs_packed);
+      nib[q] = (int)(site[q] & 1) * 4;
       cur[q].init();
-      if (!(OBS == OBS_DENSE && kRing > 0)) nxt[q].fetch(obs, pre_s[n_ops], stride, site[q], obs_packed);
-    }
-    int jobs = 0;                    // index of the next obs-consuming op (dense ring)
-    auto ring_issue = [&](int j) {   // start the copy of the j-th obs row into its ring slot
-      const int row = orow_s[j];
-      if (row >= 0) {
-        double* dst = ring + (size_t)(j % kRingSlots) * NS * S * kBlock + tid;
-#pragma unroll
-        for (int q = 0; q < NS; ++q) {
-          const double* src = reinterpret_cast<const double*>(obs) + (int64_t)row * S * stride + site[q];
-#pragma unroll
-          for (int b = 0; b < S; ++b) cp_async8(dst + (q * S + b) * kBlock, src + (int64_t)b * stride);
-        }
-      }
-      cp_async_commit();
-    };
-    if (OBS == OBS_DENSE && kRing > 0) {
-#pragma unroll
-      for (int d = 0; d < kRing; ++d) ring_issue(d);
+      cur[q].fetch(obs_q[q], pre_s[n_ops], stride);
     }
 
     for (int ip = 0; ip < n_ops; ++ip) {
       const int4 op = prog_s[ip];
       const double* Pc = P_SMEM ? (P_s + op.y) : (P + op.y);
-      if (op.x == OP_MSG_OBS || op.x == OP_APPLY_OBS) {
-        if constexpr (OBS == OBS_DENSE && kRing > 0) {
-          cp_async_wait<(kRing > 0 ? kRing - 1 : 0)>();          // the oldest row in flight has landed
-          const double* src = ring + (size_t)(jobs % kRingSlots) * NS * S * kBlock + tid;
+      // m[q][a] = sum_b P[a][b] v[q][b]; even S with P in shared memory: 16-byte loads
+      auto matvec = [&](const double (&v)[NS][S], double (&m)[NS][S]) {
 #pragma unroll
-          for (int q = 0; q < NS; ++q)
+        for (int a = 0; a < S; ++a) {
 #pragma unroll
-            for (int b = 0; b < S; ++b) cur[q].d[b] = src[(q * S + b) * kBlock];
-          ring_issue(jobs + kRing);            // reuses the slot read one obs op ago
-          ++jobs;
-        } else {
-          const int row = pre_s[ip];
+          for (int q = 0; q < NS; ++q) m[q][a] = 0.0;
+          if constexpr (P_SMEM && (S % 2 == 0)) {
+            const double2* pr = reinterpret_cast<const double2*>(Pc + a * S);
 #pragma unroll
-          for (int q = 0; q < NS; ++q) {
-            cur[q] = nxt[q];
-            nxt[q].fetch(obs, row, stride, site[q], obs_packed);
+            for (int b = 0; b < S / 2; ++b) {
+              const double2 p = pr[b];
+#pragma unroll
+              for (int q = 0; q < NS; ++q) {
+                m[q][a] = fma(p.x, v[q][2 * b], m[q][a]);
+                m[q][a] = fma(p.y, v[q][2 * b + 1], m[q][a]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < S; ++b) {
+              const double p = Pc[a * S + b];
+#pragma unroll
+              for (int q = 0; q < NS; ++q) m[q][a] = fma(p, v[q][b], m[q][a]);
+            }
           }
         }
-      }
+      };
       switch (op.x) {
         case OP_MSG_SLOT: {
           double v[NS][S], m[NS][S];
@@ -232,17 +234,8 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
 #pragma unroll
             for (int b = 0; b < S; ++b) v[q][b] = sp[b * kBlock];
             esum[q] += estk[op.z / S + q * kBlock + tid];
-#pragma unroll
-            for (int a = 0; a < S; ++a) m[q][a] = 0.0;
           }
-#pragma unroll
-          for (int a = 0; a < S; ++a)
-#pragma unroll
-            for (int b = 0; b < S; ++b) {
-              const double p = Pc[a * S + b];
-#pragma unroll
-              for (int q = 0; q < NS; ++q) m[q][a] = fma(p, v[q][b], m[q][a]);
-            }
+          matvec(v, m);
 #pragma unroll
           for (int q = 0; q < NS; ++q)
 #pragma unroll
@@ -252,8 +245,15 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
           if constexpr (OBS == OBS_CODES) {
 #pragma unroll
             for (int q = 0; q < NS; ++q) {
-              const int k = cur[q].k;
-              if (k == RT_MISSING) {
+              const int k = cur[q].code(obs_packed ? nib[q] : -1);
+              if constexpr (P_SMEM) {
+                // branch-free: column k of P, the row sums, or zeros (invalid code), all in
+                // shared memory (divergent writes to acc made the compiler copy acc every op)
+                const double* src = (k == RT_MISSING) ? (rowsum_s + op.y / S) : (k < S ? Pc + k : zero_s);
+                const int strd = (k == RT_MISSING) ? 1 : (k < S ? S : 0);
+#pragma unroll
+                for (int a = 0; a < S; ++a) acc[q][a] *= src[a * strd];
+              } else if (k == RT_MISSING) {
 #pragma unroll
                 for (int a = 0; a < S; ++a) acc[q][a] *= rowsum_s[op.y / S + a];
               } else if (k < S) {
@@ -269,23 +269,16 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
 #pragma unroll
             for (int q = 0; q < NS; ++q)
 #pragma unroll
-              for (int b = 0; b < S; ++b) {
-                v[q][b] = cur[q].get(b);
-                m[q][b] = 0.0;
-              }
-#pragma unroll
-            for (int a = 0; a < S; ++a)
-#pragma unroll
-              for (int b = 0; b < S; ++b) {
-                const double p = Pc[a * S + b];
-#pragma unroll
-                for (int q = 0; q < NS; ++q) m[q][a] = fma(p, v[q][b], m[q][a]);
-              }
+              for (int b = 0; b < S; ++b) v[q][b] = cur[q].get(b, obs_packed ? nib[q] : -1);
+            matvec(v, m);
 #pragma unroll
             for (int q = 0; q < NS; ++q)
 #pragma unroll
               for (int a = 0; a < S; ++a) acc[q][a] *= m[q][a];
           }
+          const long long off = pre_s[ip];
+#pragma unroll
+          for (int q = 0; q < NS; ++q) cur[q].fetch(obs_q[q], off, stride);
         } break;
         case OP_MSG_ONES: {
 #pragma unroll
@@ -299,18 +292,19 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
 #pragma unroll
           for (int q = 0; q < NS; ++q) {
 #pragma unroll
-            for (int a = 0; a < S; ++a) acc[q][a] *= cur[q].get(a);
+            for (int a = 0; a < S; ++a) acc[q][a] *= cur[q].get(a, obs_packed ? nib[q] : -1);
           }
+          const long long off = pre_s[ip];
+#pragma unroll
+          for (int q = 0; q < NS; ++q) cur[q].fetch(obs_q[q], off, stride);
         } break;
         case OP_STORE:
         case OP_ROOT: {
 #pragma unroll
           for (int q = 0; q < NS; ++q) {
-            double mx = acc[q][0];
-#pragma unroll
-            for (int a = 1; a < S; ++a) mx = fmax(mx, acc[q][a]);
-            if (mx > 0.0) {
-              const int e = rt_exponent(mx);
+            const int hmx = max_hiword<S>(acc[q]);
+            if (hmx >= 0x00100000) {          // largest entry is a positive normal number
+              const int e = (hmx >> 20) - 1023;
               const double sc = rt_pow2_neg(e);
 #pragma unroll
               for (int a = 0; a < S; ++a) acc[q][a] *= sc;
@@ -370,12 +364,10 @@ int launch_t(int64_t n_sites, int64_t stride, const int4* program, int n_ops, in
              double* partials, int32_t* exponents, double* loglik, int8_t* status,
              double* loglik_sum, cudaStream_t stream, int packed = 0) {
   constexpr int NS = (S <= 4) ? 2 : 1;      // sites per thread
-  size_t base = (size_t)n_ops * sizeof(int4) + sizeof(int) * (((size_t)n_ops + 4) & ~(size_t)3) +
-                sizeof(double) * (S + (size_t)n_nodes * S);
+  size_t base = (size_t)n_ops * sizeof(int4) + sizeof(long long) * (((size_t)n_ops + 2) & ~(size_t)1) +
+                sizeof(double) * (S + 2 + (size_t)n_nodes * S);
   size_t stack = (size_t)n_slots * NS * S * kBlock * sizeof(double) +
                  (size_t)n_slots * NS * kBlock * sizeof(int) + 8;
-  if (OBS == OBS_DENSE && kRing > 0)
-    stack += (size_t)kRingSlots * NS * S * kBlock * sizeof(double) + sizeof(int) * ((size_t)n_ops + kRing + 2);
   size_t pbytes = (size_t)n_nodes * S * S * sizeof(double);
   const size_t limit = 200 * 1024;
   const bool p_in_smem = base + stack + pbytes <= 96 * 1024;
