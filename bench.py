@@ -533,7 +533,36 @@ def bench_c3(dev, args):
     mjp.transition_matrices()
     b.record()
     torch.cuda.synchronize()
+    # expectations at the same size: up pass with stored partials + level-synchronous DMMA down pass
+    # (three contractions per internal edge; a leaf edge with hard codes gathers m and contracts W only)
+    exp = {}
+    try:
+        mjp.events = {}
+        for _ in range(2):
+            mjp.expected_history_statistics(obs)
+        torch.cuda.synchronize()
+        mjp.events = sub = {}
+        te = []
+        for _ in range(3):
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2.record()
+            mjp.expected_history_statistics(obs)
+            b2.record()
+            torch.cuda.synchronize()
+            te.append(a2.elapsed_time(b2))
+        pair = lambda L: [(L[i], L[i + 1]) for i in range(0, len(L) - 1, 2)]
+        up_ms = float(np.mean([x.elapsed_time(y) for x, y in pair(sub['up'])]))
+        down_ms = float(np.mean([x.elapsed_time(y) for x, y in pair(sub['down'])]))
+        n_leaf_edges = E - n_int_edges
+        flops_down = N * (3.0 * n_int_edges + 1.0 * n_leaf_edges) * 2.0 * 64 * 64
+        exp = dict(expectations_ms=float(np.mean(te)), up_store_ms=up_ms, down_ms=down_ms,
+                   down_tflops_executed_on_tensor_pipe=flops_down / (down_ms * 1e-3) / 1e12,
+                   down_frac_executed=flops_down / (down_ms * 1e-3) / 1e12 / peak)
+        mjp.events = None
+    except Exception as e:  # pragma: no cover
+        exp = dict(expectations_error=repr(e))
     return dict(workload='C3: 61-state MG94 codon MJP, 128-leaf tree, 1e5 sites, log-lik',
+                expectations=exp,
                 ms=ms, messages_per_sec=N * E / (ms * 1e-3),
                 tflops_nominal=flops_nominal / (ms * 1e-3) / 1e12,
                 tflops_executed_on_tensor_pipe=flops_dmma / (ms * 1e-3) / 1e12,

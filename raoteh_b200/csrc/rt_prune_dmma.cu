@@ -20,16 +20,26 @@
 // P_c is stored XOR-swizzled (column ^ 4*(row&3)) so fragment loads are bank-conflict
 // free without padding.
 #include "rt_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int kWarps = 4;                // 2 CTAs per SM run out of phase: one's bookkeeping hides behind the other's DMMAs
+// RT_PD_NT n-tiles (8 sites each) per warp.  2: 4 warps x 16 sites, ~246 registers, one warp of each
+// of the 2 resident CTAs per SM sub-partition.  1: 8 warps x 8 sites, <= 128 registers, two warps
+// of each CTA per sub-partition (more warps to cover the latency-bound bookkeeping between the
+// DMMA phases, at 1.125 instead of 0.625 shared-memory fragment loads per DMMA).
+#ifndef RT_PD_NT
+#define RT_PD_NT 2
+#endif
+constexpr int kNT = RT_PD_NT;
+constexpr int kWarps = 8 / kNT;
 constexpr int kThreads = kWarps * 32;
-constexpr int kNT = 2;                 // n-tiles (8 sites each) per warp
-constexpr int kWarpSites = 8 * kNT;    // 16
-constexpr int kTileSites = kWarps * kWarpSites;  // 128
-constexpr int kLdB = kWarpSites + 4;   // 20: B tile row stride (== 4 mod 16 -> conflict-free)
+constexpr int kWarpSites = 8 * kNT;    // 16 / 8
+constexpr int kTileSites = kWarps * kWarpSites;  // 64
+constexpr int kLdB = kWarpSites + 4;   // 20 / 12: B tile row stride (== 4 mod 8 -> conflict-free)
+constexpr int kFillRows = 32 / kWarpSites;   // rows of the B tile one warp fills per step
 constexpr int kMaxSlots = 32;
+constexpr int kPhaseDelayCycles = 6000;   // one-time start offset of the second CTA on each SM
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -99,7 +109,8 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
                   const double* __restrict__ root_distn, const void* __restrict__ obs,
                   double* __restrict__ slots_ws, double* __restrict__ partials,
                   int32_t* __restrict__ exponents, double* __restrict__ loglik,
-                  int8_t* __restrict__ status, double* __restrict__ loglik_sum) {
+                  int8_t* __restrict__ status, double* __restrict__ loglik_sum,
+                  int* __restrict__ sm_arrivals, int phase_delay) {
   constexpr int SP = 8 * MT;
   constexpr int LDP = SP;       // swizzled, no padding
   constexpr int KS = SP / 4;   // k-steps
@@ -149,6 +160,25 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
   };
   if (tid == 0) { issue_next(); issue_next(); }
   int consumed = 0;
+
+  // The two CTAs resident on an SM run the same program with the same timing, so launched
+  // together they stay in lockstep: both want the FP64 tensor pipe at the same time and both
+  // leave it idle during their bookkeeping.  The second CTA to arrive on each SM therefore
+  // waits phase_delay cycles once; every later CTA inherits the offset from the finishing
+  // time of its predecessor.
+  if (phase_delay > 0) {
+    __shared__ int arrival;
+    if (tid == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      arrival = atomicAdd(&sm_arrivals[smid], 1);
+    }
+    __syncthreads();
+    if (arrival == 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < phase_delay) __nanosleep(200);
+    }
+  }
 
   // the sites this thread's C-fragment columns map to
   const int64_t site0 = (int64_t)blockIdx.x * kTileSites + warp * kWarpSites;
@@ -219,16 +249,16 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
                                     : slots_ws + (int64_t)op.z * S * stride;
           __syncwarp();
           {
-            const int c = lane & 15, rh = lane >> 4;
+            const int c = lane % kWarpSites, rh = lane / kWarpSites;
             const bool okc = site0 + c < n_sites;
             const double* sp = src + (int64_t)rh * stride + site0 + c;
             double* bp = Bw + rh * kLdB + c;
 #pragma unroll 8
-            for (int r0 = 0; r0 < SP; r0 += 2) {
+            for (int r0 = 0; r0 < SP; r0 += kFillRows) {
               const double v = (r0 + rh < S && okc) ? __ldcs(sp) : 0.0;
               *bp = v;
-              sp += 2 * stride;
-              bp += 2 * kLdB;
+              sp += kFillRows * stride;
+              bp += kFillRows * kLdB;
             }
           }
         }
@@ -240,17 +270,17 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
         __syncwarp();
         if (OBS == OBS_MASK) {
           const unsigned long long* mk = reinterpret_cast<const unsigned long long*>(obs);
-          const int c = lane & 15;
+          const int c = lane % kWarpSites;
           const int64_t sg = site0 + c;
           const unsigned long long m = (sg < n_sites) ? mk[(int64_t)op.z * stride + sg] : ~0ull;
-          for (int r0 = 0; r0 < SP; r0 += 2) {
-            const int r = r0 + (lane >> 4);
+          for (int r0 = 0; r0 < SP; r0 += kFillRows) {
+            const int r = r0 + lane / kWarpSites;
             Bw[r * kLdB + c] = (r < S && ((m >> r) & 1ull)) ? 1.0 : 0.0;
           }
         } else {
           const double* d = reinterpret_cast<const double*>(obs) + (int64_t)op.z * S * stride;
-          for (int r0 = 0; r0 < SP; r0 += 2) {
-            const int r = r0 + (lane >> 4), c = lane & 15;
+          for (int r0 = 0; r0 < SP; r0 += kFillRows) {
+            const int r = r0 + lane / kWarpSites, c = lane % kWarpSites;
             const int64_t sg = site0 + c;
             double v = (r < S) ? 1.0 : 0.0;
             if (r < S && sg < n_sites) v = d[(int64_t)r * stride + sg];
@@ -447,7 +477,7 @@ template <int MT, int OBS, bool STORE>
 int launch(int S, int64_t n_sites, int64_t stride, const int4* program, int n_ops, int n_slots,
            const double* Ppad, const double* PT, const double* rowsum, const double* root_distn,
            const void* obs, double* slots_ws, double* partials, int32_t* exponents, double* loglik,
-           int8_t* status, double* loglik_sum, cudaStream_t stream) {
+           int8_t* status, double* loglik_sum, int* sm_arrivals, int phase_delay, cudaStream_t stream) {
   constexpr int SP = 8 * MT;
   constexpr int LDP = SP;
   auto kern = prune_dmma_kernel<MT, OBS, STORE>;
@@ -459,7 +489,7 @@ int launch(int S, int64_t n_sites, int64_t stride, const int4* program, int n_op
   const unsigned grid = (unsigned)((n_sites + kTileSites - 1) / kTileSites);
   kern<<<grid, kThreads, smem, stream>>>(S, n_sites, stride, program, n_ops, n_slots, Ppad, PT,
                                          rowsum, root_distn, obs, slots_ws, partials, exponents,
-                                         loglik, status, loglik_sum);
+                                         loglik, status, loglik_sum, sm_arrivals, phase_delay);
   RT_CUDA_CHECK(cudaGetLastError());
   return RT_OK;
 }
@@ -469,9 +499,9 @@ int launch_mt(int S, int obs_kind, bool store, int64_t n_sites, int64_t stride, 
               int n_ops, int n_slots, const double* Ppad, const double* PT, const double* rowsum,
               const double* root_distn, const void* obs, double* slots_ws, double* partials,
               int32_t* exponents, double* loglik, int8_t* status, double* loglik_sum,
-              cudaStream_t stream) {
+              int* sm_arrivals, int phase_delay, cudaStream_t stream) {
 #define RT_ARGS S, n_sites, stride, program, n_ops, n_slots, Ppad, PT, rowsum, root_distn, obs, \
-                slots_ws, partials, exponents, loglik, status, loglik_sum, stream
+                slots_ws, partials, exponents, loglik, status, loglik_sum, sm_arrivals, phase_delay, stream
   switch (obs_kind) {
     case OBS_CODES: return store ? launch<MT, OBS_CODES, true>(RT_ARGS) : launch<MT, OBS_CODES, false>(RT_ARGS);
     case OBS_MASK:  return store ? launch<MT, OBS_MASK, true>(RT_ARGS)  : launch<MT, OBS_MASK, false>(RT_ARGS);
@@ -495,16 +525,25 @@ int rt_prune_dmma_dispatch(int S, int obs_kind, bool store, int64_t n_sites, int
   const size_t n_pad = (size_t)n_nodes * SP * LDP, n_pt = (size_t)n_nodes * SP * SP,
                n_rs = (size_t)n_nodes * SP;
   const size_t n_slot = store ? 0 : (size_t)n_slots * S * (size_t)stride;
-  RT_CUDA_CHECK(cudaMallocAsync(&ws, sizeof(double) * (n_pad + n_pt + n_rs + n_slot), stream));
+  constexpr size_t kArrivals = 1024;     // >= SM count, in ints (512 doubles of workspace)
+  RT_CUDA_CHECK(cudaMallocAsync(&ws, sizeof(double) * (n_pad + n_pt + n_rs + n_slot + kArrivals / 2), stream));
   double* Ppad = ws;
   double* PT = Ppad + n_pad;
   double* rowsum = PT + n_pt;
-  double* slots_ws = store ? nullptr : rowsum + n_rs;
+  int* sm_arrivals = reinterpret_cast<int*>(rowsum + n_rs);
+  double* slots_ws = store ? nullptr : rowsum + n_rs + kArrivals / 2;
+  static int phase_delay = -1;
+  if (phase_delay < 0) {
+    const char* env = getenv("RT_PRUNE_DMMA_PHASE_DELAY");
+    phase_delay = env ? atoi(env) : kPhaseDelayCycles;
+  }
+  RT_CUDA_CHECK(cudaMemsetAsync(sm_arrivals, 0, sizeof(int) * kArrivals, stream));
   pack_kernel<<<n_nodes, 256, 0, stream>>>(P, S, SP, n_nodes, Ppad, PT, rowsum);
   const int4* prog = reinterpret_cast<const int4*>(program);
   int rc;
 #define RT_ARGS S, obs_kind, store, n_sites, stride, prog, n_ops, n_slots, Ppad, PT, rowsum, \
-                root_distn, obs, slots_ws, partials, exponents, loglik, status, loglik_sum, stream
+                root_distn, obs, slots_ws, partials, exponents, loglik, status, loglik_sum,   \
+                sm_arrivals, phase_delay, stream
   switch (MT) {
     case 2: rc = launch_mt<2>(RT_ARGS); break;
     case 4: rc = launch_mt<4>(RT_ARGS); break;

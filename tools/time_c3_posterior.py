@@ -24,4 +24,4 @@ down = np.mean([x.elapsed_time(y) for x, y in pair(sub['down'])])
 n_int = int((~sched.is_leaf[1:]).sum())
 print(json.dumps(dict(total_ms=float(np.mean(ts)), up_ms=float(up), down_ms=float(down), n_levels=r['n_levels'],
                       edges=sched.n_edges, internal_edges=n_int,
-                      down_tflops_executed=float(obs.n_sites * sched.n_edges * 3 * 2 * 64 * 64 / (down * 1e-3) / 1e12))))
+                      down_tflops_executed=float(obs.n_sites * (3 * n_int + (sched.n_edges - n_int)) * 2 * 64 * 64 / (down * 1e-3) / 1e12))))
