@@ -201,6 +201,19 @@ down_level_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ edge
 #ifndef RT_WALK_BLOCK
 #define RT_WALK_BLOCK 128
 #endif
+// G = D / m: D == 0 gives 0 * (1/m) = 0 for any m > 0, so only m > 0 needs a test (one DSETP
+// per entry less on the FP64 pipe); RT_WALK_TEST_D=1 restores the explicit D > 0 test
+#ifndef RT_WALK_TEST_D
+#define RT_WALK_TEST_D 0
+#endif
+#if RT_WALK_TEST_D
+#define RT_WALK_DCHECK(d) (d) > 0.0 &&
+#else
+#define RT_WALK_DCHECK(d)
+#endif
+#ifndef RT_WALK_L2PF
+#define RT_WALK_L2PF 0      // distance (ops) of the extra L2 prefetch of stored partials; 0 = off
+#endif
 constexpr int kWalkBlock = RT_WALK_BLOCK;
 
 template <int V>
@@ -356,6 +369,21 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
     // internal child, or the code byte of a leaf) are issued into a second register buffer
     // before op ip is computed: ping-pong buffers, loop unrolled by two.
     auto issue = [&](int j, double (&Lb)[NS][S], int (&kb)[NS]) {
+#if RT_WALK_L2PF > 0
+      // stored partials of the op RT_WALK_L2PF further down the walk: pulled into L2 now, so the
+      // register prefetch one op ahead of the use finds them there
+      if (j - RT_WALK_L2PF >= 0) {
+        const int4 px = prog_s[j - RT_WALK_L2PF];
+        if ((px.x & 0xff) == OP_MSG_SLOT) {
+          const double* src = partials + off_s[j - RT_WALK_L2PF] + site0;
+#pragma unroll
+          for (int q = 0; q < NS; ++q)
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+              asm volatile("prefetch.global.L2 [%0];" :: "l"(src + (int64_t)s * stride + q * kWalkBlock));
+        }
+      }
+#endif
       if (j < 0) return;
       const int4 nx = prog_s[j];
       const int ncode = nx.x & 0xff;
@@ -445,7 +473,7 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
               double m = 0.0;
 #pragma unroll
               for (int b = 0; b < S; ++b) m = fma(Pr[a * S + b], L[b], m);
-              G[a] = (cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
+              G[a] = (RT_WALK_DCHECK(cur[q][a]) m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
             }
             double t[S];
 #pragma unroll
@@ -487,7 +515,7 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
 #pragma unroll
             for (int a = 0; a < S; ++a) {
               const double m = Pl[a * SP1 + col];
-              G[a] = (live[q] && cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
+              G[a] = (live[q] && RT_WALK_DCHECK(cur[q][a]) m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
               L[a] = (k == RT_MISSING || k == a) ? 1.0 : 0.0;
             }
 #pragma unroll
@@ -531,7 +559,7 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
               double m = 0.0;
 #pragma unroll
               for (int b = 0; b < S; ++b) m = fma(Pr[a * S + b], L[b], m);
-              G[a] = (cur[q][a] > 0.0 && m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
+              G[a] = (RT_WALK_DCHECK(cur[q][a]) m > 0.0) ? cur[q][a] * fast_rcp(m) : 0.0;
             }
 #pragma unroll
             for (int i = 0; i < S * S; ++i) w[i] = fma(G[i / S], L[i % S], w[i]);
