@@ -53,8 +53,11 @@ def launches(csv_path, command, note):
 
 
 def full(rep_path):
-    out = subprocess.run(['ncu', '-i', rep_path, '--page', 'raw', '--csv'], capture_output=True,
-                         text=True).stdout
+    if rep_path.endswith('.csv'):      # already exported on the GPU box (`ncu -i rep --page raw --csv`)
+        out = open(rep_path).read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep_path, '--page', 'raw', '--csv'], capture_output=True,
+                             text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     res = []
