@@ -140,6 +140,11 @@ raoteh_kernel(SweepArgs A) {
       // =============================== UP ===============================
       int nA = 0;                                   // entries pushed to the scratch list
       int rd = A.cap - A.ev_total[traj];            // read cursor in the old jump list
+      // the old jump list is consumed strictly in order (across edges too), so its next entry
+      // is loaded when the previous one is consumed, long before it is needed
+      float pf_time = -1.0f;
+      int pf_sb = 0;
+      if (A.init_k < 0 && rd < A.cap) { pf_time = evt_p[rd]; pf_sb = evs_p[rd]; }
       bool overflow = false;
       double acc[S];
 #pragma unroll
@@ -179,8 +184,9 @@ raoteh_kernel(SweepArgs A) {
             cur = ns_p[(int64_t)c * st];
             k_old = cnt_p[(int64_t)c * st];
             if (k_old > 0) {
-              next_old = evt_p[rd];
-              next_sb = evs_p[rd];
+              next_old = pf_time;
+              next_sb = pf_sb;
+              if (rd + 1 < A.cap) { pf_time = evt_p[rd + 1]; pf_sb = evs_p[rd + 1]; }
             }
           }
           while (true) {
@@ -212,9 +218,15 @@ raoteh_kernel(SweepArgs A) {
             // record beta just below the event, then push it through B
             if (nA < A.scr_cap) {
               unsigned char* rp = rec_p + (size_t)nA * kRec;
-              *reinterpret_cast<float2*>(rp) = make_float2(cand, __uint_as_float(u_draw));
+              if constexpr (S % 2 == 0) {
 #pragma unroll
-              for (int s = 0; s < S; ++s) reinterpret_cast<double*>(rp + 8)[s] = beta[s];
+                for (int s = 0; s < S; s += 2)
+                  reinterpret_cast<double2*>(rp)[s / 2] = make_double2(beta[s], beta[s + 1]);
+              } else {
+#pragma unroll
+                for (int s = 0; s < S; ++s) reinterpret_cast<double*>(rp)[s] = beta[s];
+              }
+              *reinterpret_cast<float2*>(rp + 8 * S) = make_float2(cand, __uint_as_float(u_draw));
             } else overflow = true;
             ++nA; ++kA;
             {
@@ -235,8 +247,9 @@ raoteh_kernel(SweepArgs A) {
               ++rd;
               --k_old;
               if (k_old > 0) {
-                next_old = evt_p[rd];
-                next_sb = evs_p[rd];
+                next_old = pf_time;
+                next_sb = pf_sb;
+                if (rd + 1 < A.cap) { pf_time = evt_p[rd + 1]; pf_sb = evs_p[rd + 1]; }
               } else {
                 next_old = -1.0f;
               }
@@ -301,6 +314,26 @@ raoteh_kernel(SweepArgs A) {
       ns_p[0] = (uint8_t)root_state;
       int rdA = nA;          // scratch is consumed backwards
       int wr = A.cap;        // new jump list grows backwards from the end
+      // ... strictly in order, so record rdA - 2 is loaded while record rdA - 1 is sampled
+      float2 tu_n = make_float2(0.0f, 0.0f);
+      double b_n[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) b_n[s] = 0.0;
+      auto load_rec = [&](int idx) {
+        const unsigned char* rp = rec_p + (size_t)idx * kRec;
+        if constexpr (S % 2 == 0) {
+#pragma unroll
+          for (int s = 0; s < S; s += 2) {
+            const double2 v = reinterpret_cast<const double2*>(rp)[s / 2];
+            b_n[s] = v.x; b_n[s + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < S; ++s) b_n[s] = reinterpret_cast<const double*>(rp)[s];
+        }
+        tu_n = *reinterpret_cast<const float2*>(rp + 8 * S);
+      };
+      if (nA > 0) load_rec(nA - 1);
       bool pool_overflow = false;
       for (int ip = A.n_ops - 1; ip >= 0; --ip) {
         const int4 op = prog_s[ip];
@@ -313,17 +346,16 @@ raoteh_kernel(SweepArgs A) {
         int kept = 0;
         for (int j = 0; j < kA; ++j) {
           --rdA;
-          const unsigned char* rp = rec_p + (size_t)rdA * kRec;
-          const float2 tu = *reinterpret_cast<const float2*>(rp);
-          const float tau = tu.x;
-          const uint32_t u_draw = __float_as_uint(tu.y);
+          const float tau = tu_n.x;
+          const uint32_t u_draw = __float_as_uint(tu_n.y);
           // child-side state ~ B[cur, :] * beta  (_sample_mc0.py:66-90)
           double w[S], tot = 0.0;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
-            w[s] = B_s[cur * S + s] * reinterpret_cast<const double*>(rp + 8)[s];
+            w[s] = B_s[cur * S + s] * b_n[s];
             tot += w[s];
           }
+          if (rdA > 0) load_rec(rdA - 1);
           const double x = ((double)u_draw + 0.5) * 2.3283064365386963e-10 * tot;
           double cum = 0.0;
           int nxt = -1;
