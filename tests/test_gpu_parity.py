@@ -237,6 +237,60 @@ def test_expectations_match_oracle(rt, S, n_leaves, n_sites):
     np.testing.assert_allclose(float(r['dwell'].sum()), length.sum() * n_sites, rtol=1e-10)
 
 
+@pytest.mark.parametrize('S,n_leaves,n_sites,kind', [(20, 9, 2500, 'codes'), (61, 10, 2100, 'codes'),
+                                                     (20, 7, 1300, 'mask'), (11, 6, 1100, 'dense')])
+def test_large_state_down_pass_tiles_and_observation_kinds(rt, S, n_leaves, n_sites, kind):
+    """The DMMA down pass (9 <= S <= 64) across several CTAs of the site axis (1024 sites each: the
+    next tile's rows are prefetched across tile ends and past the last site), with 30 % unobserved
+    leaf cells (row-sum gathers on leaf edges), and with mask / dense observations (contracted,
+    not gathered), against the oracle (_mjp_dense.py:410-539)."""
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200 import synth
+    rng = np.random.default_rng(77 + S)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.15, rng)
+    if S == 61:
+        Q, pi, _ = synth.mg94()
+    else:
+        Q = rng.exponential(1.0, size=(S, S))
+        np.fill_diagonal(Q, 0)
+        Q -= np.diag(Q.sum(axis=1))
+        Q /= np.abs(np.diag(Q)).mean()
+        pi = rng.dirichlet(np.ones(S))
+    n = len(parent)
+    sched = TreeSchedule(parent, length)
+    mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+    P = np_oracle.expm_edges(Q, length)
+    if kind == 'codes':
+        codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.3)
+        obs = rt.Observations.from_leaf_codes(sched, codes, leaves)
+        oobs = np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes)
+    elif kind == 'mask':
+        bits = rng.random((n, n_sites, S)) < 0.4
+        bits[np.arange(n)[:, None], np.arange(n_sites)[None, :], rng.integers(0, S, size=(n, n_sites))] = True
+        unrestricted = rng.random((n, n_sites)) < 0.7
+        unrestricted[leaves] = rng.random((len(leaves), n_sites)) < 0.1
+        bits[unrestricted] = True
+        mask = (bits.astype(np.uint64) << np.arange(S, dtype=np.uint64)[None, None, :]).sum(axis=2).astype(np.uint64)
+        obs = rt.Observations.from_masks(sched, mask)
+        oobs = np_oracle.Obs('mask', S, n_sites, mask=mask)
+    else:
+        lik = rng.random((len(leaves), S, n_sites)) ** 3
+        obs = rt.Observations.from_dense(sched, lik, leaves)
+        full = np.ones((n, n_sites, S))
+        has = np.zeros(n, dtype=bool)
+        has[leaves] = True
+        full[leaves] = lik.transpose(0, 2, 1)
+        oobs = np_oracle.Obs('dense', S, n_sites, lik=full, has=has)
+    r = mjp.expected_history_statistics(obs)
+    o = np_oracle.expected_history_statistics(parent, length, Q, P, oobs, pi)
+    ok = np.isfinite(o['loglik'])
+    assert ok.sum() > n_sites // 2
+    np.testing.assert_allclose(r['loglik'].cpu().numpy()[ok], o['loglik'][ok], rtol=RTOL)
+    np.testing.assert_allclose(r['dwell'].cpu().numpy(), o['dwell'], rtol=RTOL)
+    np.testing.assert_allclose(r['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(float(r['dwell'].sum()), length.sum() * ok.sum(), rtol=1e-10)
+
+
 def test_support_sets_match_oracle(rt):
     import torch
     from raoteh_b200.lowering import TreeSchedule
