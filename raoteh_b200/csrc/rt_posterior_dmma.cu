@@ -96,6 +96,7 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
   double* Lall = Ps + SP * LDP;                              // [kWarps][SP][kLd]
   double* Gall = Lall + (size_t)kWarps * SP * kLd;           // [kWarps][SP][kLd]
   double* rs_s = Gall + (size_t)kWarps * SP * kLd;           // [SP] row sums of P_b
+  double* krs_s = rs_s + SP;                                 // [SP] row sums of K_b (BR only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -123,6 +124,12 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
     double sum = 0.0;
     for (int c = 0; c < S; ++c) sum += Ps[tid * LDP + c];
     rs_s[tid] = sum;
+  } else if (BR && tid < 2 * SP) {
+    const int r = tid - SP;
+    double sum = 0.0;
+    if (r < S)
+      for (int c = 0; c < S; ++c) sum += Kmat[(size_t)b * S * S + r * S + c];
+    krs_s[r] = sum;
   }
 
   // ---- staging layout of L_b^T: lane owns site column lane & 15, rows r0 + (lane >> 4) ------
@@ -234,7 +241,24 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
     // ---- (BR) kl = K L, same shape as m ------------------------------------------------
     double kl[BR ? MT : 1][kNT][2];
     double xs[kNT][2];
-    if (BR) {
+    if (BR && gather) {
+      // hard codes at a leaf: K L is column k of K_b (its row sum for an unobserved site)
+      const double* Kb = Kmat + (size_t)b * S * S;
+#pragma unroll
+      for (int j = 0; j < kNT; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = __shfl_sync(0xffffffffu, kcur, 8 * j + 2 * t + h);
+#pragma unroll
+          for (int i = 0; i < MT; ++i) {
+            const int r = 8 * i + g;
+            kl[BR ? i : 0][j][h] = (r >= S) ? 0.0
+                                   : (k == RT_MISSING) ? krs_s[r]
+                                   : ((k >= 0 && k < S) ? __ldg(&Kb[r * S + k]) : 0.0);
+          }
+          xs[j][h] = 0.0;
+        }
+    } else if (BR) {
       const double* Kb = Kmat + (size_t)b * S * S;
 #pragma unroll
       for (int i = 0; i < MT; ++i)
@@ -364,7 +388,7 @@ int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edg
   int64_t gr = (n_sites + 255) / 256;
   root_distn_generic_kernel<<<(int)(gr < 1184 ? gr : 1184), 256, sizeof(double) * S, stream>>>(
       S, n_sites, stride, root_distn, partials, status, node_distn, root_post_sum);
-  const size_t smem = sizeof(double) * ((size_t)SP * LDP + 2 * (size_t)kWarps * SP * kLd + SP);
+  const size_t smem = sizeof(double) * ((size_t)SP * LDP + 2 * (size_t)kWarps * SP * kLd + 2 * SP);
   const int4* edges = reinterpret_cast<const int4*>(edges_dev);
   const unsigned gx = (unsigned)((n_sites + kTilesPerCta * kTileSites - 1) / (kTilesPerCta * kTileSites));
 #define RT_LAUNCH(OBSK)                                                                           \
