@@ -425,7 +425,7 @@ def run_gpu(args):
                                    % (n_sample, per_site, n_edges / per_site))
 
     if rank == 0:
-        launches_per_step = 2 + 1 + 1 + 3    # expm (2), up, down walk, Frechet contraction (3)
+        launches_per_step = 2 + 1 + 1 + 4    # expm (2), up, down walk, Frechet contraction (3) + edge accumulation (1)
         line = dict(
             metric='site_edge_messages_per_sec', value=value, unit='messages/s', n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,

@@ -72,6 +72,18 @@ int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t
                         const double* W, int n_mat, int S, double* M, void* stream);
 
 /*
+ * rt_frechet_contract followed by the accumulation over edges, in one call:
+ *   M[m] as above for m in [0, n_mat), M[m] = 0 for m < first (the root slot has no edge);
+ *   dwell[c]    = sum_{m >= first} M[m][c][c]                         (double [S])
+ *   trans[c][d] = sum_{m >= first} Q[q_index[m]][c][d] * M[m][c][d]   (c != d; 0 on the diagonal; [S][S])
+ * Replaces the loop over edges of _mjp_dense.get_expected_history_statistics
+ * (raoteh/sampler/_mjp_dense.py:497-533: dwell times :521-526, transition counts :527-533).
+ */
+int rt_history_statistics(const double* Q, const int32_t* q_index, const double* t,
+                          const double* W, int n_mat, int first, int S, double* M,
+                          double* dwell, double* trans, void* stream);
+
+/*
  * Structural support of every node for every site (integer work):
  * backward pass (state kept iff every child has a reachable kept state) then
  * forward pass (state kept iff reachable from a kept parent state).

@@ -37,6 +37,8 @@ static int unsupported(const char* msg) {
 int rt_expm_batched_impl(const double*, const int32_t*, const double*, int, int, double*, cudaStream_t);
 int rt_frechet_contract_impl(const double*, const int32_t*, const double*, const double*, int, int,
                              double*, cudaStream_t);
+int rt_history_statistics_impl(const double*, const int32_t*, const double*, const double*, int, int, int,
+                               double*, double*, double*, cudaStream_t);
 int rt_support_sets_impl(int, int, int64_t, int64_t, int, const int32_t*, const double*, uint64_t*, cudaStream_t);
 int rt_joint_distn_impl(int, int, int64_t, int64_t, const int32_t*, int, const double*, const void*,
                         const double*, const double*, const int8_t*, double*, double*, cudaStream_t);
@@ -82,6 +84,17 @@ int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t
   if (S < 1 || S > 64) return unsupported("rt_frechet_contract needs 1 <= S <= 64");
   ensure_pool_cached();
   return rt_frechet_contract_impl(Q, q_index, t, W, n_mat, S, M, (cudaStream_t)stream);
+}
+
+int rt_history_statistics(const double* Q, const int32_t* q_index, const double* t, const double* W,
+                          int n_mat, int first, int S, double* M, double* dwell, double* trans,
+                          void* stream) {
+  if (!Q || !t || !W || !M || !dwell || !trans) return arg_error("null pointer");
+  if (S < 1 || S > 64) return unsupported("rt_history_statistics needs 1 <= S <= 64");
+  if (first < 0 || first > n_mat) return arg_error("first out of range");
+  ensure_pool_cached();
+  return rt_history_statistics_impl(Q, q_index, t, W, n_mat, first, S, M, dwell, trans,
+                                    (cudaStream_t)stream);
 }
 
 int rt_support_sets(int S, int n_nodes, int64_t n_sites, int64_t site_stride, int passes,

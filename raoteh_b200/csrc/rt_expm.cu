@@ -425,6 +425,31 @@ __global__ void extract_frechet_kernel(const double* __restrict__ blk, const dou
   }
 }
 
+// dwell[c] = sum_{m >= m0} M[m][c][c];  trans[c][d] = sum_{m >= m0} Q_m[c][d] * M[m][c][d] (c != d, 0 on the
+// diagonal).  One CTA per entry (c, d), threads stride over the matrices.
+// raoteh/sampler/_mjp_dense.py:521-533 (the accumulation over edges).
+__global__ void __launch_bounds__(128)
+history_stats_kernel(const double* __restrict__ Q, const int32_t* __restrict__ q_index,
+                     const double* __restrict__ M, int n_mat, int m0, int S,
+                     double* __restrict__ dwell, double* __restrict__ trans) {
+  __shared__ double red[4];
+  const int idx = blockIdx.x, c = idx / S, d = idx % S;
+  double acc = 0.0;
+  for (int m = m0 + threadIdx.x; m < n_mat; m += blockDim.x) {
+    const double v = M[(size_t)m * S * S + idx];
+    acc += (c == d) ? v : Q[(size_t)(q_index ? q_index[m] : 0) * S * S + idx] * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double tot = red[0] + red[1] + red[2] + red[3];
+    if (c == d) { dwell[c] = tot; trans[idx] = 0.0; }
+    else trans[idx] = tot;
+  }
+}
+
 }  // namespace
 
 // P[m] = expm(Q[q_index[m]] * t[m]) for m in [0, n_mat)
@@ -460,5 +485,16 @@ int rt_frechet_contract_impl(const double* Q, const int32_t* q_index, const doub
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(buf, stream);
   RT_CUDA_CHECK(e);
+  return RT_OK;
+}
+
+int rt_history_statistics_impl(const double* Q, const int32_t* q_index, const double* t,
+                               const double* W, int n_mat, int first, int S, double* M,
+                               double* dwell, double* trans, cudaStream_t stream) {
+  int rc = rt_frechet_contract_impl(Q, q_index, t, W, n_mat, S, M, stream);
+  if (rc != RT_OK) return rc;
+  if (first > 0) RT_CUDA_CHECK(cudaMemsetAsync(M, 0, sizeof(double) * (size_t)first * S * S, stream));
+  history_stats_kernel<<<S * S, 128, 0, stream>>>(Q, q_index, M, n_mat, first, S, dwell, trans);
+  RT_CUDA_CHECK(cudaGetLastError());
   return RT_OK;
 }

@@ -503,15 +503,23 @@ class TreeMJP(object):
                 out_status[lo:hi].copy_(status[lo:hi], non_blocking=True)
         for cs in self._compute_streams:
             cur.wait_stream(cs)
-        M = self.frechet_contract(W)
-        M[0].zero_()
-        if getattr(self, '_offdiag', None) is None:
-            self._offdiag = 1.0 - torch.eye(S, dtype=torch.float64, device=dev)
-        Qe = self.Q[0].expand(n, S, S) if self.q_index is None else self.Q[self.q_index.long()]
-        dwell = torch.diagonal(M, dim1=1, dim2=2).sum(dim=0)
-        trans = (Qe * self._offdiag * M).sum(dim=0)
+        M, dwell, trans = self.history_statistics(W)
         cur.wait_stream(s_out)
         return dict(loglik_sum=llsum[0], dwell=dwell, trans=trans, root_post_sum=rps, M_edges=M)
+
+    def history_statistics(self, W):
+        """(M_edges, dwell, trans) from the per-edge weights W: one Frechet contraction per edge
+        and the accumulation over edges, one library call (rt_history_statistics;
+        raoteh/sampler/_mjp_dense.py:497-533)."""
+        n, S = self.sched.n, self.S
+        M = self._buf('M', (n, S, S), torch.float64)
+        dwell = torch.empty(S, dtype=torch.float64, device=self.device)
+        trans = torch.empty((S, S), dtype=torch.float64, device=self.device)
+        rc = _native.lib().rt_history_statistics(_ptr(self.Q), _ptr(self.q_index), _ptr(self.length),
+                                                 _ptr(W), n, 1, S, _ptr(M), _ptr(dwell), _ptr(trans),
+                                                 _stream())
+        _native.check(rc, 'rt_history_statistics')
+        return M, dwell, trans
 
     def frechet_contract(self, W):
         """M[b] = L(t_b Q_b^T, t_b W[b]) for every node b (slot 0 -> 0)."""
@@ -530,16 +538,11 @@ class TreeMJP(object):
         edges (raoteh/sampler/_mjp_dense.py:497-533 with one Frechet derivative per
         edge, the form of examples/code2x3/extras.py:108-129)."""
         post = self.posterior(obs, want_node_distn=want_node_distn, overlap_chunks=overlap_chunks)
-        M = self.frechet_contract(post['W'])
-        M[0].zero_()
+        M, dwell, trans = self.history_statistics(post['W'])
         S = self.S
         if self.q_index is None:
             Qe = self.Q[0].expand(self.sched.n, S, S)
         else:
             Qe = self.Q[self.q_index.long()]
-        if getattr(self, '_offdiag', None) is None:
-            self._offdiag = 1.0 - torch.eye(S, dtype=torch.float64, device=self.device)
-        dwell = torch.diagonal(M, dim1=1, dim2=2).sum(dim=0)
-        trans = (Qe * self._offdiag * M).sum(dim=0)
         post.update(dwell=dwell, trans=trans, M_edges=M, Q_edges=Qe)
         return post
