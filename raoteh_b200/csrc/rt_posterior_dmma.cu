@@ -72,7 +72,8 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // BR: a fourth contraction kl = K_b L_b and, per site, x = sum_a G_a kl_a: the posterior
 // expectation on this branch of the statistic with per-edge kernel K (e.g. expected number of
 // synonymous / non-synonymous substitutions, examples/code2x3/extras.py:19-132,
-// examples/p53/liwen-branch-expectation.py:176-356).  K is read through L1 (no shared memory left).
+// examples/p53/liwen-branch-expectation.py:176-356).  K_b is staged per tile into the G region,
+// which is idle between the W contraction of one tile and the G phase of the next.
 //
 // Latency hiding (ncu, profiles/r1_ncu_full_summary.json: the first version spent 34 % of its
 // warp samples on the scoreboard of the D_a and L_b loads): the D_a values of a tile are loaded
@@ -167,6 +168,15 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
     if (tile0 >= n_sites) break;
     const int64_t site0 = tile0 + warp * kWarpSites;
 
+    if (BR && !gather) {
+      // the G region is idle until the G tiles of this tile are written (the previous tile's W
+      // phase ended with a block barrier): it holds K_b, padded like P_b, for the fourth contraction
+      const double* Kb = Kmat + (size_t)b * S * S;
+      for (int idx = tid; idx < SP * LDP; idx += kThreads) {
+        const int r = idx / LDP, c = idx % LDP;
+        Gall[idx] = (r < S && c < S) ? __ldg(&Kb[r * S + c]) : 0.0;
+      }
+    }
     // ---- stage the prefetched L_b^T tile of this warp: [SP][16 sites] ----------------------
     const int kcur = live_pre ? kpre : -1;          // code of site column sc (gather edges)
     {
@@ -259,7 +269,9 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
           xs[j][h] = 0.0;
         }
     } else if (BR) {
-      const double* Kb = Kmat + (size_t)b * S * S;
+      // K_b was staged into the (idle) G region at the top of the tile; every warp reads all of it
+      const double* Ks = Gall;
+      __syncthreads();
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -271,14 +283,14 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
         for (int j = 0; j < kNT; ++j) bf[j] = Lw[(4 * kk + t) * kLd + 8 * j + g];
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
-          const int r = 8 * i + g, cc = 4 * kk + t;
-          const double a = (r < S && cc < S) ? __ldg(&Kb[r * S + cc]) : 0.0;
+          const double a = Ks[(8 * i + g) * LDP + 4 * kk + t];
 #pragma unroll
           for (int j = 0; j < kNT; ++j) dmma884(kl[BR ? i : 0][j][0], kl[BR ? i : 0][j][1], a, bf[j]);
         }
       }
 #pragma unroll
       for (int j = 0; j < kNT; ++j) xs[j][0] = xs[j][1] = 0.0;
+      __syncthreads();      // all warps are done with K_b before the G tiles overwrite it
     }
     // ---- G = D_a / m (0 where D_a == 0), written to the warp's G tile ---------------
 #pragma unroll
