@@ -61,6 +61,16 @@ int rt_expm_batched(const double* Q, const int32_t* q_index, const double* t,
                     int n_mat, int S, double* P, void* stream);
 
 /*
+ * P[m] = A diag(exp(t[m] * lam)) B for m in [0, n_mat): transition matrices of a time-reversible
+ * rate matrix from its spectral decomposition (A, lam, B double [S][S], [S], [S][S]; S <= 64),
+ * d_off (nullable, uint8 [S]): states whose diagonal entry is forced to 1.
+ * Replaces getp_spectral_v2 / reconstruct_spectral_v2 called once per branch
+ * (examples/p53/qtop.py:76-85, 283-288; decomposition qtop.py:126-148 stays on the host).
+ */
+int rt_expm_spectral(const double* A, const double* lam, const double* B, const double* t,
+                     const uint8_t* d_off, int n_mat, int S, double* P, void* stream);
+
+/*
  * M[m] = L(t[m] Q^T, t[m] W[m]) -- Frechet derivative of expm; equals
  * sum_ab W[m][a][b] * expm_frechet(tQ, t E_cd)[a][b] at entry [c][d].  (S <= 64)
  * Replaces the S + nnz(Q) scipy.linalg.expm_frechet calls per edge per site at

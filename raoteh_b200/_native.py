@@ -22,6 +22,8 @@ EXPORTS = {
     'rt_expm_batched': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
     'rt_frechet_contract': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                              c_void_p], c_int),
+    'rt_expm_spectral': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                          c_void_p], c_int),
     'rt_history_statistics': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p], c_int),
     'rt_support_sets': ([c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,

@@ -39,6 +39,8 @@ int rt_frechet_contract_impl(const double*, const int32_t*, const double*, const
                              double*, cudaStream_t);
 int rt_history_statistics_impl(const double*, const int32_t*, const double*, const double*, int, int, int,
                                double*, double*, double*, cudaStream_t);
+int rt_expm_spectral_impl(const double*, const double*, const double*, const double*, const uint8_t*,
+                          int, int, double*, cudaStream_t);
 int rt_support_sets_impl(int, int, int64_t, int64_t, int, const int32_t*, const double*, uint64_t*, cudaStream_t);
 int rt_joint_distn_impl(int, int, int64_t, int64_t, const int32_t*, int, const double*, const void*,
                         const double*, const double*, const int8_t*, double*, double*, cudaStream_t);
@@ -84,6 +86,13 @@ int rt_frechet_contract(const double* Q, const int32_t* q_index, const double* t
   if (S < 1 || S > 64) return unsupported("rt_frechet_contract needs 1 <= S <= 64");
   ensure_pool_cached();
   return rt_frechet_contract_impl(Q, q_index, t, W, n_mat, S, M, (cudaStream_t)stream);
+}
+
+int rt_expm_spectral(const double* A, const double* lam, const double* B, const double* t,
+                     const uint8_t* d_off, int n_mat, int S, double* P, void* stream) {
+  if (!A || !lam || !B || !t || !P) return arg_error("null pointer");
+  if (S < 1 || S > 64) return unsupported("rt_expm_spectral needs 1 <= S <= 64");
+  return rt_expm_spectral_impl(A, lam, B, t, d_off, n_mat, S, P, (cudaStream_t)stream);
 }
 
 int rt_history_statistics(const double* Q, const int32_t* q_index, const double* t, const double* W,

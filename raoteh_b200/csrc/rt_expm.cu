@@ -450,7 +450,47 @@ history_stats_kernel(const double* __restrict__ Q, const int32_t* __restrict__ q
   }
 }
 
+// P[m] = A diag(exp(t[m] * lam)) B for every edge m: the spectral form of a time-reversible rate
+// matrix Q = S diag(D), A = diag(D^-1/2) U, B = U^T diag(D^1/2), (lam, U) = eigh(D^1/2 S D^1/2)
+// (examples/p53/qtop.py:76-85 getp_spectral_v2, :283-288 reconstruct_spectral_v2).  One CTA per
+// edge; A scaled by the exponentials and B live in shared memory, a thread owns output entries.
+// d_off[i] != 0 marks states with D[i] == 0, whose diagonal entry is set to 1 (qtop.py:83-84).
+__global__ void __launch_bounds__(256)
+expm_spectral_kernel(const double* __restrict__ A, const double* __restrict__ lam,
+                     const double* __restrict__ B, const double* __restrict__ t,
+                     const uint8_t* __restrict__ d_off, int S, double* __restrict__ P) {
+  extern __shared__ double sms[];
+  double* As = sms;                 // [S][S+1]  A[i][k] * exp(t lam_k)
+  double* Bs = As + S * (S + 1);    // [S][S]
+  const int m = blockIdx.x;
+  const double tm = t[m];
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, k = idx % S;
+    As[i * (S + 1) + k] = A[idx] * exp(tm * lam[k]);
+    Bs[idx] = B[idx];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int i = idx / S, j = idx % S;
+    double acc = 0.0;
+    for (int k = 0; k < S; ++k) acc = fma(As[i * (S + 1) + k], Bs[k * S + j], acc);
+    if (d_off && i == j && d_off[i]) acc = 1.0;
+    P[(size_t)m * S * S + idx] = acc;
+  }
+}
+
 }  // namespace
+
+int rt_expm_spectral_impl(const double* A, const double* lam, const double* B, const double* t,
+                          const uint8_t* d_off, int n_mat, int S, double* P, cudaStream_t stream) {
+  if (n_mat <= 0) return RT_OK;
+  const size_t smem = sizeof(double) * ((size_t)S * (S + 1) + (size_t)S * S);
+  if (smem > 48 * 1024)
+    RT_CUDA_CHECK(cudaFuncSetAttribute(expm_spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  expm_spectral_kernel<<<n_mat, 256, smem, stream>>>(A, lam, B, t, d_off, S, P);
+  RT_CUDA_CHECK(cudaGetLastError());
+  return RT_OK;
+}
 
 // P[m] = expm(Q[q_index[m]] * t[m]) for m in [0, n_mat)
 int rt_expm_batched_impl(const double* Q, const int32_t* q_index, const double* t, int n_mat, int S,

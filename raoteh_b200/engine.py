@@ -170,6 +170,29 @@ class TreeMJP(object):
         self.Q_host = Q
         self._P_valid = False
 
+    def use_spectral(self, D):
+        """Switch P(t) to the spectral scheme of examples/p53/qtop.py:76-85 for a time-reversible
+        rate matrix with stationary weights `D` (one shared rate matrix only): the symmetric
+        eigenproblem is solved on the host whenever the rate matrix changes, the reconstruction
+        for all branches is one `rt_expm_spectral` call.  `D=None` goes back to Pade."""
+        if D is not None and (self.q_index is not None or self.Q.shape[0] != 1):
+            raise ValueError('the spectral scheme needs one shared rate matrix')
+        self._spectral_D = None if D is None else np.asarray(D, dtype=np.float64)
+        self._P_valid = False
+
+    def _spectral_matrices(self):
+        from . import qtop
+        S, n = self.S, self.sched.n
+        D = self._spectral_D
+        A, lam, B = qtop.decompose_spectral_v2(qtop.symmetric_factor(self.Q_host[0], D), D)
+        stage = np.concatenate([A.ravel(), lam, B.ravel()])
+        dec = torch.from_numpy(stage).to(self.device)
+        off = torch.from_numpy((D == 0).astype(np.uint8)).to(self.device)
+        a, l, b = dec[:S * S], dec[S * S:S * S + S], dec[S * S + S:]
+        rc = _native.lib().rt_expm_spectral(_ptr(a), _ptr(l), _ptr(b), _ptr(self.length), _ptr(off),
+                                            n, S, _ptr(self._P), _stream())
+        _native.check(rc, 'rt_expm_spectral')
+
     # ---- K1 ---------------------------------------------------------------
     def transition_matrices(self):
         """P[b] = expm(Q_b t_b) for every node b (slot 0 = identity); cached."""
@@ -177,9 +200,12 @@ class TreeMJP(object):
             n, S = self.sched.n, self.S
             if self._P is None:
                 self._P = torch.empty((n, S, S), dtype=torch.float64, device=self.device)
-            rc = _native.lib().rt_expm_batched(_ptr(self.Q), _ptr(self.q_index), _ptr(self.length),
-                                               n, S, _ptr(self._P), _stream())
-            _native.check(rc, 'rt_expm_batched')
+            if getattr(self, '_spectral_D', None) is not None:
+                self._spectral_matrices()
+            else:
+                rc = _native.lib().rt_expm_batched(_ptr(self.Q), _ptr(self.q_index), _ptr(self.length),
+                                                   n, S, _ptr(self._P), _stream())
+                _native.check(rc, 'rt_expm_batched')
             self._P_valid = True
         return self._P
 

@@ -1,0 +1,101 @@
+"""Spectral P(t) scheme: host mirror of examples/p53/qtop.py (CPU tests, the
+reference's own round-trip / expm tests qtop.py:437-475, 562-610 ported) and the batched device
+reconstruction rt_expm_spectral (GPU tests)."""
+import numpy as np
+import pytest
+import scipy.linalg
+
+from raoteh_b200 import qtop
+
+
+def random_reversible_rate_matrix(n, rng, off_states=()):
+    """qtop.py:340-372 (random symmetric rates, random stationary weights, rows sum to zero)."""
+    S = np.square(rng.standard_normal((n, n)))
+    S = S + S.T
+    np.fill_diagonal(S, 0)
+    D = np.square(rng.standard_normal(n)) + 0.05
+    off = list(off_states)
+    S[off, :] = 0
+    S[:, off] = 0
+    D[off] = 0
+    D /= D.sum()
+    pre_Q = S * D[None, :]
+    Q = pre_Q - np.diag(pre_Q.sum(axis=1))
+    return Q, Q * qtop.pseudo_reciprocal(D)[None, :], D
+
+
+@pytest.mark.parametrize('n', [4, 7, 20])
+def test_spectral_v2_round_trip_and_expm(n):
+    rng = np.random.default_rng(1234 + n)
+    Q, S, D = random_reversible_rate_matrix(n, rng)
+    np.testing.assert_allclose(S, S.T, atol=1e-12)
+    np.testing.assert_allclose(S * D[None, :], Q, atol=1e-14)
+    A, lam, B = qtop.decompose_spectral_v2(S, D)
+    np.testing.assert_allclose(qtop.reconstruct_spectral_v2(A, lam, B), Q, atol=1e-12)
+    for t in (0.0, 0.23, 3.0):
+        P = qtop.reconstruct_spectral_v2(A, np.exp(t * lam), B)
+        np.testing.assert_allclose(P, scipy.linalg.expm(Q * t), atol=1e-13)
+    np.testing.assert_allclose(qtop.symmetric_factor(Q, D), S, atol=1e-14)
+
+
+def test_symmetric_factor_rejects_irreversible_matrices():
+    rng = np.random.default_rng(5)
+    Q = rng.exponential(1.0, size=(5, 5))
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    with pytest.raises(ValueError):
+        qtop.symmetric_factor(Q, np.full(5, 0.2))
+
+
+def test_hky_and_mg94_are_reversible_with_respect_to_their_root_distribution():
+    from raoteh_b200 import synth
+    cfg = synth.config_c2(n_sites=8)
+    qtop.symmetric_factor(cfg['Q'], cfg['pi'])
+    Q, pi, _ = synth.mg94()
+    A, lam, B = qtop.decompose_spectral_v2(qtop.symmetric_factor(Q, pi), pi)
+    np.testing.assert_allclose(qtop.reconstruct_spectral_v2(A, np.exp(0.3 * lam), B),
+                               scipy.linalg.expm(0.3 * Q), atol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,off', [(4, ()), (5, (0, 2)), (20, ()), (61, ())])
+def test_rt_expm_spectral_matches_expm(n, off):
+    """getp_spectral_v2 for a vector of branch lengths vs scipy.linalg.expm (and, for states with
+    D == 0, the forced unit diagonal of qtop.py:83-84)."""
+    rng = np.random.default_rng(99 + n)
+    if n == 61:
+        from raoteh_b200 import synth
+        Q, D, _ = synth.mg94()
+        S = qtop.symmetric_factor(Q, D)
+    else:
+        Q, S, D = random_reversible_rate_matrix(n, rng, off)
+    A, lam, B = qtop.decompose_spectral_v2(S, D)
+    t = np.concatenate([[0.0], rng.exponential(0.3, size=40), [5.0]])
+    P = qtop.getp_spectral_v2(D, A, lam, B, t).cpu().numpy()
+    for i, ti in enumerate(t):
+        want = scipy.linalg.expm(Q * ti)
+        want[np.asarray(D) == 0, np.asarray(D) == 0] = 1
+        np.testing.assert_allclose(P[i], want, rtol=1e-10, atol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('S', [4, 61])
+def test_tree_likelihood_with_spectral_scheme_matches_pade(S):
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    cfg = synth.config_c2(n_sites=3000, n_leaves=16) if S == 4 else synth.config_c3(n_sites=700)
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    mjp = engine.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'])
+    obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'])
+    ref = mjp.expected_history_statistics(obs)
+    ref = {k: ref[k].clone() for k in ('loglik', 'dwell', 'trans')}
+    P_pade = mjp.transition_matrices().clone()
+    mjp.use_spectral(cfg['pi'])
+    P_spec = mjp.transition_matrices()
+    np.testing.assert_allclose(P_spec[1:].cpu().numpy(), P_pade[1:].cpu().numpy(), rtol=1e-9, atol=1e-13)
+    got = mjp.expected_history_statistics(obs)
+    np.testing.assert_allclose(got['loglik'].cpu().numpy(), ref['loglik'].cpu().numpy(), rtol=1e-10)
+    np.testing.assert_allclose(got['dwell'].cpu().numpy(), ref['dwell'].cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(got['trans'].cpu().numpy(), ref['trans'].cpu().numpy(), rtol=1e-9, atol=1e-12)
+    mjp.use_spectral(None)
+    np.testing.assert_allclose(mjp.transition_matrices().cpu().numpy(), P_pade.cpu().numpy(), rtol=0, atol=0)
