@@ -81,8 +81,10 @@ struct SweepArgs {
   int8_t* status;        // [stride]
 };
 
+// S <= 4: 80 registers, 6 CTAs per SM (the shared-memory limit): the kernel is latency bound and
+// 24 warps per SM beat 16 by 9 % at C4 (profiles/r1_raoteh_occupancy.log; 5 CTAs: no gain)
 template <int S, int OBS, bool STATS>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, (S <= 4 ? 6 : 4))
 raoteh_kernel(SweepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
