@@ -50,6 +50,16 @@ int rt_version(void);
 const char* rt_last_error_string(void);
 
 /*
+ * Per-call workspaces (expm scratch, Rao-Teh event records, ...) come from a PRIVATE
+ * stream-ordered memory pool per device, created on first use; the device's default pool and
+ * its attributes are never touched.  Freed workspaces stay cached in that pool between calls.
+ * rt_release_workspace() synchronises the device and returns the cached memory to the driver.
+ * Largest workspace: rt_raoteh_sweeps, min(n_traj, 2^19) x cap x (8 S + 16) bytes (trajectories
+ * are processed in launches of 2^19); rt_tmjp_run sizes its scratch by resident warps.
+ */
+int rt_release_workspace(void);
+
+/*
  * P[m] = expm(Q[q_index[m]] * t[m]),  m = 0..n_mat-1   (S <= 128)
  * Q: [n_q][S][S] row-major with diagonal; q_index: [n_mat] or NULL (all use Q[0]).
  * Replaces scipy.linalg.expm called once per edge PER SITE at
@@ -244,6 +254,44 @@ int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, in
                      int init_k, double* dwell_sum, double* trans_sum, int8_t* status,
                      void* stream);
 
+/*
+ * The same sweeps with the arguments in a struct, plus two options:
+ *   time_f64    : every event time, branch position and Poisson hazard in fp64, the arithmetic of
+ *                 the reference (raoteh/sampler/_sample_mjp.py:47-69 draws the event times with
+ *                 numpy's fp64 exponentials); ev_time is then double [traj_stride][cap]
+ *                 (S in {2,3,4,5,6,8}).  With 0, ev_time is float [traj_stride][cap] (half the
+ *                 jump-list bytes).  Both consume the same Philox words in the same order.
+ *   sweep_count : nullable int32 [traj_stride], the number of sweeps every trajectory has
+ *                 completed.  When given, trajectory t runs sweeps sweep_count[t] .. sweep0 +
+ *                 n_sweeps - 1 (Philox counter = its own sweep index) and the count is written
+ *                 back, so a trajectory that stopped early (status 3, event capacity) can be
+ *                 continued by repeating the call after growing `cap` and clearing its status:
+ *                 every (trajectory, sweep) contributes to dwell_sum / trans_sum exactly once.
+ */
+typedef struct rt_raoteh_args {
+  int32_t S, n_nodes, n_ops, n_slots, obs_kind, cap, n_sweeps, init_k;
+  int32_t time_f64, reserved;
+  int64_t n_traj, traj_stride, n_sites, traj0, obs_stride, sweep0;
+  uint64_t seed;
+  const int32_t* program;
+  const int32_t* parent;
+  const double* length;
+  const double* B;
+  const double* rate;
+  const double* root_distn;
+  const void* obs;
+  uint8_t* node_state;
+  void* ev_time;
+  uint8_t* ev_sb;
+  uint8_t* ev_count;
+  int32_t* ev_total;
+  int32_t* sweep_count;
+  double* dwell_sum;
+  double* trans_sum;
+  int8_t* status;
+} rt_raoteh_args;
+
+int rt_raoteh_run(const rt_raoteh_args* args, void* stream);
 
 /*
  * Warp-cooperative Rao-Teh kernels: one warp per (chain, site) trajectory.

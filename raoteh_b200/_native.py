@@ -18,6 +18,7 @@ c_int64 = ctypes.c_int64
 
 EXPORTS = {
     'rt_version': ([], c_int),
+    'rt_release_workspace': ([], c_int),
     'rt_last_error_string': ([], ctypes.c_char_p),
     'rt_expm_batched': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
     'rt_frechet_contract': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
@@ -48,6 +49,27 @@ EXPORTS = {
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, ctypes.c_uint64,
                           c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
 }
+
+
+class RaotehArgs(ctypes.Structure):
+    """Mirror of `rt_raoteh_args` (include/rt_b200.h)."""
+    _fields_ = [
+        ('S', ctypes.c_int32), ('n_nodes', ctypes.c_int32), ('n_ops', ctypes.c_int32),
+        ('n_slots', ctypes.c_int32), ('obs_kind', ctypes.c_int32), ('cap', ctypes.c_int32),
+        ('n_sweeps', ctypes.c_int32), ('init_k', ctypes.c_int32),
+        ('time_f64', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('n_traj', c_int64), ('traj_stride', c_int64), ('n_sites', c_int64), ('traj0', c_int64),
+        ('obs_stride', c_int64), ('sweep0', c_int64),
+        ('seed', ctypes.c_uint64),
+        ('program', c_void_p), ('parent', c_void_p), ('length', c_void_p), ('B', c_void_p),
+        ('rate', c_void_p), ('root_distn', c_void_p), ('obs', c_void_p),
+        ('node_state', c_void_p), ('ev_time', c_void_p), ('ev_sb', c_void_p),
+        ('ev_count', c_void_p), ('ev_total', c_void_p), ('sweep_count', c_void_p),
+        ('dwell_sum', c_void_p), ('trans_sum', c_void_p), ('status', c_void_p),
+    ]
+
+
+EXPORTS['rt_raoteh_run'] = ([ctypes.POINTER(RaotehArgs), c_void_p], c_int)
 
 
 class TmjpArgs(ctypes.Structure):

@@ -9,20 +9,42 @@ static thread_local char g_err[512] = "";
 void rt_set_last_error(cudaError_t e, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
 }
-// Workspaces come from the device's default stream-ordered pool (cudaMallocAsync).
-// Keep freed blocks cached in the pool instead of returning them to the OS at
-// every synchronisation (default threshold 0), once per device.
-static void ensure_pool_cached() {
-  static thread_local int done_for = -1;
+// Workspaces come from a private stream-ordered pool per device (cudaMemPoolCreate), so the
+// library never touches the attributes of the device's default pool.  Freed blocks stay cached
+// in the pool (release threshold = max) until rt_release_workspace() trims it; the largest
+// per-call workspaces are bounded by the dispatchers (rt_raoteh.cu launches in trajectory
+// chunks, rt_tmjp.cu sizes its scratch by resident warps, not by trajectories).
+static cudaMemPool_t g_pool[64] = {};
+static cudaError_t ws_pool(cudaMemPool_t* out) {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!g_pool[dev]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    e = cudaMemPoolCreate(&pool, &props);
+    if (e != cudaSuccess) return e;
     unsigned long long thr = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    g_pool[dev] = pool;
   }
-  done_for = dev;
+  *out = g_pool[dev];
+  return cudaSuccess;
 }
+cudaError_t rt_ws_alloc(void** p, size_t bytes, cudaStream_t stream) {
+  cudaMemPool_t pool;
+  cudaError_t e = ws_pool(&pool);
+  if (e != cudaSuccess) return e;
+  return cudaMallocFromPoolAsync(p, bytes, pool, stream);
+}
+cudaError_t rt_ws_free(void* p, cudaStream_t stream) { return cudaFreeAsync(p, stream); }
+static void ensure_pool_cached() {}
 
 static int arg_error(const char* msg) {
   snprintf(g_err, sizeof(g_err), "argument error: %s", msg);
@@ -60,16 +82,23 @@ int rt_posterior_dmma_dispatch(int, int, int64_t, int64_t, const int32_t*, const
                                const int8_t*, double*, double*, double*, const double*, double*,
                                cudaStream_t);
 
-int rt_raoteh_dispatch(int, int, int, int64_t, int64_t, int64_t, int64_t, const int32_t*, int, int,
-                       const int32_t*, const double*, const double*, const double*, const double*,
-                       const void*, int64_t, uint8_t*, float*, uint8_t*, uint8_t*, int32_t*, int,
-                       uint64_t, int64_t, int, int, double*, double*, int8_t*, cudaStream_t);
+int rt_raoteh_dispatch(const rt_raoteh_args&, cudaStream_t);
 
 int rt_tmjp_dispatch(const rt_tmjp_args&, cudaStream_t);
 
 extern "C" {
 
-int rt_version(void) { return 100; }
+int rt_version(void) { return 200; }
+
+int rt_release_workspace(void) {
+  int dev = 0;
+  RT_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && g_pool[dev]) {
+    RT_CUDA_CHECK(cudaDeviceSynchronize());
+    RT_CUDA_CHECK(cudaMemPoolTrimTo(g_pool[dev], 0));
+  }
+  return RT_OK;
+}
 const char* rt_last_error_string(void) { return g_err; }
 
 int rt_expm_batched(const double* Q, const int32_t* q_index, const double* t, int n_mat, int S,
@@ -220,6 +249,50 @@ int rt_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pit
   return RT_OK;
 }
 
+}  // extern "C"
+
+static int raoteh_run_impl(const rt_raoteh_args& R, void* stream) {
+  if (!R.program || !R.parent || !R.length || !R.B || !R.rate || !R.obs || !R.node_state ||
+      !R.ev_time || !R.ev_sb || !R.ev_count || !R.ev_total || !R.status)
+    return arg_error("null pointer");
+  if (R.obs_kind != 0 && R.obs_kind != 1) return arg_error("rt_raoteh_sweeps takes codes or masks");
+  if (R.traj_stride < R.n_traj || R.n_sites <= 0 || R.cap <= 0) return arg_error("sizes");
+  if (R.n_traj <= 0) return RT_OK;
+  const int S = R.S;
+  if ((S > 8 || S == 7) && S <= 64) {
+    if (R.time_f64) return unsupported("fp64 event times: S in {2,3,4,5,6,8} only");
+    if (R.sweep_count) return unsupported("sweep_count: S in {2,3,4,5,6,8} only");
+    // warp-per-trajectory kernel (csrc/rt_tmjp.cu) on the same trajectory layout
+    rt_tmjp_args A;
+    memset(&A, 0, sizeof(A));
+    A.S = S; A.n_parts = 0; A.n_nodes = R.n_nodes; A.n_ops = R.n_ops; A.n_slots = R.n_slots;
+    A.cap_p = R.cap; A.cap_t = 1; A.obs_kind = R.obs_kind;
+    A.program = R.program; A.parent = R.parent; A.length = R.length; A.B = R.B; A.rate_p = R.rate;
+    A.pi_p = R.root_distn; A.obs = R.obs; A.obs_stride = R.obs_stride;
+    A.n_traj = R.n_traj; A.n_sites = R.n_sites; A.traj0 = R.traj0;
+    A.p_node = R.node_state; A.p_cnt = R.ev_count; A.pn_traj_stride = 1; A.pn_node_stride = R.traj_stride;
+    A.p_total = R.ev_total; A.p_time = (float*)R.ev_time; A.p_sb = R.ev_sb; A.status = R.status;
+    A.seed = R.seed; A.sweep0 = R.sweep0; A.n_sweeps = R.n_sweeps;
+    A.mode = R.init_k >= 0 ? RT_TMJP_INIT_PRIMARY : RT_TMJP_SWEEP; A.init_k = R.init_k;
+    const bool st = R.dwell_sum != nullptr && R.trans_sum != nullptr && R.init_k < 0;
+    A.flags = st ? RT_TMJP_F_STATS_PRIMARY : 0;
+    A.prim_dwell = R.dwell_sum; A.prim_trans = R.trans_sum;
+    int rc = rt_tmjp_dispatch(A, (cudaStream_t)stream);
+    if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: shared-memory budget");
+    return rc;
+  }
+  int rc = rt_raoteh_dispatch(R, (cudaStream_t)stream);
+  if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: S or shared-memory budget");
+  return rc;
+}
+
+extern "C" {
+
+int rt_raoteh_run(const rt_raoteh_args* args, void* stream) {
+  if (!args) return arg_error("null pointer");
+  return raoteh_run_impl(*args, stream);
+}
+
 int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, int64_t n_sites,
                      int64_t traj0, const int32_t* program, int n_ops, int n_slots,
                      const int32_t* parent, const double* length, const double* B,
@@ -228,40 +301,22 @@ int rt_raoteh_sweeps(int S, int n_nodes, int64_t n_traj, int64_t traj_stride, in
                      uint8_t* ev_count, int32_t* ev_total, int cap, uint64_t seed, int64_t sweep0,
                      int n_sweeps, int init_k, double* dwell_sum, double* trans_sum, int8_t* status,
                      void* stream) {
-  if (!program || !parent || !length || !B || !rate || !obs || !node_state || !ev_time || !ev_sb ||
-      !ev_count || !ev_total || !status)
-    return arg_error("null pointer");
-  if (obs_kind != 0 && obs_kind != 1) return arg_error("rt_raoteh_sweeps takes codes or masks");
-  if (traj_stride < n_traj || n_sites <= 0 || cap <= 0) return arg_error("sizes");
-  if (n_traj <= 0) return RT_OK;
-  ensure_pool_cached();
-  if ((S > 8 || S == 7) && S <= 64) {
-    // warp-per-trajectory kernel (csrc/rt_tmjp.cu) on the same trajectory layout
-    rt_tmjp_args A;
-    memset(&A, 0, sizeof(A));
-    A.S = S; A.n_parts = 0; A.n_nodes = n_nodes; A.n_ops = n_ops; A.n_slots = n_slots;
-    A.cap_p = cap; A.cap_t = 1; A.obs_kind = obs_kind;
-    A.program = program; A.parent = parent; A.length = length; A.B = B; A.rate_p = rate;
-    A.pi_p = root_distn; A.obs = obs; A.obs_stride = obs_stride;
-    A.n_traj = n_traj; A.n_sites = n_sites; A.traj0 = traj0;
-    A.p_node = node_state; A.p_cnt = ev_count; A.pn_traj_stride = 1; A.pn_node_stride = traj_stride;
-    A.p_total = ev_total; A.p_time = ev_time; A.p_sb = ev_sb; A.status = status;
-    A.seed = seed; A.sweep0 = sweep0; A.n_sweeps = n_sweeps;
-    A.mode = init_k >= 0 ? RT_TMJP_INIT_PRIMARY : RT_TMJP_SWEEP; A.init_k = init_k;
-    const bool st = dwell_sum != nullptr && trans_sum != nullptr && init_k < 0;
-    A.flags = st ? RT_TMJP_F_STATS_PRIMARY : 0;
-    A.prim_dwell = dwell_sum; A.prim_trans = trans_sum;
-    int rc = rt_tmjp_dispatch(A, (cudaStream_t)stream);
-    if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: shared-memory budget");
-    return rc;
-  }
-  int rc = rt_raoteh_dispatch(S, obs_kind, n_nodes, n_traj, traj_stride, n_sites, traj0, program,
-                              n_ops, n_slots, parent, length, B, rate, root_distn, obs, obs_stride,
-                              node_state, ev_time, ev_sb, ev_count, ev_total, cap, seed, sweep0,
-                              n_sweeps, init_k, dwell_sum, trans_sum, status, (cudaStream_t)stream);
-  if (rc == RT_ERR_UNSUPPORTED) snprintf(g_err, sizeof(g_err), "unsupported: S or shared-memory budget");
-  return rc;
+  rt_raoteh_args R;
+  memset(&R, 0, sizeof(R));
+  R.S = S; R.n_nodes = n_nodes; R.n_ops = n_ops; R.n_slots = n_slots; R.obs_kind = obs_kind;
+  R.cap = cap; R.n_sweeps = n_sweeps; R.init_k = init_k;
+  R.n_traj = n_traj; R.traj_stride = traj_stride; R.n_sites = n_sites; R.traj0 = traj0;
+  R.obs_stride = obs_stride; R.sweep0 = sweep0; R.seed = seed;
+  R.program = program; R.parent = parent; R.length = length; R.B = B; R.rate = rate;
+  R.root_distn = root_distn; R.obs = obs; R.node_state = node_state; R.ev_time = ev_time;
+  R.ev_sb = ev_sb; R.ev_count = ev_count; R.ev_total = ev_total;
+  R.dwell_sum = dwell_sum; R.trans_sum = trans_sum; R.status = status;
+  return raoteh_run_impl(R, stream);
 }
+
+}  // extern "C"
+
+extern "C" {
 
 int rt_tmjp_run(const rt_tmjp_args* a, void* stream) {
   if (!a) return arg_error("null pointer");

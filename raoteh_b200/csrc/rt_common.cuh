@@ -50,6 +50,13 @@ enum {
 
 void rt_set_last_error(cudaError_t e, const char* file, int line);
 
+// Per-call workspaces come from a PRIVATE stream-ordered pool of the current device (rt_api.cu),
+// not from the device's default pool: freed blocks stay cached in it between calls (no allocator
+// round trip per launch) without changing the behaviour of anybody else's cudaMallocAsync.
+// rt_release_workspace() (C ABI) trims it.
+cudaError_t rt_ws_alloc(void** p, size_t bytes, cudaStream_t stream);
+cudaError_t rt_ws_free(void* p, cudaStream_t stream);
+
 // exponent of a positive finite double (floor(log2 x)); 0 for x == 0
 __device__ __forceinline__ int rt_exponent(double x) {
   int hi = __double2hiint(x);

@@ -498,11 +498,11 @@ int rt_expm_batched_impl(const double* Q, const int32_t* q_index, const double* 
   if (n_mat <= 0) return RT_OK;
   if (S < 1 || S > 128) return RT_ERR_UNSUPPORTED;
   double* scratch = nullptr;
-  RT_CUDA_CHECK(cudaMallocAsync(&scratch, sizeof(double) * 7 * (size_t)S * S * n_mat, stream));
+  RT_CUDA_CHECK(rt_ws_alloc((void**)&scratch, sizeof(double) * 7 * (size_t)S * S * n_mat, stream));
   build_scaled_kernel<<<n_mat, 256, 0, stream>>>(Q, q_index, t, S, P);
   launch_expm(P, S, n_mat, scratch, stream);
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(scratch, stream);
+  rt_ws_free(scratch, stream);
   RT_CUDA_CHECK(e);
   return RT_OK;
 }
@@ -515,7 +515,7 @@ int rt_frechet_contract_impl(const double* Q, const int32_t* q_index, const doub
   const int n = 2 * S;
   double* buf = nullptr;
   const size_t nn = (size_t)n * n;
-  RT_CUDA_CHECK(cudaMallocAsync(&buf, sizeof(double) * (8 * nn + 1) * n_mat, stream));
+  RT_CUDA_CHECK(rt_ws_alloc((void**)&buf, sizeof(double) * (8 * nn + 1) * n_mat, stream));
   double* blk = buf;
   double* scratch = buf + nn * n_mat;
   double* scale = buf + 8 * nn * n_mat;
@@ -523,7 +523,7 @@ int rt_frechet_contract_impl(const double* Q, const int32_t* q_index, const doub
   launch_expm(blk, n, n_mat, scratch, stream);
   extract_frechet_kernel<<<n_mat, 256, 0, stream>>>(blk, t, scale, S, M);
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(buf, stream);
+  rt_ws_free(buf, stream);
   RT_CUDA_CHECK(e);
   return RT_OK;
 }

@@ -526,7 +526,7 @@ int rt_prune_dmma_dispatch(int S, int obs_kind, bool store, int64_t n_sites, int
                n_rs = (size_t)n_nodes * SP;
   const size_t n_slot = store ? 0 : (size_t)n_slots * S * (size_t)stride;
   constexpr size_t kArrivals = 1024;     // >= SM count, in ints (512 doubles of workspace)
-  RT_CUDA_CHECK(cudaMallocAsync(&ws, sizeof(double) * (n_pad + n_pt + n_rs + n_slot + kArrivals / 2), stream));
+  RT_CUDA_CHECK(rt_ws_alloc((void**)&ws, sizeof(double) * (n_pad + n_pt + n_rs + n_slot + kArrivals / 2), stream));
   double* Ppad = ws;
   double* PT = Ppad + n_pad;
   double* rowsum = PT + n_pt;
@@ -552,6 +552,6 @@ int rt_prune_dmma_dispatch(int S, int obs_kind, bool store, int64_t n_sites, int
     default: rc = RT_ERR_UNSUPPORTED;
   }
 #undef RT_ARGS
-  cudaFreeAsync(ws, stream);
+  rt_ws_free(ws, stream);
   return rc;
 }

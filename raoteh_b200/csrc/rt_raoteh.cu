@@ -33,6 +33,7 @@
 //        rewrite the jump lists.  This is FFBS on the implicit chunk tree.
 #include "rt_common.cuh"
 #include "rt_philox.cuh"
+#include "../../include/rt_b200.h"
 
 namespace {
 
@@ -53,9 +54,23 @@ __device__ __forceinline__ void load_obs_vec(const void* obs, int slot, int64_t 
   }
 }
 
+// TT = type of every event time, branch position and hazard: float (default; 4-byte jump
+// lists) or double (the reference's arithmetic; rt_raoteh_sweeps_f64)
+template <typename TT> struct TimeOps;
+template <> struct TimeOps<float> {
+  static __device__ __forceinline__ float neglog_unit(uint32_t u) { return -__logf(RT_U32_TO_UNIT(u)); }
+};
+template <> struct TimeOps<double> {
+  static __device__ __forceinline__ double neglog_unit(uint32_t u) {
+    return -log(((double)u + 0.5) * 2.3283064365386963e-10);
+  }
+};
+
+template <typename TT>
 struct SweepArgs {
   int n_nodes, n_ops, n_slots, cap, scr_cap;
   int64_t n_traj, stride, n_sites, obs_stride, traj0;
+  int64_t scr_stride;    // trajectories per launch chunk (row length of scr_count)
   const int4* program;
   const int32_t* parent;
   const double* length;
@@ -64,18 +79,20 @@ struct SweepArgs {
   const double* root_distn;
   const void* obs;
   uint8_t* node_state;   // [n_nodes][stride]
-  float* ev_time;        // [stride][cap]   jumps in up order, occupying [cap - total, cap)
+  TT* ev_time;           // [stride][cap]   jumps in up order, occupying [cap - total, cap)
   uint8_t* ev_sb;        // [stride][cap]   state on the parent side of the jump
   uint8_t* ev_count;     // [n_nodes][stride]
   int32_t* ev_total;     // [stride]
   // candidate events of the sweep, up order, one contiguous record per event and
-  // trajectory: [stride][scr_cap] x { float time; uint32 u; double beta[S]; } padded to 16 B
+  // trajectory of the launch chunk: [scr_stride][scr_cap] x { double beta[S]; TT time; uint32 u; }
+  // padded to 16 B
   unsigned char* scr_rec;
-  uint8_t* scr_count;    // [n_nodes][stride]
+  uint8_t* scr_count;    // [n_nodes][scr_stride]
   unsigned long long seed;
   long long sweep0;
   int n_sweeps;
   int init_k;            // >= 0: initial-history mode with init_k equally spaced events per edge
+  int32_t* sweep_count;  // nullable [stride]: sweeps completed per trajectory (see rt_raoteh_args)
   double* dwell_sum;     // [S]   += over trajectories and sweeps
   double* trans_sum;     // [S*S] +=
   int8_t* status;        // [stride]
@@ -83,18 +100,18 @@ struct SweepArgs {
 
 // S <= 4: 80 registers, 6 CTAs per SM (the shared-memory limit): the kernel is latency bound and
 // 24 warps per SM beat 16 by 9 % at C4 (profiles/r1_raoteh_occupancy.log; 5 CTAs: no gain)
-template <int S, int OBS, bool STATS>
-__global__ void __launch_bounds__(kBlock, (S <= 4 ? 6 : 4))
-raoteh_kernel(SweepArgs A) {
+template <int S, int OBS, bool STATS, typename TT>
+__global__ void __launch_bounds__(kBlock, (S <= 4 && sizeof(TT) == 4 ? 6 : 4))
+raoteh_kernel(SweepArgs<TT> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int4* prog_s = reinterpret_cast<int4*>(smem_raw);
   double* B_s = reinterpret_cast<double*>(prog_s + A.n_ops);
   double* pi_s = B_s + S * S;
   double* dwell_s = pi_s + S;                                       // [S][kBlock]
   uint32_t* trans_s = reinterpret_cast<uint32_t*>(dwell_s + S * kBlock);   // [S*S][kBlock]
-  float* rate_s = reinterpret_cast<float*>(trans_s + S * S * kBlock);      // [S] poisson rates
-  float* rinv_s = rate_s + S;                                       // [S]
-  float* len_s = rinv_s + S;                                        // [n_nodes]
+  TT* rate_s = reinterpret_cast<TT*>(trans_s + S * S * kBlock);      // [S] poisson rates
+  TT* rinv_s = rate_s + S;                                       // [S]
+  TT* len_s = rinv_s + S;                                        // [n_nodes]
   int* par_s = reinterpret_cast<int*>(len_s + A.n_nodes);           // [n_nodes]
   double* stk = reinterpret_cast<double*>(
       (reinterpret_cast<uintptr_t>(par_s + A.n_nodes) + 7) & ~(uintptr_t)7);   // [n_slots][S][kBlock]
@@ -104,11 +121,11 @@ raoteh_kernel(SweepArgs A) {
   for (int i = tid; i < A.n_ops; i += kBlock) prog_s[i] = A.program[i];
   for (int i = tid; i < S * S; i += kBlock) B_s[i] = A.B[i];
   if (tid < S) {
-    rate_s[tid] = (float)A.rate[tid];
-    rinv_s[tid] = A.rate[tid] > 0.0 ? (float)(1.0 / A.rate[tid]) : 0.0f;
+    rate_s[tid] = (TT)A.rate[tid];
+    rinv_s[tid] = A.rate[tid] > 0.0 ? (TT)(1.0 / A.rate[tid]) : (TT)0;
     pi_s[tid] = A.root_distn ? A.root_distn[tid] : 1.0;
   }
-  for (int i = tid; i < A.n_nodes; i += kBlock) { len_s[i] = (float)A.length[i]; par_s[i] = A.parent[i]; }
+  for (int i = tid; i < A.n_nodes; i += kBlock) { len_s[i] = (TT)A.length[i]; par_s[i] = A.parent[i]; }
 #pragma unroll
   for (int s = 0; s < S; ++s) dwell_s[s * kBlock + tid] = 0.0;
 #pragma unroll
@@ -125,12 +142,16 @@ raoteh_kernel(SweepArgs A) {
     uint8_t* ns_p = A.node_state + traj;
     uint8_t* cnt_p = A.ev_count + traj;
     uint8_t* scnt_p = A.scr_count + traj;
-    float* evt_p = A.ev_time + (size_t)traj * A.cap;      // [traj][cap]: a thread's jumps are contiguous
+    const int64_t sst = A.scr_stride;
+    TT* evt_p = A.ev_time + (size_t)traj * A.cap;      // [traj][cap]: a thread's jumps are contiguous
     uint8_t* evs_p = A.ev_sb + (size_t)traj * A.cap;
-    constexpr int kRec = (8 + 8 * S + 15) / 16 * 16;        // bytes per scratch record
+    constexpr int kRec = (8 * S + (int)sizeof(TT) + 4 + 15) / 16 * 16;        // bytes per scratch record
     unsigned char* rec_p = A.scr_rec + (size_t)traj * A.scr_cap * kRec;
-    for (int sw = 0; sw < A.n_sweeps; ++sw) {
-      rng.init(A.seed, (uint64_t)(A.traj0 + traj), (uint32_t)(A.sweep0 + sw));
+    // with a per-trajectory counter the trajectory resumes at its own sweep index
+    const long long sw_end = A.sweep0 + A.n_sweeps;
+    long long sw = (A.sweep_count && A.init_k < 0) ? (long long)A.sweep_count[traj] : A.sweep0;
+    for (; sw < sw_end; ++sw) {
+      rng.init(A.seed, (uint64_t)(A.traj0 + traj), (uint32_t)sw);
       // substream 0: root draw (word 0) and the first unit-rate gap (word 1)
       rng.block(0u, 0u);
       const uint32_t u_root = rng.out[0];
@@ -138,13 +159,13 @@ raoteh_kernel(SweepArgs A) {
       // in HAZARD space.  Walking the segments in program order, `hrem` is the hazard left
       // until the next event (unit-rate exponential gaps); a segment of hazard h consumes
       // it, and only an actual event costs a random number and a logarithm.
-      float hrem = -__logf(RT_U32_TO_UNIT(rng.out[1]));
+      TT hrem = TimeOps<TT>::neglog_unit(rng.out[1]);
       // =============================== UP ===============================
       int nA = 0;                                   // entries pushed to the scratch list
       int rd = A.cap - A.ev_total[traj];            // read cursor in the old jump list
       // the old jump list is consumed strictly in order (across edges too), so its next entry
       // is loaded when the previous one is consumed, long before it is needed
-      float pf_time = -1.0f;
+      TT pf_time = (TT)-1;
       int pf_sb = 0;
       if (A.init_k < 0 && rd < A.cap) { pf_time = evt_p[rd]; pf_sb = evs_p[rd]; }
       bool overflow = false;
@@ -169,19 +190,19 @@ raoteh_kernel(SweepArgs A) {
 #pragma unroll
             for (int s = 0; s < S; ++s) beta[s] = 1.0;
           }
-          const float tc = len_s[c];
+          const TT tc = len_s[c];
           // --- walk the edge from the child end to the parent end over its candidate
           //     events (old jumps + fresh virtual events): one loop, one event site ---
           int kA = 0;
           int cur = 0, k_old = 0;
-          float next_old = -1.0f;          // time of the next old jump toward the parent (-1: none)
+          TT next_old = (TT)-1;            // time of the next old jump toward the parent (-1: none)
           int next_sb = 0;
-          float pos = tc;                  // current position (moving toward 0)
+          TT pos = tc;                     // current position (moving toward 0)
           int init_left = 0;
           if (A.init_k >= 0) {
             // no events on a zero-length branch: its end states are equal (P(0) = I), and a jump
             // at time 0 would be indistinguishable from 'no more jumps' in the sweeps
-            init_left = tc > 0.0f ? A.init_k : 0;
+            init_left = tc > (TT)0 ? A.init_k : 0;
           } else {
             cur = ns_p[(int64_t)c * st];
             k_old = cnt_p[(int64_t)c * st];
@@ -192,22 +213,24 @@ raoteh_kernel(SweepArgs A) {
             }
           }
           while (true) {
-            float cand;                    // position of the next candidate event
+            TT cand;                       // position of the next candidate event
             bool is_old = false, is_virtual = false;
             if (A.init_k >= 0) {
               if (init_left == 0) break;
-              cand = tc * (float)init_left / (float)(A.init_k + 1);
+              cand = tc * (TT)init_left / (TT)(A.init_k + 1);
               --init_left;
             } else {
-              const float seg_start = next_old > 0.0f ? next_old : 0.0f;
-              const float h = rate_s[cur] * (pos - seg_start);
+              const TT seg_start = next_old > (TT)0 ? next_old : (TT)0;
+              const TT h = rate_s[cur] * (pos - seg_start);
               if (hrem < h) {
                 cand = pos - hrem * rinv_s[cur];
-                if (!(cand > seg_start)) cand = seg_start + 0.5f * (pos - seg_start);   // rounding guard
+                // strictly inside the segment: a virtual event that rounds onto an end of its
+                // segment would duplicate an existing jump time (or the branch end)
+                if (!(cand > seg_start && cand < pos)) cand = seg_start + (TT)0.5 * (pos - seg_start);
                 is_virtual = true;
               } else {
                 hrem -= h;
-                if (next_old > 0.0f) { cand = next_old; is_old = true; }
+                if (next_old > (TT)0) { cand = next_old; is_old = true; }
                 else break;
               }
             }
@@ -216,7 +239,7 @@ raoteh_kernel(SweepArgs A) {
             const bool odd = (kA & 1) != 0;
             const uint32_t u_draw = odd ? rng.out[2] : rng.out[0];
             const uint32_t u_gap = odd ? rng.out[3] : rng.out[1];
-            if (is_virtual) hrem = -__logf(RT_U32_TO_UNIT(u_gap));
+            if (is_virtual) hrem = TimeOps<TT>::neglog_unit(u_gap);
             // record beta just below the event, then push it through B
             if (nA < A.scr_cap) {
               unsigned char* rp = rec_p + (size_t)nA * kRec;
@@ -228,7 +251,12 @@ raoteh_kernel(SweepArgs A) {
 #pragma unroll
                 for (int s = 0; s < S; ++s) reinterpret_cast<double*>(rp)[s] = beta[s];
               }
-              *reinterpret_cast<float2*>(rp + 8 * S) = make_float2(cand, __uint_as_float(u_draw));
+              if constexpr (sizeof(TT) == 4) {
+                *reinterpret_cast<float2*>(rp + 8 * S) = make_float2((float)cand, __uint_as_float(u_draw));
+              } else {
+                *reinterpret_cast<double*>(rp + 8 * S) = (double)cand;
+                *reinterpret_cast<uint32_t*>(rp + 8 * S + 8) = u_draw;
+              }
             } else overflow = true;
             ++nA; ++kA;
             {
@@ -253,12 +281,12 @@ raoteh_kernel(SweepArgs A) {
                 next_sb = pf_sb;
                 if (rd + 1 < A.cap) { pf_time = evt_p[rd + 1]; pf_sb = evs_p[rd + 1]; }
               } else {
-                next_old = -1.0f;
+                next_old = (TT)-1;
               }
             }
           }
           if (kA > 255) overflow = true;
-          scnt_p[(int64_t)c * st] = (uint8_t)(kA > 255 ? 255 : kA);
+          scnt_p[(int64_t)c * sst] = (uint8_t)(kA > 255 ? 255 : kA);
           if (kA > 0) {   // keep the chain of B-steps in range
             double mx = beta[0];
 #pragma unroll
@@ -317,7 +345,8 @@ raoteh_kernel(SweepArgs A) {
       int rdA = nA;          // scratch is consumed backwards
       int wr = A.cap;        // new jump list grows backwards from the end
       // ... strictly in order, so record rdA - 2 is loaded while record rdA - 1 is sampled
-      float2 tu_n = make_float2(0.0f, 0.0f);
+      TT t_n = (TT)0;
+      uint32_t u_n = 0u;
       double b_n[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) b_n[s] = 0.0;
@@ -333,7 +362,13 @@ raoteh_kernel(SweepArgs A) {
 #pragma unroll
           for (int s = 0; s < S; ++s) b_n[s] = reinterpret_cast<const double*>(rp)[s];
         }
-        tu_n = *reinterpret_cast<const float2*>(rp + 8 * S);
+        if constexpr (sizeof(TT) == 4) {
+          const float2 tu = *reinterpret_cast<const float2*>(rp + 8 * S);
+          t_n = (TT)tu.x; u_n = __float_as_uint(tu.y);
+        } else {
+          t_n = (TT)*reinterpret_cast<const double*>(rp + 8 * S);
+          u_n = *reinterpret_cast<const uint32_t*>(rp + 8 * S + 8);
+        }
       };
       if (nA > 0) load_rec(nA - 1);
       bool pool_overflow = false;
@@ -342,14 +377,14 @@ raoteh_kernel(SweepArgs A) {
         if ((op.x & 0xff) > OP_MSG_ONES) continue;
         const int c = op.y;
         int cur = ns_p[(int64_t)par_s[c] * st];
-        const int kA = scnt_p[(int64_t)c * st];
-        const float tc = len_s[c];
-        float prev = 0.0f;
+        const int kA = scnt_p[(int64_t)c * sst];
+        const TT tc = len_s[c];
+        TT prev = (TT)0;
         int kept = 0;
         for (int j = 0; j < kA; ++j) {
           --rdA;
-          const float tau = tu_n.x;
-          const uint32_t u_draw = __float_as_uint(tu_n.y);
+          const TT tau = t_n;
+          const uint32_t u_draw = u_n;
           // child-side state ~ B[cur, :] * beta  (_sample_mc0.py:66-90)
           double w[S], tot = 0.0;
 #pragma unroll
@@ -391,6 +426,8 @@ raoteh_kernel(SweepArgs A) {
       if (pool_overflow) { A.status[traj] = 4; A.ev_total[traj] = 0; break; }
       A.ev_total[traj] = A.cap - wr;
     }
+    // sw = first sweep NOT completed (== sw_end unless the trajectory stopped early)
+    if (A.sweep_count) A.sweep_count[traj] = (int32_t)sw;
   }
 
   if (STATS && A.dwell_sum) {
@@ -410,20 +447,20 @@ raoteh_kernel(SweepArgs A) {
   }
 }
 
-template <int S, int OBS>
-int launch(const SweepArgs& A, bool stats, cudaStream_t stream) {
+template <int S, int OBS, typename TT>
+int launch(const SweepArgs<TT>& A, bool stats, cudaStream_t stream) {
   size_t smem = sizeof(int4) * A.n_ops + sizeof(double) * (S * S + S) +
                 sizeof(double) * S * kBlock + sizeof(uint32_t) * S * S * kBlock +
-                sizeof(float) * 2 * S + sizeof(float) * A.n_nodes + sizeof(int) * A.n_nodes +
+                sizeof(TT) * 2 * S + sizeof(TT) * A.n_nodes + sizeof(int) * A.n_nodes +
                 sizeof(double) * (size_t)A.n_slots * S * kBlock + 32;
   if (smem > 200 * 1024) return RT_ERR_UNSUPPORTED;
   const unsigned grid = (unsigned)((A.n_traj + kBlock - 1) / kBlock);
   if (stats) {
-    auto kern = raoteh_kernel<S, OBS, true>;
+    auto kern = raoteh_kernel<S, OBS, true, TT>;
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kBlock, smem, stream>>>(A);
   } else {
-    auto kern = raoteh_kernel<S, OBS, false>;
+    auto kern = raoteh_kernel<S, OBS, false, TT>;
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kBlock, smem, stream>>>(A);
   }
@@ -431,56 +468,80 @@ int launch(const SweepArgs& A, bool stats, cudaStream_t stream) {
   return RT_OK;
 }
 
-template <int S>
-int launch_s(int obs_kind, const SweepArgs& A, bool stats, cudaStream_t stream) {
-  if (obs_kind == OBS_CODES) return launch<S, OBS_CODES>(A, stats, stream);
-  if (obs_kind == OBS_MASK) return launch<S, OBS_MASK>(A, stats, stream);
+template <int S, typename TT>
+int launch_s(int obs_kind, const SweepArgs<TT>& A, bool stats, cudaStream_t stream) {
+  if (obs_kind == OBS_CODES) return launch<S, OBS_CODES, TT>(A, stats, stream);
+  if (obs_kind == OBS_MASK) return launch<S, OBS_MASK, TT>(A, stats, stream);
   return RT_ERR_ARG;
 }
 
-}  // namespace
+// Trajectories per launch: the per-event scratch (cap records of 48 B at S = 4) is sized for one
+// chunk and reused by the next launch on the same stream, so the workspace does not grow with the
+// number of trajectories (4096 chains x 1e4 sites = 4.1e7 trajectories at BASELINE config C4).
+// 2^19 trajectories = 4.6 waves of 6 CTAs x 148 SMs.
+constexpr int64_t kChunkTraj = 1 << 19;
 
-int rt_raoteh_dispatch(int S, int obs_kind, int n_nodes, int64_t n_traj, int64_t stride,
-                       int64_t n_sites, int64_t traj0, const int32_t* program, int n_ops, int n_slots,
-                       const int32_t* parent, const double* length, const double* B,
-                       const double* rate, const double* root_distn, const void* obs,
-                       int64_t obs_stride, uint8_t* node_state, float* ev_time, uint8_t* ev_sb,
-                       uint8_t* ev_count, int32_t* ev_total, int cap, uint64_t seed, int64_t sweep0,
-                       int n_sweeps, int init_k, double* dwell_sum, double* trans_sum,
-                       int8_t* status, cudaStream_t stream) {
-  SweepArgs A;
+template <typename TT>
+int dispatch_t(const rt_raoteh_args& R, cudaStream_t stream) {
+  const int S = R.S, obs_kind = R.obs_kind, n_nodes = R.n_nodes, n_ops = R.n_ops, n_slots = R.n_slots;
+  const int cap = R.cap, n_sweeps = R.n_sweeps, init_k = R.init_k;
+  const int64_t n_traj = R.n_traj, stride = R.traj_stride, n_sites = R.n_sites, traj0 = R.traj0;
+  const int64_t obs_stride = R.obs_stride, sweep0 = R.sweep0;
+  const uint64_t seed = R.seed;
+  const int32_t* program = R.program; const int32_t* parent = R.parent;
+  const double* length = R.length; const double* B = R.B; const double* rate = R.rate;
+  const double* root_distn = R.root_distn; const void* obs = R.obs;
+  uint8_t* node_state = R.node_state; TT* ev_time = reinterpret_cast<TT*>(R.ev_time);
+  uint8_t* ev_sb = R.ev_sb; uint8_t* ev_count = R.ev_count; int32_t* ev_total = R.ev_total;
+  double* dwell_sum = R.dwell_sum; double* trans_sum = R.trans_sum; int8_t* status = R.status;
+  SweepArgs<TT> A;
   A.n_nodes = n_nodes; A.n_ops = n_ops; A.n_slots = n_slots; A.cap = cap;
   // sweeps: kept jumps <= scratch entries <= cap, so the jump list cannot overflow.
   // init mode: init_k events on every edge are candidates (status 4 if more than
   // `cap` of them turn out to be real jumps).
   A.scr_cap = cap;
   if (init_k > 0 && (n_nodes - 1) * init_k > cap) A.scr_cap = (n_nodes - 1) * init_k;
-  A.n_traj = n_traj; A.stride = stride; A.n_sites = n_sites; A.obs_stride = obs_stride; A.traj0 = traj0;
+  A.stride = stride; A.n_sites = n_sites; A.obs_stride = obs_stride;
   A.program = reinterpret_cast<const int4*>(program);
   A.parent = parent; A.length = length; A.B = B; A.rate = rate; A.root_distn = root_distn;
-  A.obs = obs; A.node_state = node_state; A.ev_time = ev_time; A.ev_sb = ev_sb;
-  A.ev_count = ev_count; A.ev_total = ev_total;
+  A.obs = obs;
   A.seed = seed; A.sweep0 = sweep0; A.n_sweeps = n_sweeps; A.init_k = init_k;
-  A.dwell_sum = dwell_sum; A.trans_sum = trans_sum; A.status = status;
-  // scratch: full event list (time + table) and per-edge counts
+  A.dwell_sum = dwell_sum; A.trans_sum = trans_sum;
+  const int64_t chunk = n_traj < kChunkTraj ? n_traj : kChunkTraj;
+  A.scr_stride = chunk;
+  // scratch of one chunk: event records and per-edge candidate counts
   unsigned char* ws = nullptr;
-  const size_t n_scr = (size_t)A.scr_cap * (size_t)stride;
-  const size_t rec = (size_t)((8 + 8 * S + 15) / 16 * 16);
-  const size_t bytes = n_scr * rec + (size_t)n_nodes * (size_t)stride + 64;
-  RT_CUDA_CHECK(cudaMallocAsync(&ws, bytes, stream));
+  const size_t n_scr = (size_t)A.scr_cap * (size_t)chunk;
+  const size_t rec = (size_t)((8 * S + (int)sizeof(TT) + 4 + 15) / 16 * 16);
+  const size_t bytes = n_scr * rec + (size_t)n_nodes * (size_t)chunk + 64;
+  RT_CUDA_CHECK(rt_ws_alloc((void**)&ws, bytes, stream));
   A.scr_rec = ws;
   A.scr_count = ws + n_scr * rec;
   const bool stats = dwell_sum != nullptr && trans_sum != nullptr && init_k < 0;
-  int rc;
-  switch (S) {
-    case 2: rc = launch_s<2>(obs_kind, A, stats, stream); break;
-    case 3: rc = launch_s<3>(obs_kind, A, stats, stream); break;
-    case 4: rc = launch_s<4>(obs_kind, A, stats, stream); break;
-    case 5: rc = launch_s<5>(obs_kind, A, stats, stream); break;
-    case 6: rc = launch_s<6>(obs_kind, A, stats, stream); break;
-    case 8: rc = launch_s<8>(obs_kind, A, stats, stream); break;
-    default: rc = RT_ERR_UNSUPPORTED;
+  int rc = RT_OK;
+  for (int64_t lo = 0; lo < n_traj && rc == RT_OK; lo += chunk) {
+    A.n_traj = (n_traj - lo < chunk) ? n_traj - lo : chunk;
+    A.traj0 = traj0 + lo;
+    A.node_state = node_state + lo; A.ev_count = ev_count + lo; A.ev_total = ev_total + lo;
+    A.ev_time = ev_time + (size_t)lo * cap; A.ev_sb = ev_sb + (size_t)lo * cap;
+    A.status = status + lo;
+    A.sweep_count = R.sweep_count ? R.sweep_count + lo : nullptr;
+    switch (S) {
+      case 2: rc = launch_s<2, TT>(obs_kind, A, stats, stream); break;
+      case 3: rc = launch_s<3, TT>(obs_kind, A, stats, stream); break;
+      case 4: rc = launch_s<4, TT>(obs_kind, A, stats, stream); break;
+      case 5: rc = launch_s<5, TT>(obs_kind, A, stats, stream); break;
+      case 6: rc = launch_s<6, TT>(obs_kind, A, stats, stream); break;
+      case 8: rc = launch_s<8, TT>(obs_kind, A, stats, stream); break;
+      default: rc = RT_ERR_UNSUPPORTED;
+    }
   }
-  cudaFreeAsync(ws, stream);
+  rt_ws_free(ws, stream);
   return rc;
+}
+
+}  // namespace
+
+int rt_raoteh_dispatch(const rt_raoteh_args& R, cudaStream_t stream) {
+  return R.time_f64 ? dispatch_t<double>(R, stream) : dispatch_t<float>(R, stream);
 }

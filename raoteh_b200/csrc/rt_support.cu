@@ -59,14 +59,14 @@ int rt_support_sets_impl(int S, int n_nodes, int64_t n_sites, int64_t stride, in
   if (S < 1 || S > 64) return RT_ERR_UNSUPPORTED;
   if (n_nodes <= 0 || n_sites <= 0) return RT_OK;
   unsigned long long* rowbits = nullptr;
-  RT_CUDA_CHECK(cudaMallocAsync(&rowbits, sizeof(unsigned long long) * (size_t)n_nodes * S, stream));
+  RT_CUDA_CHECK(rt_ws_alloc((void**)&rowbits, sizeof(unsigned long long) * (size_t)n_nodes * S, stream));
   const int tot = n_nodes * S;
   pack_pattern_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(P, S, n_nodes, rowbits);
   support_kernel<<<(unsigned)((n_sites + 127) / 128), 128, 0, stream>>>(
       S, n_nodes, n_sites, stride, passes, parent, rowbits,
       reinterpret_cast<unsigned long long*>(mask));
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(rowbits, stream);
+  rt_ws_free(rowbits, stream);
   RT_CUDA_CHECK(e);
   return RT_OK;
 }

@@ -1256,7 +1256,7 @@ int launch(const rt_tmjp_args& A, cudaStream_t stream) {
   const size_t b_tb = tol ? al(n_warps * (size_t)X.cap_ts * 32 * sizeof(double2), 256) : 0;
   const size_t b_seg = want_seg ? al(n_warps * (size_t)X.n_seg * 32 * sizeof(double2), 256) : 0;
   unsigned char* ws = nullptr;
-  RT_CUDA_CHECK(cudaMallocAsync(&ws, b_beta + b_tu + b_tb + b_seg + 256, stream));
+  RT_CUDA_CHECK(rt_ws_alloc((void**)&ws, b_beta + b_tu + b_tb + b_seg + 256, stream));
   unsigned char* p = ws;
   X.p_beta = reinterpret_cast<double*>(p); p += b_beta;
   X.t_tu = tol ? reinterpret_cast<float2*>(p) : nullptr; p += b_tu;
@@ -1264,7 +1264,7 @@ int launch(const rt_tmjp_args& A, cudaStream_t stream) {
   X.seg = want_seg ? reinterpret_cast<double2*>(p) : nullptr;
   kern<<<(unsigned)grid, kThreads, L.total, stream>>>(A, X);
   cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(ws, stream);
+  rt_ws_free(ws, stream);
   if (e != cudaSuccess) { rt_set_last_error(e, __FILE__, __LINE__); return RT_ERR_CUDA; }
   return RT_OK;
 }

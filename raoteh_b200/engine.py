@@ -106,6 +106,7 @@ class Observations(object):
 
 class TreeMJP(object):
     """Markov jump process on a rooted tree, evaluated for batches of sites."""
+    _n_made = 0
 
     def __init__(self, sched, Q, root_distn=None, q_index=None, device='cuda', P=None):
         if not torch.cuda.is_available():
@@ -134,6 +135,8 @@ class TreeMJP(object):
             self._P_valid = True
         self._prog_cache = {}
         self._ws = {}
+        TreeMJP._n_made += 1
+        self._serial = TreeMJP._n_made
         self._Q_stage = None
         self.events = None     # optional dict: name -> [(start, end) CUDA events]
 
@@ -288,9 +291,17 @@ class TreeMJP(object):
         res = dict(loglik=loglik, status=status, partials=partials, exponents=None, node_distn=None,
                    W=W, root_post_sum=rps, n_levels=len(lp) - 1)
         # the chunk schedule is launch-bound on the host (2 launches per chunk), so it is
-        # captured once per (observations, chunking) into a CUDA graph and replayed
-        key = (obs.data.data_ptr(), N, stride, n_chunks, P.data_ptr(), partials.data_ptr(),
-               loglik.data_ptr(), W.data_ptr())
+        # captured once per (observations, chunking) into a CUDA graph and replayed.  The graphs
+        # live ON the Observations object (they bake in its data pointer, encoding and tree
+        # program), keyed by this engine's serial number and every other baked-in pointer: a new
+        # Observations never sees another one's graph even if the allocator hands it the same
+        # address, and the graphs die with the observations.
+        cache = obs.__dict__.setdefault('_rt_graphs', {})
+        key = (self._serial, obs.kind, obs.data.data_ptr(), N, stride, n_chunks, P.data_ptr(),
+               partials.data_ptr(), loglik.data_ptr(), status.data_ptr(), W.data_ptr(),
+               rps.data_ptr(), _ptr(self.root_distn), prog['ops'].data_ptr(),
+               prog['edges'].data_ptr())
+        self._ov_graphs = cache
         g = self._ov_graphs.get(key)
         if g is not None:
             g.replay()

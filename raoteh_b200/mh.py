@@ -72,7 +72,7 @@ class ToleranceMetropolisChains(object):
             saved = self.proposal.snapshot()
             self.proposal.sweep(1, stats=False)
             ll_b = self.proposal.trajectory_log_likelihood()
-            ll_t = self.target.tolerance_log_likelihood()
+            ll_t = self.target.tolerance_log_likelihood(zero_as_neg_inf=True)   # zero target = rejection
             log_ratio = ll_t - self.ll_target - ll_b + self.ll_biased          # _sampler.py:514-518
             u = torch.rand(self.n_traj, dtype=torch.float64, device=log_ratio.device, generator=self.gen)
             accept = torch.log(u) < log_ratio

@@ -23,8 +23,11 @@ class RaoTehChains(object):
     """
 
     def __init__(self, sched, Q, obs, n_chains=1, root_distn=None, uniformization_factor=2.0,
-                 cap=96, seed=0, device='cuda', traj0=0, n_traj=None, chain_matrix=None):
-        """chain_matrix: instead of a rate matrix, a transition matrix B applied at every
+                 cap=96, seed=0, device='cuda', traj0=0, n_traj=None, chain_matrix=None,
+                 time_dtype='float32'):
+        """time_dtype: 'float32' (default: 4-byte jump lists) or 'float64' (every event time,
+        branch position and Poisson hazard in the reference's fp64 arithmetic; S <= 8).
+        chain_matrix: instead of a rate matrix, a transition matrix B applied at every
         candidate event, with no virtual events (Poisson rates 0): the discrete-time chain
         samplers of raoteh/sampler/_sample_mcy.py / _sample_mcx.py are this special case."""
         if not torch.cuda.is_available():
@@ -51,6 +54,13 @@ class RaoTehChains(object):
         self.n_traj = int(n_chains) * self.n_sites if n_traj is None else int(n_traj)
         self.cap = int(cap)
         self.seed = int(seed)
+        if time_dtype not in ('float32', 'float64'):
+            raise ValueError("time_dtype must be 'float32' or 'float64'")
+        if time_dtype == 'float64' and (S > 8 or S == 7):
+            raise ValueError('fp64 event times are implemented by the thread-per-trajectory kernel '
+                             '(2, 3, 4, 5, 6 or 8 states)')
+        self.time_dtype = time_dtype
+        self._tt = torch.float64 if time_dtype == 'float64' else torch.float32
         # uniformization: omega = f * max_s q_s; B = I + Q/omega; rates omega - q_s
         q = -np.diag(Q)
         self.omega = float(uniformization_factor * q.max())
@@ -77,7 +87,11 @@ class RaoTehChains(object):
         self.node_state = torch.zeros((n, T), dtype=torch.uint8, device=dev)
         self.ev_count = torch.zeros((n, T), dtype=torch.uint8, device=dev)
         self.ev_total = torch.zeros(T, dtype=torch.int32, device=dev)
-        self.ev_time = torch.zeros((T, self.cap), dtype=torch.float32, device=dev)
+        self.ev_time = torch.zeros((T, self.cap), dtype=self._tt, device=dev)
+        # sweeps completed per trajectory (thread-per-trajectory kernel): lets a trajectory that
+        # ran out of event capacity resume at its own sweep index after grow()
+        self.sweep_count = (torch.zeros(T, dtype=torch.int32, device=dev)
+                            if (S <= 8 and S != 7) else None)
         self.ev_sb = torch.zeros((T, self.cap), dtype=torch.uint8, device=dev)
         self.status = torch.zeros(T, dtype=torch.int8, device=dev)
         self.dwell_sum = torch.zeros(S, dtype=torch.float64, device=dev)
@@ -86,16 +100,24 @@ class RaoTehChains(object):
         self.initialized = False
 
     def _call(self, n_sweeps, init_k, stats):
-        rc = _native.lib().rt_raoteh_sweeps(
-            self.S, self.sched.n, self.n_traj, self.stride, self.n_sites, self.traj0,
-            _ptr(self.ops), self.n_ops, self.n_slots, _ptr(self.parent), _ptr(self.length),
-            _ptr(self.B), _ptr(self.rate), _ptr(self.root_distn), self.obs.kind,
-            _ptr(self.obs.data), self.obs.stride, _ptr(self.node_state), _ptr(self.ev_time),
-            _ptr(self.ev_sb), _ptr(self.ev_count), _ptr(self.ev_total), self.cap, self.seed,
-            self.sweeps_done, n_sweeps, init_k,
-            _ptr(self.dwell_sum) if stats else None, _ptr(self.trans_sum) if stats else None,
-            _ptr(self.status), _stream())
-        _native.check(rc, 'rt_raoteh_sweeps')
+        import ctypes
+        A = _native.RaotehArgs()
+        A.S, A.n_nodes, A.n_ops, A.n_slots = self.S, self.sched.n, self.n_ops, self.n_slots
+        A.obs_kind, A.cap, A.n_sweeps, A.init_k = self.obs.kind, self.cap, int(n_sweeps), int(init_k)
+        A.time_f64 = 1 if self.time_dtype == 'float64' else 0
+        A.n_traj, A.traj_stride, A.n_sites, A.traj0 = self.n_traj, self.stride, self.n_sites, self.traj0
+        A.obs_stride, A.sweep0, A.seed = self.obs.stride, self.sweeps_done, self.seed
+        A.program, A.parent, A.length = _ptr(self.ops), _ptr(self.parent), _ptr(self.length)
+        A.B, A.rate, A.root_distn = _ptr(self.B), _ptr(self.rate), _ptr(self.root_distn)
+        A.obs = _ptr(self.obs.data)
+        A.node_state, A.ev_time, A.ev_sb = _ptr(self.node_state), _ptr(self.ev_time), _ptr(self.ev_sb)
+        A.ev_count, A.ev_total = _ptr(self.ev_count), _ptr(self.ev_total)
+        A.sweep_count = _ptr(self.sweep_count)
+        A.dwell_sum = _ptr(self.dwell_sum) if stats else None
+        A.trans_sum = _ptr(self.trans_sum) if stats else None
+        A.status = _ptr(self.status)
+        rc = _native.lib().rt_raoteh_run(ctypes.byref(A), _stream())
+        _native.check(rc, 'rt_raoteh_run')
 
     def initialize(self):
         """Initial feasible history: 0, 1, 3, 7, ... equally spaced events per edge
@@ -116,6 +138,8 @@ class RaoTehChains(object):
             j += 1
         self.status[self.status == DONE] = 0
         self.check()
+        if self.sweep_count is not None:
+            self.sweep_count.fill_(1)
         self.sweeps_done = 1      # sweep index 0 was the initial history
         self.initialized = True
         return k
@@ -126,17 +150,18 @@ class RaoTehChains(object):
         if not self.initialized:
             self.initialize()
         self._call(int(n_sweeps), -1, stats)
-        self.sweeps_done += int(n_sweeps)
-        if auto_grow:
+        if auto_grow and self.sweep_count is not None:
             # a trajectory that ran out of event capacity stopped at its last completed sweep
-            # (a valid history); double the pools and carry on -- it is a few sweeps behind
+            # (a valid history) and its own sweep counter: double the pools and repeat the SAME
+            # call -- trajectories already at the target do nothing, the stopped ones resume at
+            # their own sweep index, so every (trajectory, sweep) enters the statistics once
             tries = 0
             while bool((self.status == 3).any()) and self.omega * float(self.sched.length.max()) < 200 \
                     and tries < 4:
                 self.grow(2 * self.cap)
-                self._call(1, -1, stats)
-                self.sweeps_done += 1
+                self._call(int(n_sweeps), -1, stats)
                 tries += 1
+        self.sweeps_done += int(n_sweeps)
         self.check()
 
     def grow(self, cap):
@@ -146,7 +171,7 @@ class RaoTehChains(object):
         if cap <= self.cap:
             return
         T, dev = self.n_traj, self.device
-        for name, dt in (('ev_time', torch.float32), ('ev_sb', torch.uint8)):
+        for name, dt in (('ev_time', self._tt), ('ev_sb', torch.uint8)):
             new = torch.zeros((T, cap), dtype=dt, device=dev)
             new[:, cap - self.cap:] = getattr(self, name)
             setattr(self, name, new)
@@ -210,12 +235,16 @@ class RaoTehChains(object):
         tt = []
         for c in order:
             ts = sorted(float(x) for x in edge_times.get(c, ()))
+            if len(ts) > 255:
+                raise ValueError('more than 255 events on the branch above node %d: the per-branch '
+                                 'event counts of the kernels are uint8; subdivide the branch with '
+                                 'degree-two nodes (lowering.subdivide_long_branches)' % c)
             cnt[c] = len(ts)
             tt.extend(ts[::-1])                # child end first
         k = len(tt)
         if k > self.cap:
             raise ValueError('more events than cap')
-        row = np.zeros(self.cap, dtype=np.float32)
+        row = np.zeros(self.cap, dtype=np.float64 if self.time_dtype == 'float64' else np.float32)
         if k:
             row[self.cap - k:] = tt
         dev = self.device
@@ -225,6 +254,8 @@ class RaoTehChains(object):
         self.ev_total.fill_(k)
         self.node_state.zero_()
         self.status.zero_()
+        if self.sweep_count is not None:
+            self.sweep_count.fill_(self.sweeps_done)
         self.initialized = True
 
     _STATE = ('node_state', 'ev_count', 'ev_total', 'ev_time', 'ev_sb')

@@ -67,6 +67,9 @@ def _run(sched, states, index, B, node_to_allowed_states, root_distn, edge_times
     return chain.trajectory(0)
 
 
+_MAX_EVENTS_PER_BASE_EDGE = 200
+
+
 def resample_states(T, root, node_to_allowed_states=None, root_distn=None, P_default=None, seed=None):
     """raoteh/sampler/_sample_mcy.py:19-83 -> dict node -> sampled state (one step of the
     transition matrix per edge).  Raises StructuralZeroProb when nothing is feasible."""
@@ -108,10 +111,23 @@ def resample_edge_states(T, root, P, event_nodes, node_to_allowed_states=None, r
         for b in T[a]:
             if b == came:
                 continue
-            prev, cur, t, ev, path = a, b, 0.0, [], [a]
+            prev, cur, t, ev, path, t0 = a, b, 0.0, [], [a], 0.0
+            above = pos[a]
             while True:
                 w = T[prev][cur].get('weight', None)
-                t += 1.0 if not w else float(w)
+                step = 1.0 if not w else float(w)
+                if len(ev) >= _MAX_EVENTS_PER_BASE_EDGE:
+                    # the kernels count events per branch in uint8: cut the chain of event nodes
+                    # in the middle of the tree edge (prev, cur) with an unrestricted degree-two
+                    # pseudo node (no event there, so the state is the same on both sides)
+                    cut = len(base_nodes)
+                    base_nodes.append(('__cut__', cut))
+                    parent.append(above)
+                    length.append(t + 0.5 * step)
+                    times[cut] = ev
+                    path_of[cut] = (t0, path)
+                    above, t, t0, ev, path = cut, -0.5 * step, -0.5 * step, [], [prev]
+                t += step
                 path.append(cur)
                 if cur not in event_nodes:
                     break
@@ -120,18 +136,18 @@ def resample_edge_states(T, root, P, event_nodes, node_to_allowed_states=None, r
                 prev, cur = cur, nxt
             pos[cur] = len(base_nodes)
             base_nodes.append(cur)
-            parent.append(pos[a])
+            parent.append(above)
             length.append(t)
             times[pos[cur]] = ev
-            path_of[pos[cur]] = path
+            path_of[pos[cur]] = (t0, path)
             stack.append((cur, prev))
     # preorder check: parents were appended before children by construction
     sched = TreeSchedule(np.asarray(parent, dtype=np.int32), np.asarray(length), base_nodes)
     ns, edges = _run(sched, states, index, B, node_to_allowed_states, root_distn, times, seed)
     T_aug = nx.Graph()
-    for c, path in path_of.items():
+    for c, (t0, path) in path_of.items():
         jump_times, seg_states = edges[c]
-        t = 0.0
+        t = t0
         for u, v in zip(path[:-1], path[1:]):
             w = T[u][v].get('weight', None)
             step = 1.0 if not w else float(w)

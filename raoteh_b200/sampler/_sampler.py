@@ -60,7 +60,8 @@ def _trajectory_to_graph(sched, states, ns, edges, next_node):
             next_node += 1
             T_out.add_edge(prev_node, mid, weight=float(tau - prev_t), state=states[seg_states[j]])
             prev_node, prev_t = mid, float(tau)
-        T_out.add_edge(prev_node, b, weight=float(sched.length[i] - prev_t),
+        # float32 event times can exceed the fp64 branch length by one rounding step
+        T_out.add_edge(prev_node, b, weight=max(0.0, float(sched.length[i] - prev_t)),
                        state=states[seg_states[-1]])
     return T_out
 

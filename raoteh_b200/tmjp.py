@@ -84,7 +84,13 @@ class ToleranceChains(object):
             raise ValueError('the rate matrix is empty')
         self.Q_host = Q
         to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-        self.B = to(np.eye(S) + Q / self.omega_p)
+        B = np.eye(S) + Q / self.omega_p
+        if primary_distn is not None:
+            # the reference keeps a primary state with zero prior out of EVERY chunk, not only
+            # the root's (raoteh/sampler/_sample_tmjp_dense.py:301-305): no uniformized step may
+            # enter such a state
+            B[:, np.asarray(primary_distn, dtype=np.float64) == 0] = 0.0
+        self.B = to(B)
         self.rate_p = to(self.omega_p - q)
         self.pi_p = None if primary_distn is None else to(np.asarray(primary_distn, dtype=np.float64))
         self.part = to(part.astype(np.uint8))
@@ -171,7 +177,7 @@ class ToleranceChains(object):
         k, j = 0, 0
         self.status.zero_()
         while True:
-            if k > 2 * self.S:
+            if k > self.S:      # the reference's bound (raoteh/sampler/_sample_mcx_dense.py:100)
                 raise RuntimeError('failed to find a feasible primary history')
             self._run(MODE_INIT_PRIMARY, init_k=k)
             failed = self.status == 1
@@ -220,12 +226,22 @@ class ToleranceChains(object):
         self.check()
         return self.summary_out[:, :7]
 
-    def tolerance_log_likelihood(self):
+    def tolerance_log_likelihood(self, zero_as_neg_inf=False):
         """log-likelihood of every current primary trajectory under the compound process with
         the tolerance histories integrated out (raoteh/sampler/_tmjp.py:406-492,
-        _tmjp_dense.py:407-505) -> [n_traj].  Runs the summary kernel."""
-        self.tolerance_summary()
-        return self.summary_out[:, 7]
+        _tmjp_dense.py:407-505) -> [n_traj].  Runs the summary kernel.
+        zero_as_neg_inf: a trajectory whose compound likelihood is numerically zero (status 2,
+        where the reference raises NumericalZeroProb) gets -inf and a cleared status instead of
+        an exception: as a Metropolis-Hastings target that is simply a rejected proposal."""
+        if not zero_as_neg_inf:
+            self.tolerance_summary()
+            return self.summary_out[:, 7]
+        self._run(MODE_SUMMARY)
+        zero = self.status == 2
+        self.status[zero] = 0
+        self.check()
+        return torch.where(zero, torch.full_like(self.summary_out[:, 7], float('-inf')),
+                           self.summary_out[:, 7])
 
     def trajectory_log_likelihood(self):
         """log-likelihood of every current primary trajectory under the primary process itself
