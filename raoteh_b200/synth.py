@@ -135,7 +135,14 @@ def simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng,
         cdf /= cdf[:, -1:]
         u = rng.random(n_sites)
         ps = states[parent[b]]
-        states[b] = (u[:, None] > cdf[ps]).sum(axis=1).astype(np.uint8)
+        # number of cdf entries strictly below u, per parent state (same result as comparing
+        # against the gathered cdf rows, without the [n_sites, S] temporary)
+        out = np.empty(n_sites, dtype=np.uint8)
+        for a in range(S):
+            idx = np.nonzero(ps == a)[0]
+            if len(idx):
+                out[idx] = np.searchsorted(cdf[a], u[idx], side='left')
+        states[b] = out
     codes = states[leaves].copy()
     if missing_frac > 0:
         codes[rng.random(codes.shape) < missing_frac] = MISSING

@@ -269,3 +269,58 @@ def test_capacity_growth_keeps_histories():
     tiny.initialize()
     tiny.sweep(3, auto_grow=True)
     assert tiny.cap > 12 and int((tiny.status != 0).sum()) == 0
+
+
+def test_auto_grow_keeps_every_trajectory_on_the_same_sweep():
+    """A trajectory that runs out of event capacity stops at its last completed sweep; with
+    auto_grow the pools are doubled and the SAME call is repeated, the stopped trajectories resume
+    at their own sweep index: afterwards every trajectory has done every sweep exactly once (the
+    statistics hold n_traj x n_sweeps histories: total dwell = tree length x that count) and the
+    histories are those of a run that had the larger capacity from the start."""
+    import torch
+    from raoteh_b200.raoteh import RaoTehChains
+    parent, length, leaves, Q, pi, codes, sched, obs = _setup(4, 12, 4, 21)
+    small = RaoTehChains(sched, Q, obs, n_chains=300, root_distn=pi, seed=8, cap=24)
+    small.initialize()
+    n_sweeps = 40
+    small.sweep(n_sweeps, auto_grow=True)
+    assert small.cap > 24                                  # the capacity was in fact exceeded
+    assert bool((small.sweep_count == 1 + n_sweeps).all())
+    np.testing.assert_allclose(float(small.dwell_sum.sum()), length.sum() * small.n_traj * n_sweeps, rtol=1e-5)
+    big = RaoTehChains(sched, Q, obs, n_chains=300, root_distn=pi, seed=8, cap=small.cap)
+    big.initialize()
+    big.sweep(n_sweeps)
+    assert bool((big.node_state == small.node_state).all())
+    assert bool((big.ev_total == small.ev_total).all())
+    assert torch.equal(big.trans_sum, small.trans_sum)
+
+
+def test_long_event_chains_are_subdivided():
+    """_sample_mcy.resample_edge_states on a path with more event nodes than the kernels' uint8
+    per-branch counters hold (the reference takes any number, raoteh/sampler/_sample_mcy.py:86-187):
+    the chain is cut with unrestricted pseudo nodes; load_events itself refuses > 255 loudly."""
+    import networkx as nx
+    from raoteh_b200 import engine
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200.raoteh import RaoTehChains
+    from raoteh_b200.sampler import _sample_mcy
+    n_ev = 700
+    T = nx.Graph()
+    for i in range(n_ev + 1):
+        T.add_edge(i, i + 1, weight=1.0)
+    root, leaf = 0, n_ev + 1
+    P = nx.DiGraph()
+    for a in range(3):
+        for b in range(3):
+            P.add_edge(a, b, weight=0.8 if a == b else 0.1)
+    T_aug = _sample_mcy.resample_edge_states(T, root, P, set(range(1, n_ev + 1)),
+                                             node_to_allowed_states={root: {0}, leaf: {2}}, seed=5)
+    states = [T_aug[i][i + 1]['state'] for i in range(n_ev + 1)]
+    assert states[0] == 0 and states[-1] == 2 and T_aug.number_of_edges() == n_ev + 1
+    changes = sum(1 for a, b in zip(states[:-1], states[1:]) if a != b)
+    assert 60 < changes < 220                # ~ Binomial(700, 0.2) conditioned on the end states
+    sched = TreeSchedule(np.array([-1, 0], dtype=np.int32), np.array([0.0, 1.0]))
+    obs = engine.Observations.from_masks(sched, np.array([[7], [7]], dtype=np.uint64))
+    ch = RaoTehChains(sched, None, obs, n_chains=1, cap=400, chain_matrix=np.full((3, 3), 1 / 3.0))
+    with pytest.raises(ValueError):
+        ch.load_events({1: list(np.linspace(0.001, 0.999, 300))})
