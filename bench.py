@@ -56,11 +56,11 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0), 'fallback'
 
 
-def fp64_peak():
+def fp64_peak(which='dmma'):
     """FP64 tensor (DMMA) peak measured on this pool's B200 with tools/fp64_peak.cu
     (profiles/r1_fp64_peak.jsonl): 37.0 TFLOP/s; DFMA 33.5 TFLOP/s."""
     path = os.path.join(ROOT, 'profiles', 'r1_fp64_peak.jsonl')
-    best = 37.0
+    best = 37.0 if which == 'dmma' else 33.5
     if os.path.exists(path):
         vals = []
         for line in open(path):
@@ -68,7 +68,7 @@ def fp64_peak():
                 d = json.loads(line)
             except ValueError:
                 continue
-            if d.get('probe') == 'dmma_m8n8k4':
+            if d.get('probe', '').startswith('dmma' if which == 'dmma' else 'dfma'):
                 vals.append(d['tflops'])
         if vals:
             best = max(vals)
@@ -162,7 +162,12 @@ def ncu_traffic(kernel_substr):
     if not os.path.exists(path):
         return None
     mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-    for k in json.load(open(path)):
+    ks = []
+    for name in ('r2_ncu_full_summary.json', 'r1_ncu_full_summary.json'):
+        pth = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(pth):
+            ks += json.load(open(pth))
+    for k in ks:
         if kernel_substr in k['kernel']:
             tot = 0.0
             for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
@@ -421,27 +426,54 @@ def run_gpu(args):
     value = total_sites * n_edges / (ms * 1e-3)
     e2e_value = total_sites * n_edges / (ms_e2e * 1e-3)
 
-    # roofline of the dominant kernel (down pass: root + one launch per level)
+    # roofline of the dominant kernel
     peaks, peak_kind = measured_peaks()
     torch.cuda.synchronize()
     pair = lambda L: [(L[i], L[i + 1]) for i in range(0, len(L) - 1, 2)]
-    up_ms = float(np.mean([a.elapsed_time(b) for a, b in pair(sub['up'])]))
-    down_ms = float(np.mean([a.elapsed_time(b) for a, b in pair(sub['down'])]))
-    up_b, down_b = c2_bytes_per_site(sched, S)
-    down_gbs = N * down_b / (down_ms * 1e-3) / 1e9
-    up_gbs = N * up_b / (up_ms * 1e-3) / 1e9
-    roofline = dict(bound='hbm', kernel='down_walk_kernel<4,codes> (1 launch/step, %.0f%% of the step)'
-                    % (100 * down_ms / ms), achieved=down_gbs, peak=peaks['hbm_gbs'], unit='GB/s',
-                    frac=down_gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
-                    traffic=ncu_traffic('down_walk_kernel<4, 0'),
-                    algorithmic_bytes_per_launch=N * down_b, ms=down_ms,
-                    note='S=4 walk is issue / FP64-pipe bound, not HBM bound (ncu, profiles/'
-                         'r1_ncu_full_summary.json: issue active 53%, fp64 pipe 38%, dram 18%); it reads '
-                         'each stored partial exactly once (dram bytes = algorithmic bytes)',
-                    also=dict(kernel='prune_small_kernel<4,codes,store>', achieved=up_gbs,
-                              frac=up_gbs / peaks['hbm_gbs'], ms=up_ms,
-                              algorithmic_bytes_per_launch=N * up_b,
-                              traffic=ncu_traffic('prune_small_kernel<4, 0, 1')))
+    n_int, n_leaf = sched.n_store, len(sched.leaves)
+    n_int_edges = n_edges - n_leaf
+    if 'fused' in sub:
+        # ONE kernel does the up pass, root combine, down walk and W accumulation of a site tile;
+        # the partials stay in an L2-resident per-CTA scratch, so the algorithmic HBM bytes are the
+        # leaf codes + status + log-lik: (L + 1 + 8) per site
+        f_ms = float(np.mean([a.elapsed_time(b) for a, b in pair(sub['fused'])]))
+        b_site = n_leaf + 9
+        gbs = N * b_site / (f_ms * 1e-3) / 1e9
+        # algorithmic FP64 work per site: up 2S^2+S per internal edge, S per leaf
+        # edge, S per rescale, 2S root; down 6S^2+2S per internal edge (m, G, D_child, W), 2S per leaf
+        flop_site = (n_int_edges * (2 * S * S + S) + n_leaf * S + n_int * S + 2 * S +
+                     n_int_edges * (6 * S * S + 2 * S) + n_leaf * 2 * S)
+        tfl = N * flop_site / (f_ms * 1e-3) / 1e12
+        fma_peak = fp64_peak('dfma')
+        roofline = dict(bound='hbm', kernel='fused_small_kernel<4,codes> (1 launch/step, %.0f%% of the step)'
+                        % (100 * f_ms / ms), achieved=gbs, peak=peaks['hbm_gbs'], unit='GB/s',
+                        frac=gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
+                        traffic=ncu_traffic('fused_small_kernel<4, 0'),
+                        algorithmic_bytes_per_launch=N * b_site, ms=f_ms,
+                        fp64_pipe=dict(achieved=tfl, peak=fma_peak, unit='TFLOP/s', frac=tfl / fma_peak,
+                                       algorithmic_flop_per_site=flop_site,
+                                       peak_source='tools/fp64_peak.cu DFMA probe (profiles/r1_fp64_peak.jsonl)'),
+                        note='the S=4 evaluation is bound by issue slots / the FP64 pipe, not by HBM: '
+                             'fusing the up pass and the down walk removed the 2 x %d B/site of stored '
+                             'partials from HBM (they live in an L2-resident per-CTA scratch), which '
+                             'LOWERS the HBM fraction while making the step faster; the HBM-bound form of '
+                             '4-state pruning is the dense-emission input (extra.c2_loglik_only)'
+                             % (n_int * S * 8))
+    else:
+        up_ms = float(np.mean([a.elapsed_time(b) for a, b in pair(sub['up'])]))
+        down_ms = float(np.mean([a.elapsed_time(b) for a, b in pair(sub['down'])]))
+        up_b, down_b = c2_bytes_per_site(sched, S)
+        down_gbs = N * down_b / (down_ms * 1e-3) / 1e9
+        up_gbs = N * up_b / (up_ms * 1e-3) / 1e9
+        roofline = dict(bound='hbm', kernel='down_walk_kernel<4,codes> (1 launch/step, %.0f%% of the step)'
+                        % (100 * down_ms / ms), achieved=down_gbs, peak=peaks['hbm_gbs'], unit='GB/s',
+                        frac=down_gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
+                        traffic=ncu_traffic('down_walk_kernel<4, 0'),
+                        algorithmic_bytes_per_launch=N * down_b, ms=down_ms,
+                        also=dict(kernel='prune_small_kernel<4,codes,store>', achieved=up_gbs,
+                                  frac=up_gbs / peaks['hbm_gbs'], ms=up_ms,
+                                  algorithmic_bytes_per_launch=N * up_b,
+                                  traffic=ncu_traffic('prune_small_kernel<4, 0, 1')))
 
     # ---- strong scaling beside the weak figure: 1e6 sites IN TOTAL, 1/N of them on this rank
     strong = None
@@ -513,7 +545,8 @@ def run_gpu(args):
                             reference_as_is=reference_as_is_record())
 
     if rank == 0:
-        launches_per_step = 2 + 1 + 1 + 4    # expm (2), up, down walk, Frechet contraction (3) + edge accumulation (1)
+        # expm (2), fused up+down (1; or up + down walk), Frechet contraction (3) + edge accumulation (1)
+        launches_per_step = 2 + (1 if 'fused' in sub else 2) + 4
         line = dict(
             metric='site_edge_messages_per_sec', value=value, unit='messages/s', n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,

@@ -198,6 +198,27 @@ int rt_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pit
                     size_t width_bytes, size_t height, int to_device, void* stream);
 
 /*
+ * FUSED evaluation for S <= 4: upward pruning, root combine, downward pass and per-edge
+ * statistics in ONE persistent kernel -- the batched form of the whole per-site chain of
+ * _mjp_dense.get_expected_history_statistics (raoteh/sampler/_mjp_dense.py:410-539:
+ * pyfelscore.mcy_esd_get_node_to_pmap _mcy_dense.py:286-291, _mc0_dense.get_likelihood
+ * _mc0_dense.py:147-212, mc0_esd_get_node_to_distn _mc0_dense.py:381, mc0_esd_get_joint_endpoint_distn
+ * _mcy_dense.py:205, accumulation :502-533) when the caller wants neither the stored partials nor
+ * the node marginals.  Same arguments as rt_prune_loglik + rt_posterior_stats; the partials of a
+ * site tile live in a per-CTA scratch (private workspace pool) that stays L2 resident, so HBM sees
+ * the observations in and loglik / status out.  n_store = number of internal nodes.
+ * Outputs: loglik[n_sites], status[n_sites]; += loglik_sum[1] (nullable), W[n_nodes][S][S],
+ * root_post_sum[S] (nullable).  ctas_per_sm: 0 = as many as fit.
+ * *handled = 0 (and RT_OK) when the shape is not covered (S > 4, or a program whose tables exceed
+ * the shared-memory budget): the caller then runs rt_prune_loglik + rt_posterior_stats.
+ */
+int rt_posterior_fused(int S, int n_nodes, int n_store, int64_t n_sites, int64_t site_stride,
+                       const int32_t* program, int n_ops, int n_slots, const double* P,
+                       const double* root_distn, int obs_kind, const void* obs, double* loglik,
+                       int8_t* status, double* loglik_sum, double* W, double* root_post_sum,
+                       int ctas_per_sm, int* handled, void* stream);
+
+/*
  * Materialised per-edge joints and all-node marginals for small batches
  * (n_sites <= 65535):  J[b][site][a][c] = D[parent(b)][a] * norm(P_b[a,:] L_b)[c],
  * D_all[b][site][c] = sum_a J[b][site][a][c].  edges: all rows of the downward

@@ -83,6 +83,9 @@ int rt_posterior_dmma_dispatch(int, int, int64_t, int64_t, const int32_t*, const
                                cudaStream_t);
 
 int rt_raoteh_dispatch(const rt_raoteh_args&, cudaStream_t);
+int rt_fused_small_dispatch(int, int, int64_t, int64_t, const int32_t*, int, int, int, int, const double*,
+                            const double*, const void*, double*, int8_t*, double*, double*, double*,
+                            int, cudaStream_t, bool*);
 
 int rt_tmjp_dispatch(const rt_tmjp_args&, cudaStream_t);
 
@@ -238,6 +241,25 @@ int rt_posterior_branch_stats(int S, int n_nodes, int64_t n_sites, int64_t site_
   return posterior_common(S, n_nodes, n_sites, site_stride, program, n_ops, n_slots, edges,
                           level_ptr_h, n_levels, P, root_distn, obs_kind, obs, partials, status,
                           node_distn, W, root_post_sum, K, branch_out, stream);
+}
+
+int rt_posterior_fused(int S, int n_nodes, int n_store, int64_t n_sites, int64_t site_stride,
+                       const int32_t* program, int n_ops, int n_slots, const double* P,
+                       const double* root_distn, int obs_kind, const void* obs, double* loglik,
+                       int8_t* status, double* loglik_sum, double* W, double* root_post_sum,
+                       int ctas_per_sm, int* handled, void* stream) {
+  if (!program || !P || !loglik || !status || !W || !handled) return arg_error("null pointer");
+  if (obs_kind < 0 || obs_kind > 3) return arg_error("obs_kind");
+  if (site_stride < n_sites) return arg_error("site_stride < n_sites");
+  *handled = 0;
+  if (n_ops <= 0 || n_slots <= 0 || n_nodes <= 1 || n_store <= 0) return arg_error("empty program");
+  if (n_sites <= 0) { *handled = 1; return RT_OK; }
+  bool h = false;
+  int rc = rt_fused_small_dispatch(S, obs_kind, n_sites, site_stride, program, n_ops, n_slots, n_nodes,
+                                   n_store, P, root_distn, obs, loglik, status, loglik_sum, W,
+                                   root_post_sum, ctas_per_sm, (cudaStream_t)stream, &h);
+  *handled = h ? 1 : 0;
+  return rc;
 }
 
 int rt_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,

@@ -108,7 +108,11 @@ def _check_history(ch, t, sched, parent, length, leaves, codes, site):
 def test_c4_shape_sweeps_match_closed_form(rt, time_dtype):
     """BASELINE configs[3]: the 127-node tree.  Mean dwell times / transition counts of the sampled
     histories against _mjp.get_expected_history_statistics (closed form, oracle), |z| < 5 with the
-    standard error from 16 independent groups of chains; both event-time precisions."""
+    standard error from 16 independent groups of chains; both event-time precisions.
+    Burn-in: on this tree the sampler needs several hundred sweeps to forget the initial history
+    (one event in the middle of every branch) -- at 60 sweeps of burn-in a transition count sits
+    5-10 standard errors off (relative 1e-3 .. 2e-2), at 1000 every statistic is inside 3.5
+    (tools/diag_c4_bias.py, run on the B200; float32 and fp64 times give the same z-scores)."""
     from raoteh_b200 import synth
     from raoteh_b200.lowering import TreeSchedule
     from raoteh_b200.raoteh import RaoTehChains
@@ -121,7 +125,7 @@ def test_c4_shape_sweeps_match_closed_form(rt, time_dtype):
     P = np_oracle.expm_edges(Q, length)
     o = np_oracle.expected_history_statistics(
         parent, length, Q, P, np_oracle.Obs('codes', 4, n_sites, leaf_nodes=leaves, codes=codes), pi)
-    groups, n_chains, burn, n_sweeps = 16, 512, 60, 100
+    groups, n_chains, burn, n_sweeps = 16, 512, 1000, 200
     dwell = np.zeros((groups, 4))
     trans = np.zeros((groups, 4, 4))
     for g in range(groups):

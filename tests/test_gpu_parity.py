@@ -502,3 +502,68 @@ def test_packed_codes4_are_bit_identical_to_uint8_codes(S, n_sites):
     assert torch.equal(out_ll, a['loglik'].cpu()) and torch.equal(out_st, a['status'].cpu())
     np.testing.assert_allclose(r['dwell'].cpu().numpy(), a['dwell'].cpu().numpy(), rtol=1e-12)
     np.testing.assert_allclose(r['trans'].cpu().numpy(), a['trans'].cpu().numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize('S,n_leaves,n_sites,kind', [(4, 32, 3001, 'codes'), (4, 32, 777, 'codes4'), (3, 9, 515, 'codes'),
+                                                     (2, 6, 300, 'mask'), (4, 11, 1300, 'mask'), (4, 7, 600, 'dense')])
+def test_fused_small_kernel_matches_oracle(rt, S, n_leaves, n_sites, kind):
+    """rt_posterior_fused (S <= 4: up pass, root combine, down walk and W accumulation in one
+    persistent kernel, partials in a per-CTA scratch) against the oracle and against the two-kernel
+    path, for every observation encoding, ragged site counts, missing cells and a reducible rate
+    matrix with infeasible sites (_mjp_dense.py:410-539)."""
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200 import synth
+    rng = np.random.default_rng(900 + S + n_leaves)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.1, rng)
+    if S == 4:
+        Q, pi = synth.hky85()
+    else:
+        Q = rng.exponential(1.0, size=(S, S))
+        np.fill_diagonal(Q, 0)
+        if S == 3:
+            Q[2, :] = 0.0                 # absorbing state: structural zeros in P, infeasible sites
+        Q -= np.diag(Q.sum(axis=1))
+        pi = rng.dirichlet(np.ones(S))
+    n = len(parent)
+    sched = TreeSchedule(parent, length)
+    P = np_oracle.expm_edges(Q, length)
+    if kind in ('codes', 'codes4'):
+        codes = synth.simulate_leaf_codes(parent, length, leaves, Q if S != 3 else Q + 0.3 * (1 - np.eye(3)) - 0.6 * np.eye(3),
+                                          pi, n_sites, rng, 0.05)
+        obs = (rt.Observations.from_leaf_codes4 if kind == 'codes4' else rt.Observations.from_leaf_codes)(
+            sched, codes, leaves)
+        oobs = np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes)
+    elif kind == 'mask':
+        bits = rng.random((n, n_sites, S)) < 0.5
+        bits[np.arange(n)[:, None], np.arange(n_sites)[None, :], rng.integers(0, S, size=(n, n_sites))] = True
+        unrestricted = rng.random((n, n_sites)) < 0.6
+        unrestricted[leaves] = rng.random((len(leaves), n_sites)) < 0.1
+        bits[unrestricted] = True
+        mask = (bits.astype(np.uint64) << np.arange(S, dtype=np.uint64)[None, None, :]).sum(axis=2).astype(np.uint64)
+        obs = rt.Observations.from_masks(sched, mask)
+        oobs = np_oracle.Obs('mask', S, n_sites, mask=mask)
+    else:
+        nodes = np.concatenate([leaves, sched.internal[1:3]])
+        lik = rng.random((len(nodes), S, n_sites)) ** 3
+        obs = rt.Observations.from_dense(sched, lik, nodes)
+        full = np.ones((n, n_sites, S))
+        has = np.zeros(n, dtype=bool)
+        has[nodes] = True
+        full[nodes] = lik.transpose(0, 2, 1)
+        oobs = np_oracle.Obs('dense', S, n_sites, lik=full, has=has)
+    o = np_oracle.expected_history_statistics(parent, length, Q, P, oobs, pi)
+    res = {}
+    for fused in (True, False):
+        mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+        mjp.fused = fused
+        r = mjp.expected_history_statistics(obs)
+        assert (r['partials'] is None) == fused        # the fused path really ran (no stored partials)
+        res[fused] = r
+        ok = np.isfinite(o['loglik'])
+        assert ((r['status'].cpu().numpy() == 0) == ok).all()
+        np.testing.assert_allclose(r['loglik'].cpu().numpy()[ok], o['loglik'][ok], rtol=RTOL)
+        np.testing.assert_allclose(float(r['loglik_sum']), o['loglik'][ok].sum(), rtol=1e-10)
+        np.testing.assert_allclose(r['dwell'].cpu().numpy(), o['dwell'], rtol=RTOL)
+        np.testing.assert_allclose(r['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(r['root_post_sum'].cpu().numpy(), o['root_post'].sum(axis=0), rtol=RTOL)
+    np.testing.assert_allclose(res[True]['W'].cpu().numpy(), res[False]['W'].cpu().numpy(), rtol=1e-11, atol=1e-13)
