@@ -172,3 +172,23 @@ def get_expected_history_statistics(T, node_to_allowed_states, root, root_distn=
                 trans.add_edge(sc, sd, weight=0.0)
             trans[sc][sd]['weight'] += Q[sc][sd]['weight'] * M[i, index[sc], index[sd]]
     return dict(dwell), _sparse.vec_to_dict(D[0], states), trans
+
+
+def differential_entropy_helper(Q, prior_root_distn, post_root_distn, post_dwell_times,
+                                post_transitions):
+    """raoteh/sampler/_mjp.py:255-306: the three contributions (initial state, dwell times,
+    transitions) to the expected negative log-likelihood of a trajectory, from posterior
+    expectations such as those of get_expected_history_statistics."""
+    from scipy import special
+    total_rates = get_total_rates(Q)
+    diff_ent_init = 0.0
+    for state, prob in post_root_distn.items():
+        diff_ent_init -= special.xlogy(prob, prior_root_distn[state])
+    diff_ent_dwell = 0.0
+    for s in set(total_rates) & set(post_dwell_times):
+        diff_ent_dwell += post_dwell_times[s] * total_rates[s]
+    diff_ent_trans = 0.0
+    for sa in set(Q) & set(post_transitions):
+        for sb in set(Q[sa]) & set(post_transitions[sa]):
+            diff_ent_trans -= special.xlogy(post_transitions[sa][sb]['weight'], Q[sa][sb]['weight'])
+    return diff_ent_init, diff_ent_dwell, diff_ent_trans

@@ -249,3 +249,12 @@ def get_forward_sample(T, Q, root, root_distn):
         node_to_state[b] = state
         T_out.add_edge(prev_node, b, state=state, weight=weight - total_dwell)
     return T_out
+
+
+def gen_forward_samples(T, Q, root, root_distn, nsamples=None):
+    """raoteh/sampler/_sampler.py:67-160: unconditional forward samples, one augmented tree per
+    draw (host code like the reference: it makes test data, it is not on the accelerated path)."""
+    for i in itertools.count():
+        if i == nsamples:
+            return
+        yield get_forward_sample(T, Q, root, root_distn)

@@ -92,3 +92,46 @@ def get_tolerance_summary(ctm, T_primary, root, disease_data=None):
 def get_tolerance_ll_contribs(rate_on, rate_off, total_tree_length, *summary):
     """raoteh/sampler/_tmjp.py:744-812"""
     return _tmjp_dense.get_tolerance_ll_contribs(rate_on, rate_off, total_tree_length, *summary)
+
+
+def get_tolerance_process_log_likelihood(ctm, T_primary, root):
+    """raoteh/sampler/_tmjp.py:406-490: compound log-likelihood of a primary trajectory with the
+    tolerance histories integrated out (sparse inputs; evaluated by the dense twin)."""
+    if root is None:
+        raise ValueError('unspecified root')
+    if root not in T_primary:
+        raise ValueError('the specified root is not a node in the tree')
+    states, index, Q, distn, part = ctm._dense()
+    T_dense = nx.Graph()
+    for a, b, d in T_primary.edges(data=True):
+        T_dense.add_edge(a, b, weight=d['weight'], state=index[d['state']])
+    if len(T_primary) == 1:
+        T_dense.add_node(root)
+    return _tmjp_dense.get_tolerance_process_log_likelihood(
+        Q, part, T_dense, ctm.rate_off, ctm.rate_on, distn, root)
+
+
+def differential_entropy_helper(ctm, post_root_distn, post_dwell_times, post_transitions):
+    """raoteh/sampler/_tmjp.py:217-349: sparse inputs (dicts over compound states, DiGraph of
+    expected transition counts) -> CompoundNegLL, through the dense twin on a dense compound model
+    with the same state numbering (itertools.product order, raoteh/sampler/_tmjp.py:75-83)."""
+    states, index, Q, distn, part = ctm._dense()
+    dense = _tmjp_dense.CompoundToleranceModel(Q, distn, part, ctm.rate_on, ctm.rate_off)
+    dense.init_compound()
+    # the sparse model has transitions only between states of positive prior probability
+    # (raoteh/sampler/_tmjp.py:117-119); the dense one also between the formal infeasible states
+    ok = np.asarray(dense.compound_distn) > 0
+    Qc = np.where(ok[:, None] & ok[None, :], dense.Q_compound, 0.0)
+    np.fill_diagonal(Qc, 0.0)
+    dense.Q_compound = Qc - np.diag(Qc.sum(axis=1))
+    n = dense.ncompound
+    root = np.zeros(n)
+    for k, v in post_root_distn.items():
+        root[k] = v
+    dwell = np.zeros(n)
+    for k, v in post_dwell_times.items():
+        dwell[k] = v
+    trans = np.zeros((n, n))
+    for a, b, d in post_transitions.edges(data=True):
+        trans[a, b] = d['weight']
+    return _tmjp_dense.differential_entropy_helper(dense, root, dwell, trans)

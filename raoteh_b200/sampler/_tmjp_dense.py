@@ -145,6 +145,117 @@ def get_tolerance_ll_contribs(rate_on, rate_off, total_tree_length,
     return init_ll, dwell_prim, dwell_tol, trans_ll
 
 
+def get_tolerance_process_log_likelihood(Q_primary, primary_to_part, T_primary,
+                                         rate_off, rate_on, primary_root_distn, root):
+    """raoteh/sampler/_tmjp_dense.py:407-505: log-likelihood of a primary trajectory under the
+    compound process with the tolerance histories integrated out -- log prior of the root state,
+    xlogy(count, rate) over the primary transitions, and per tolerance class the log-likelihood of
+    its piecewise homogeneous 3-state process (rt_expm_batched + rt_prune_loglik with one rate
+    matrix per edge).  The batched device form is column 7 of the tolerance summary
+    (raoteh_b200.tmjp.ToleranceChains.tolerance_log_likelihood)."""
+    from . import _mjp_dense
+    if root is None:
+        raise ValueError('unspecified root')
+    if root not in T_primary:
+        raise ValueError('the specified root is not a node in the tree')
+    check_square_dense(Q_primary)
+    nprimary = len(primary_to_part)
+    tolerance_distn = get_three_state_tolerance_distn(rate_off, rate_on)
+    root_state, transitions = _mjp_dense.get_history_root_state_and_transitions(
+        T_primary, nprimary, root=root)
+    log_likelihood = np.log(primary_root_distn[root_state])
+    off = ~np.eye(nprimary, dtype=bool)
+    log_likelihood += special.xlogy(transitions[off], np.asarray(Q_primary)[off]).sum()
+    edges = list(nx.bfs_edges(T_primary, root))
+    for tolerance_class in sorted(set(primary_to_part.values())):
+        if primary_to_part[root_state] == tolerance_class:
+            prior = np.array([0.0, 1.0, 0.0])
+        else:
+            prior = tolerance_distn
+        T_tol, allowed = get_inhomogeneous_mjp(primary_to_part, rate_on, rate_off, Q_primary,
+                                               T_primary, root, edges, tolerance_class)
+        likelihood = _mjp_dense.get_likelihood(T_tol, allowed, root, 3, root_distn=prior, Q_default=None)
+        log_likelihood += np.log(likelihood)
+    return log_likelihood
+
+
+class CompoundNegLL(object):
+    """raoteh/sampler/_tmjp_util.py:4-25"""
+
+    def __init__(self, init_prim, init_tol, dwell_prim, dwell_tol, trans_prim, trans_tol):
+        self.init_prim, self.init_tol = init_prim, init_tol
+        self.dwell_prim, self.dwell_tol = dwell_prim, dwell_tol
+        self.trans_prim, self.trans_tol = trans_prim, trans_tol
+
+    @property
+    def init(self):
+        return self.init_prim + self.init_tol
+
+    @property
+    def dwell(self):
+        return self.dwell_prim + self.dwell_tol
+
+    @property
+    def trans(self):
+        return self.trans_prim + self.trans_tol
+
+
+def differential_entropy_helper(ctm, post_root_distn, post_dwell_times, post_transitions):
+    """raoteh/sampler/_tmjp_dense.py:508-721 (sparse twin _tmjp.py:217-349): the negative expected
+    log-likelihood of the compound trajectory from posterior expectations over the COMPOUND state
+    space (1-D root posterior and dwell times, 2-D expected transition counts), separated into
+    primary / tolerance parts of the initial-state, dwell and transition terms.  Vectorised over
+    the compound states; the three consistency checks of the reference are kept."""
+    from . import _mjp_dense
+    if ctm.Q_compound is None:
+        raise ValueError('call ctm.init_compound() first')
+    Qc = np.asarray(ctm.Q_compound, dtype=float)
+    n = ctm.ncompound
+    post_root = np.asarray(post_root_distn, dtype=float)
+    dwell = np.asarray(post_dwell_times, dtype=float)
+    trans = np.asarray(post_transitions, dtype=float)
+    init, dwl, trn = _mjp_dense.differential_entropy_helper(
+        Qc, np.asarray(ctm.compound_distn, dtype=float), post_root, dwell, trans)
+    prim = np.asarray(ctm.compound_to_primary)
+    tols = np.asarray(ctm.compound_to_tolerances)
+    part_of = np.array([ctm.primary_to_part[p] for p in range(ctm.nprimary)])
+    # initial state (states with zero posterior mass are skipped, :608-652): primary prior, then
+    # the tolerance classes other than the primary state's own
+    sel = post_root != 0
+    init_prim = -special.xlogy(post_root[sel], np.asarray(ctm.primary_distn, dtype=float)[prim[sel]]).sum()
+    own_on = tols[np.arange(n), part_of[prim]] == 1
+    on_count = tols.sum(axis=1)
+    off_count = ctm.nparts - on_count
+    t_off, t_on = ctm.tolerance_distn[0], ctm.tolerance_distn[1]
+    init_tol = 0.0
+    if (sel & ~own_on).any():
+        init_tol = np.inf          # the reference assigns an infinite cost to such a formal state
+    if (sel & (on_count > 0)).any():
+        m = sel & (on_count > 0)
+        init_tol = (init_tol - special.xlogy(post_root[m] * (on_count[m] - 1), t_on).sum()) if t_on else np.inf
+    if (sel & (off_count > 0)).any():
+        m = sel & (off_count > 0)
+        init_tol = (init_tol - special.xlogy(post_root[m] * off_count[m], t_off).sum()) if t_off else np.inf
+    if not np.allclose(init_prim + init_tol, init):
+        raise Exception('internal differential entropy calculation error: %s + %s = %s but expected %s'
+                        % (init_prim, init_tol, init_prim + init_tol, init))
+    # dwell times (:667-690): tolerance part = blinking of the other classes, primary part = rates
+    # of primary changes out of the compound state
+    dwell_tol = float((dwell * off_count * ctm.rate_on + dwell * (on_count - 1) * ctm.rate_off).sum())
+    same_prim = prim[:, None] == prim[None, :]
+    absorption = np.where(~same_prim, Qc, 0.0).sum(axis=1)
+    dwell_prim = float((dwell * absorption).sum())
+    if not np.allclose(dwell_prim + dwell_tol, dwl):
+        raise Exception('internal error')
+    # transitions (:697-707): every ordered pair, split by whether the primary state changes
+    x = special.xlogy(trans, Qc)
+    trans_prim = -x[~same_prim].sum()
+    trans_tol = -x[same_prim].sum()
+    if not np.allclose(trans_prim + trans_tol, trn):
+        raise Exception('internal error')
+    return CompoundNegLL(init_prim, init_tol, dwell_prim, dwell_tol, trans_prim, trans_tol)
+
+
 # ---------------------------------------------------------------------------
 # the compound tolerance model (raoteh/sampler/_tmjp_dense.py:35-179)
 # ---------------------------------------------------------------------------

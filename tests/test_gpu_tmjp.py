@@ -754,3 +754,38 @@ def test_code2x3_blinking_model_golden_values_by_sampling(level):
     for a, s, w in zip(m, se, want):
         assert abs(a - w) < 5 * s, (level, m, se, want)
     assert (se < 0.02 * want).all()
+
+
+def test_scalar_tolerance_process_log_likelihood_matches_reference_fixture():
+    """_tmjp.get_tolerance_process_log_likelihood (raoteh/sampler/_tmjp.py:406-490) and its dense
+    twin (_tmjp_dense.py:407-505), the scalar mirrors: against the values the reference itself
+    returned for the fixture trajectories (relative 1e-9: the 3 x 3 pieces go through the generic
+    fp64 path, rt_expm_batched + rt_prune_loglik with one rate matrix per edge)."""
+    import networkx as nx
+    from raoteh_b200.sampler import _tmjp, _tmjp_dense
+    g = load_golden('tolerance_summary.json')
+    Q = np.array(g['Q_primary'])
+    part = dict((i, g['primary_to_part'][str(i)]) for i in range(6))
+    distn = np.ones(6) / 6
+    Qs = nx.DiGraph()
+    for a in range(6):
+        for b in range(6):
+            if a != b and Q[a, b] > 0:
+                Qs.add_edge(a, b, weight=Q[a, b])
+    n = 0
+    for case in g['cases']:
+        if case['disease'] is not None or 'tol_ll' not in case:
+            continue
+        T = nx.Graph()
+        for a, b, w, s in case['edges']:
+            T.add_edge(a, b, weight=w, state=s)
+        got = _tmjp_dense.get_tolerance_process_log_likelihood(
+            Q, part, T, case['rate_off'], case['rate_on'], distn, case['root'])
+        np.testing.assert_allclose(got, case['tol_ll'], rtol=1e-9)
+        ctm = _tmjp.CompoundToleranceModel(Qs, dict(enumerate(distn)), part, case['rate_on'], case['rate_off'])
+        got = _tmjp.get_tolerance_process_log_likelihood(ctm, T, case['root'])
+        np.testing.assert_allclose(got, case['tol_ll'], rtol=1e-9)
+        n += 1
+        if n >= 6:
+            break
+    assert n >= 3
