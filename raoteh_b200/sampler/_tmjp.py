@@ -133,5 +133,6 @@ def differential_entropy_helper(ctm, post_root_distn, post_dwell_times, post_tra
         dwell[k] = v
     trans = np.zeros((n, n))
     for a, b, d in post_transitions.edges(data=True):
-        trans[a, b] = d['weight']
+        if a != b and Qc[a, b] > 0:        # only transitions the sparse model has (:329-331)
+            trans[a, b] = d['weight']
     return _tmjp_dense.differential_entropy_helper(dense, root, dwell, trans)
