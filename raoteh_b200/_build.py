@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     '-O3', '-lineinfo', '-std=c++17',
     '-Xcompiler', '-fPIC',
     '--expt-relaxed-constexpr',
-]
+] + os.environ.get('RT_EXTRA_NVCC_FLAGS', '').split()
 
 
 def sources():

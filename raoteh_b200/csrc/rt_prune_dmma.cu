@@ -36,10 +36,34 @@ namespace {
 // sub-partition.  1: 16 warps x 8 sites, <= 128 registers, four warps per sub-partition (more warps
 // to cover the latency-bound bookkeeping between the DMMA phases, at 1.125 instead of 0.625
 // shared-memory fragment loads per DMMA).  RT_PRUNE_DMMA_NT selects at run time.
+#ifndef RT_PD_PROFILE
+#define RT_PD_PROFILE 0
+#endif
+#if RT_PD_PROFILE
+// per-phase cycle counters of the pruning kernel (debug builds only: -DRT_PD_PROFILE=1), summed
+// over warps: 0 tile loop, 1 leaf gathers, 2 B-tile fills, 3 wait for P_c, 4 wait for the pipe
+// token, 5 DMMA loop, 6 release + product, 7 store / root, 8 code staging, 9 other ops
+__device__ unsigned long long g_pd_prof[16];
+#define RT_PROF_DECL long long prof_t0 = 0, prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define RT_PROF_BEGIN prof_t0 = clock64();
+#define RT_PROF_END(k) prof_acc[k] += clock64() - prof_t0;
+#else
+#define RT_PROF_DECL
+#define RT_PROF_BEGIN
+#define RT_PROF_END(k)
+#endif
 constexpr int kTileSites = 128;        // sites per CTA tile = (16 / NT) warps x 8 NT sites
 constexpr int kMaxSlots = 32;
-constexpr int kRing = 3;               // P_c buffers
-constexpr int kMaxCodeBytes = 24 * 1024;   // shared-memory budget of the staged leaf codes
+#ifndef RT_PD_RING
+#define RT_PD_RING 3
+#endif
+#ifndef RT_PD_CODE_KB
+#define RT_PD_CODE_KB 24
+#endif
+// (Tried: two P_c buffers and no staged codes, i.e. <= 164 KB of shared memory and ~90 KB of L1
+// for the leaf-edge column gathers -- no gain, profiles/r2_prune_dmma_variants.md.)
+constexpr int kRing = RT_PD_RING;          // P_c buffers
+constexpr int kMaxCodeBytes = RT_PD_CODE_KB * 1024;   // shared-memory budget of the staged leaf codes (0: L1)
 // defaults chosen by measurement on B200 at C3 size (profiles/r2_prune_dmma_variants.md)
 constexpr int kDefaultNT = 1;
 constexpr int kDefaultPingpong = 0;
@@ -128,7 +152,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
   __shared__ __align__(8) uint64_t full_bar[kRing];
   __shared__ int done_cnt[kRing];
   __shared__ volatile int turn_s[4];
-  __shared__ int counts_s[2];      // staged edges per tile, observation rows to stage
+  __shared__ int counts_s[3];      // staged edges per tile, observation rows to stage, observation rows
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -160,9 +184,10 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
     counts_s[0] = k;
     // the tile's leaf codes are staged in shared memory when they fit, else read from global
     counts_s[1] = (OBS == OBS_CODES && rows * kTileSites <= code_capacity) ? rows : 0;
+    counts_s[2] = rows;
   }
   __syncthreads();
-  const int n_staged = counts_s[0], n_code_rows = counts_s[1];
+  const int n_staged = counts_s[0], n_code_rows = counts_s[1], code_rows_all = counts_s[2];
   uint8_t* codes_w = codes_s + (size_t)warp * n_code_rows * kWarpSites;
 
   const int64_t tiles = (n_sites + kTileSites - 1) / kTileSites;
@@ -196,7 +221,12 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
   };
 
   double my_ll = 0.0;
+  RT_PROF_DECL
+#if RT_PD_PROFILE
+  const long long prof_start = clock64();
+#endif
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    RT_PROF_BEGIN
     // the sites this thread's C-fragment columns map to
     const int64_t site0 = tile * kTileSites + warp * kWarpSites;
     int64_t csite[kNT][2];
@@ -229,9 +259,17 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
       }
       __syncwarp();
     }
+    if (OBS == OBS_CODES && n_code_rows == 0 && code_rows_all > 0) {
+      // codes are read through L1: pull the tile's 128-byte row segments in now
+      const uint8_t* codes = reinterpret_cast<const uint8_t*>(obs);
+      const int64_t t0 = tile * kTileSites;
+      for (int r = tid; r < code_rows_all; r += kThreads)
+        if (warp == 0 || true) asm volatile("prefetch.global.L1 [%0];" :: "l"(codes + (int64_t)r * stride + t0));
+    }
+    RT_PROF_END(8)
     auto code_of = [&](int row, int j, int h) -> int {
       if (n_code_rows > 0) return codes_w[row * kWarpSites + 8 * j + 2 * t + h];
-      return cvalid[j][h] ? reinterpret_cast<const uint8_t*>(obs)[(int64_t)row * stride + csite[j][h]]
+      return cvalid[j][h] ? __ldg(reinterpret_cast<const uint8_t*>(obs) + (int64_t)row * stride + csite[j][h])
                           : RT_MISSING;
     };
 
@@ -252,6 +290,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
       const int code = op.x & 0xff;
       const bool fresh = (op.x >> 8) & 1;
 
+      RT_PROF_BEGIN
       if (code == OP_MSG_OBS && OBS == OBS_CODES) {
         // ---- leaf with hard codes: the message is column k of P_c = row k of PT_c (no flops) ----
         const double* PTc = PT + (size_t)op.y * SP * SP;
@@ -300,6 +339,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
               }
             }
         }
+        RT_PROF_END(1)
         continue;
       }
       if (needs_stage(op)) {
@@ -353,9 +393,13 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
           }
         }
         __syncwarp();
+        RT_PROF_END(2)
+        RT_PROF_BEGIN
 
         // ---- wait for P_c and (optionally) for this warp's turn on the sub-partition's tensor pipe ----
         mbar_wait(&full_bar[buf], parity);
+        RT_PROF_END(3)
+        RT_PROF_BEGIN
         if (pingpong == 1) {          // strict rotation among the sub-partition's warps
           if (lane == 0)
             while (turn_s[pair] != my_turn) __nanosleep(20);
@@ -365,6 +409,8 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
             while (atomicCAS(const_cast<int*>(&turn_s[pair]), 0, 1) != 0) __nanosleep(40);
           __syncwarp();
         }
+        RT_PROF_END(4)
+        RT_PROF_BEGIN
         double msg[MT][kNT][2];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -382,6 +428,11 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
             for (int j = 0; j < kNT; ++j) dmma884(msg[i][j][0], msg[i][j][1], a, bfrag[j]);
           }
         }
+#if RT_PD_PROFILE
+        asm volatile("" :: "d"(msg[0][0][0]), "d"(msg[MT - 1][kNT - 1][1]));
+#endif
+        RT_PROF_END(5)
+        RT_PROF_BEGIN
         if (pingpong) {
           __syncwarp();
           if (lane == 0) turn_s[pair] = pingpong == 1 ? (my_turn + 1) % kTurns : 0;
@@ -400,6 +451,7 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
             for (int j = 0; j < kNT; ++j) { acc[i][j][0] *= msg[i][j][0]; acc[i][j][1] *= msg[i][j][1]; }
         }
         first = false;
+        RT_PROF_END(6)
         continue;
       }
 
@@ -555,8 +607,16 @@ prune_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict
         } break;
         default: break;
       }
+      RT_PROF_END((code == OP_STORE || code == OP_ROOT) ? 7 : 9)
     }
   }
+#if RT_PD_PROFILE
+  if (lane == 0) {
+    atomicAdd(&g_pd_prof[0], (unsigned long long)(clock64() - prof_start));
+    for (int k = 1; k < 10; ++k) atomicAdd(&g_pd_prof[k], (unsigned long long)prof_acc[k]);
+    atomicAdd(&g_pd_prof[10], 1ull);
+  }
+#endif
 
   if (loglik_sum) {
     const double w = rt_warp_sum(my_ll);
@@ -658,3 +718,13 @@ int rt_prune_dmma_dispatch(int S, int obs_kind, bool store, int64_t n_sites, int
   rt_ws_free(ws, stream);
   return rc;
 }
+
+#if RT_PD_PROFILE
+extern "C" int rt_debug_prune_profile(unsigned long long* out11) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out11, g_pd_prof, sizeof(unsigned long long) * 11);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_pd_prof, z, sizeof(z));
+  return 0;
+}
+#endif
