@@ -1,5 +1,6 @@
 // K6: Rao-Teh uniformization sweeps on trees, one thread per (chain, site)
-// trajectory, counter-based Philox4x32-10 RNG.
+// trajectory; counter-based Philox4x32-10 per (trajectory, sweep), which seeds a PCG32 stream for
+// the events inside the sweep.
 //
 // Replaces the reference's per-trajectory Python/networkx sweep
 //   _sampler.gen_restricted_histories loop      raoteh/sampler/_sampler.py:366-390
@@ -155,6 +156,21 @@ raoteh_kernel(SweepArgs<TT> A) {
       // substream 0: root draw (word 0) and the first unit-rate gap (word 1)
       rng.block(0u, 0u);
       const uint32_t u_root = rng.out[0];
+      // Words 2 and 3 of the sweep's Philox block seed a PCG32 (XSH-RR, O'Neill 2014) stream for
+      // the events of this sweep: the Philox block keeps the draw addressable by (seed, trajectory,
+      // sweep) -- results do not depend on launch partitioning or rank count -- while the per-event
+      // cost drops from a ten-round Philox block per edge (~65 instructions, executed by the whole
+      // warp whenever ANY lane starts a block) to ~12 instructions per word.
+      uint64_t pcg_state = ((uint64_t)rng.out[3] << 32) | (uint64_t)rng.out[2];
+      const uint64_t pcg_inc = ((uint64_t)(A.traj0 + traj) << 1) | 1ull;
+      auto pcg_next = [&]() -> uint32_t {
+        const uint64_t old = pcg_state;
+        pcg_state = old * 6364136223846793005ull + pcg_inc;
+        const uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
+        const uint32_t rot = (uint32_t)(old >> 59);
+        return (xs >> rot) | (xs << ((32u - rot) & 31u));
+      };
+      pcg_next();      // one step away from the raw seed
       // Virtual events: a Poisson process of rate omega - q_s on every segment, sampled
       // in HAZARD space.  Walking the segments in program order, `hrem` is the hazard left
       // until the next event (unit-rate exponential gaps); a segment of hazard h consumes
@@ -234,12 +250,9 @@ raoteh_kernel(SweepArgs<TT> A) {
                 else break;
               }
             }
-            // random words of this event: substream = edge op, two events per Philox block
-            if ((kA & 1) == 0) rng.block((uint32_t)ip + 1u, (uint32_t)(kA >> 1));
-            const bool odd = (kA & 1) != 0;
-            const uint32_t u_draw = odd ? rng.out[2] : rng.out[0];
-            const uint32_t u_gap = odd ? rng.out[3] : rng.out[1];
-            if (is_virtual) hrem = TimeOps<TT>::neglog_unit(u_gap);
+            // random words of this event: the sweep's sequential stream (see pcg_next)
+            const uint32_t u_draw = pcg_next();
+            if (is_virtual) hrem = TimeOps<TT>::neglog_unit(pcg_next());
             // record beta just below the event, then push it through B
             if (nA < A.scr_cap) {
               unsigned char* rp = rec_p + (size_t)nA * kRec;
