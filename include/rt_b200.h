@@ -81,6 +81,13 @@ int rt_expm_spectral(const double* A, const double* lam, const double* B, const 
                      const uint8_t* d_off, int n_mat, int S, double* P, void* stream);
 
 /*
+ * P[m] = small-step LOWER BOUND of expm(Q t[m]), m in [0, n_mat): the probability of no change on
+ * the diagonal and of exactly one change a -> b off it (Q: [S][S] with diagonal).
+ * Replaces pyfelscore.get_lb_transition_matrix (examples/p53/liwen.py:43-46; spec getp_lb :48-82).
+ */
+int rt_lb_transition(const double* Q, const double* t, int n_mat, int S, double* P, void* stream);
+
+/*
  * M[m] = L(t[m] Q^T, t[m] W[m]) -- Frechet derivative of expm; equals
  * sum_ab W[m][a][b] * expm_frechet(tQ, t E_cd)[a][b] at entry [c][d].  (S <= 64)
  * Replaces the S + nnz(Q) scipy.linalg.expm_frechet calls per edge per site at

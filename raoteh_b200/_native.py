@@ -25,6 +25,7 @@ EXPORTS = {
                              c_void_p], c_int),
     'rt_expm_spectral': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                           c_void_p], c_int),
+    'rt_lb_transition': ([c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
     'rt_history_statistics': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p], c_int),
     'rt_support_sets': ([c_int, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p,

@@ -63,6 +63,7 @@ int rt_history_statistics_impl(const double*, const int32_t*, const double*, con
                                double*, double*, double*, cudaStream_t);
 int rt_expm_spectral_impl(const double*, const double*, const double*, const double*, const uint8_t*,
                           int, int, double*, cudaStream_t);
+int rt_lb_transition_impl(const double*, const double*, int, int, double*, cudaStream_t);
 int rt_support_sets_impl(int, int, int64_t, int64_t, int, const int32_t*, const double*, uint64_t*, cudaStream_t);
 int rt_joint_distn_impl(int, int, int64_t, int64_t, const int32_t*, int, const double*, const void*,
                         const double*, const double*, const int8_t*, double*, double*, cudaStream_t);
@@ -125,6 +126,12 @@ int rt_expm_spectral(const double* A, const double* lam, const double* B, const 
   if (!A || !lam || !B || !t || !P) return arg_error("null pointer");
   if (S < 1 || S > 64) return unsupported("rt_expm_spectral needs 1 <= S <= 64");
   return rt_expm_spectral_impl(A, lam, B, t, d_off, n_mat, S, P, (cudaStream_t)stream);
+}
+
+int rt_lb_transition(const double* Q, const double* t, int n_mat, int S, double* P, void* stream) {
+  if (!Q || !t || !P) return arg_error("null pointer");
+  if (S < 1 || S > 1024) return unsupported("rt_lb_transition needs 1 <= S <= 1024");
+  return rt_lb_transition_impl(Q, t, n_mat, S, P, (cudaStream_t)stream);
 }
 
 int rt_history_statistics(const double* Q, const int32_t* q_index, const double* t, const double* W,

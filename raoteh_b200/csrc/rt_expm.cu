@@ -481,6 +481,41 @@ expm_spectral_kernel(const double* __restrict__ A, const double* __restrict__ la
 
 }  // namespace
 
+// Lower bound of expm(tQ) over a small step (examples/p53/liwen.py:48-82; pyfelscore.
+// get_lb_transition_matrix): no change on the diagonal, exactly one change a -> b elsewhere,
+//   P[a][a] = exp(t Q[a][a]),  P[a][b] = Q[a][b] (e^{-ra t} - e^{-rb t}) / (rb - ra)   (ra = -Q[a][a]),
+//   -> Q[a][b] t e^{-rb t} when ra == rb.
+__global__ void lb_transition_kernel(const double* __restrict__ Q, const double* __restrict__ t,
+                                     int S, double* __restrict__ P) {
+  const double tm = t[blockIdx.x];
+  double* Pm = P + (size_t)blockIdx.x * S * S;
+  for (int idx = threadIdx.x; idx < S * S; idx += blockDim.x) {
+    const int a = idx / S, b = idx % S;
+    double p;
+    if (a == b) {
+      p = exp(tm * Q[idx]);
+    } else {
+      const double rab = Q[idx];
+      if (rab != 0.0) {
+        const double ra = -Q[a * S + a], rb = -Q[b * S + b];
+        if (ra == rb) p = rab * tm * exp(-rb * tm);
+        else p = rab * ((exp(-ra * tm) - exp(-rb * tm)) / (rb - ra));
+      } else {
+        p = 0.0;
+      }
+    }
+    Pm[idx] = p;
+  }
+}
+
+int rt_lb_transition_impl(const double* Q, const double* t, int n_mat, int S, double* P,
+                          cudaStream_t stream) {
+  if (n_mat <= 0) return RT_OK;
+  lb_transition_kernel<<<n_mat, 256, 0, stream>>>(Q, t, S, P);
+  RT_CUDA_CHECK(cudaGetLastError());
+  return RT_OK;
+}
+
 int rt_expm_spectral_impl(const double* A, const double* lam, const double* B, const double* t,
                           const uint8_t* d_off, int n_mat, int S, double* P, cudaStream_t stream) {
   if (n_mat <= 0) return RT_OK;

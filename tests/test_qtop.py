@@ -99,3 +99,78 @@ def test_tree_likelihood_with_spectral_scheme_matches_pade(S):
     np.testing.assert_allclose(got['trans'].cpu().numpy(), ref['trans'].cpu().numpy(), rtol=1e-9, atol=1e-12)
     mjp.use_spectral(None)
     np.testing.assert_allclose(mjp.transition_matrices().cpu().numpy(), P_pade.cpu().numpy(), rtol=0, atol=0)
+
+
+def random_for_sylvester(n, off_states, rng):
+    """qtop.py:375-434: default process (S1, D1), reference process (S0, D0) with off states,
+    switching rates L (zero at the off states)."""
+    Q1, S1, D1 = random_reversible_rate_matrix(n, rng)
+    Q0, S0, D0 = random_reversible_rate_matrix(n, rng, off_states)
+    L = np.square(rng.standard_normal(n))
+    L[list(off_states)] = 0
+    return S0, S1, D0, D1, L
+
+
+def _switching_Q(S0, S1, D0, D1, L):
+    n = len(L)
+    return qtop.build_block_2x2([[S0 * D0[None, :] - np.diag(L), np.diag(L)],
+                                 [np.zeros((n, n)), S1 * D1[None, :]]])
+
+
+def test_sylvester_round_trips():
+    """qtop.py:489-560: one-stage and two-stage decompositions reconstruct the switching-model
+    rate matrix, and with exp(t lam) its matrix exponential."""
+    rng = np.random.default_rng(1234)
+    S0, S1, D0, D1, L = random_for_sylvester(5, [0, 2], rng)
+    Q = _switching_Q(S0, S1, D0, D1, L)
+    dec = qtop.decompose_sylvester_v2(S0, S1, D0, D1, L)
+    np.testing.assert_allclose(qtop.reconstruct_sylvester_v2(*dec), Q, atol=1e-12)
+    part = qtop.partial_syl_decomp_v3(S1, D1)
+    dec3 = qtop.full_syl_decomp_v3(S0, D0, L, *part)
+    np.testing.assert_allclose(qtop.reconstruct_sylvester_v2(*dec3), Q, atol=1e-12)
+    A0, B0, A1, B1, L_, lam0, lam1, XQ = dec
+    for t in (0.1, 1.7):
+        P = qtop.reconstruct_sylvester_v2(A0, B0, A1, B1, L_, np.exp(t * lam0), np.exp(t * lam1), XQ)
+        off = np.nonzero(D0 == 0)[0]
+        P[off, off] = 1          # the states the reference process never enters (qtop.py:52-54)
+        np.testing.assert_allclose(P, scipy.linalg.expm(Q * t), atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_sylvester_device_reconstruction_matches_expm():
+    """getp_sylvester_v2 batched over branch lengths (two rt_expm_spectral calls + the off-diagonal
+    block) against scipy.linalg.expm of the 2n x 2n switching-model rate matrix; the states with
+    D0 == 0 get the unit diagonal the reference forces (qtop.py:52-54)."""
+    rng = np.random.default_rng(77)
+    for n, off in ((5, [0, 2]), (20, []), (61, [3])):
+        S0, S1, D0, D1, L = random_for_sylvester(n, off, rng)
+        Q = _switching_Q(S0, S1, D0, D1, L)
+        A0, B0, A1, B1, L_, lam0, lam1, XQ = qtop.decompose_sylvester_v2(S0, S1, D0, D1, L)
+        ts = np.array([0.0, 0.05, 0.4, 2.0])
+        P = qtop.getp_sylvester_v2(D0, A0, B0, A1, B1, L_, lam0, lam1, XQ, ts).cpu().numpy()
+        for k, t in enumerate(ts):
+            want = scipy.linalg.expm(Q * t)
+            np.testing.assert_allclose(P[k], want, atol=1e-11)
+            np.testing.assert_allclose(P[k].sum(axis=1), 1.0, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_small_step_lower_bound_matches_oracle():
+    """rt_lb_transition (liwen.py:48-82) against the numpy restatement, incl. the equal-exit-rate
+    branch; the bound is below expm entry by entry and tight for small steps; getp_bigt_lb
+    approaches expm as dt -> 0."""
+    from oracle import np_oracle
+    from raoteh_b200 import synth
+    Q, pi = synth.hky85()
+    Qe = np.array([[-1.0, 1.0, 0.0], [0.5, -1.0, 0.5], [0.0, 2.0, -2.0]])      # ra == rb for (0, 1)
+    for M in (Q, Qe, synth.mg94()[0]):
+        ts = np.array([1e-4, 0.01, 0.3])
+        P = qtop.getp_lb(M, ts).cpu().numpy()
+        for k, t in enumerate(ts):
+            np.testing.assert_allclose(P[k], np_oracle.getp_lb(M, t), rtol=1e-12, atol=1e-300)
+            assert (P[k] <= scipy.linalg.expm(M * t) + 1e-15).all()
+        np.testing.assert_allclose(P[0], scipy.linalg.expm(M * ts[0]), atol=1e-6)
+    big = qtop.getp_bigt_lb(Q, 1e-3, 0.5).cpu().numpy()
+    np.testing.assert_allclose(big, scipy.linalg.expm(Q * 0.5), atol=2e-3)
+    assert (big <= scipy.linalg.expm(Q * 0.5) + 1e-12).all()
+    np.testing.assert_allclose(qtop.getp_bigt_approx(Q, 1e-4, 0.5), scipy.linalg.expm(Q * 0.5), atol=1e-3)
