@@ -498,8 +498,11 @@ __global__ void lb_transition_kernel(const double* __restrict__ Q, const double*
       const double rab = Q[idx];
       if (rab != 0.0) {
         const double ra = -Q[a * S + a], rb = -Q[b * S + b];
-        if (ra == rb) p = rab * tm * exp(-rb * tm);
-        else p = rab * ((exp(-ra * tm) - exp(-rb * tm)) / (rb - ra));
+        // (e^{-ra t} - e^{-rb t}) / (rb - ra) without the cancellation of the literal form for
+        // small (rb - ra) t:  e^{-ra t} * (-expm1(-(rb - ra) t)) / (rb - ra)
+        const double d = rb - ra;
+        if (d == 0.0) p = rab * tm * exp(-rb * tm);
+        else p = rab * exp(-ra * tm) * (-expm1(-d * tm) / d);
       } else {
         p = 0.0;
       }

@@ -167,7 +167,16 @@ def test_small_step_lower_bound_matches_oracle():
         ts = np.array([1e-4, 0.01, 0.3])
         P = qtop.getp_lb(M, ts).cpu().numpy()
         for k, t in enumerate(ts):
-            np.testing.assert_allclose(P[k], np_oracle.getp_lb(M, t), rtol=1e-12, atol=1e-300)
+            # the literal formula of the reference (exp(-ra t) - exp(-rb t)) / (rb - ra) cancels for
+            # small steps (relative error ~ 1e-16 / ((rb - ra) t)); the kernel uses expm1
+            np.testing.assert_allclose(P[k], np_oracle.getp_lb(M, t), rtol=3e-16 / (t * 1e-3) + 1e-12, atol=1e-300)
+            ra = -np.diag(M)
+            d = ra[None, :] - ra[:, None]                       # rb - ra
+            with np.errstate(divide='ignore', invalid='ignore'):
+                f = np.where(d == 0, t, -np.expm1(-d * t) / d)
+            stable = M * np.exp(-ra * t)[:, None] * f
+            np.fill_diagonal(stable, np.exp(-ra * t))
+            np.testing.assert_allclose(P[k], stable, rtol=1e-13, atol=1e-300)
             assert (P[k] <= scipy.linalg.expm(M * t) + 1e-15).all()
         np.testing.assert_allclose(P[0], scipy.linalg.expm(M * ts[0]), atol=1e-6)
     big = qtop.getp_bigt_lb(Q, 1e-3, 0.5).cpu().numpy()
