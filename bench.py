@@ -682,6 +682,23 @@ def bench_c3(dev, args):
                    down_tflops_executed_on_tensor_pipe=flops_down / (down_ms * 1e-3) / 1e12,
                    down_frac_executed=flops_down / (down_ms * 1e-3) / 1e12 / peak)
         mjp.events = None
+        # the same evaluation with the spectral scheme for this time-reversible model: P(t) and the
+        # Frechet contraction in the eigenbasis (host eigh once per rate matrix, batched products)
+        mjp.use_spectral(cfg['pi'])
+        for _ in range(2):
+            mjp._P_valid = False
+            mjp.expected_history_statistics(obs)
+        ts = []
+        for _ in range(3):
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            mjp._P_valid = False
+            a2.record()
+            mjp.expected_history_statistics(obs)
+            b2.record()
+            torch.cuda.synchronize()
+            ts.append(a2.elapsed_time(b2))
+        exp['expectations_ms_spectral_scheme'] = float(np.mean(ts))
+        mjp.use_spectral(None)
     except Exception as e:  # pragma: no cover
         exp = dict(expectations_error=repr(e))
     flops_useful = N * n_int_edges * (2.0 * 61 * 61 + 61)      # S = 61, internal edges only

