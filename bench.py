@@ -41,6 +41,7 @@ if ROOT not in sys.path:
 C2_SITES = 1_000_000
 E2E_CHUNKS = int(os.environ.get('RT_E2E_CHUNKS', '8'))
 E2E_PACKED = os.environ.get('RT_E2E_PACKED', '1') != '0'         # 4-bit leaf codes on the host side
+USE_GRAPH = os.environ.get('RT_STEP_GRAPH', '1') != '0'       # device-resident arm: replay the step as one CUDA graph
 DEV_CHUNKS = int(os.environ.get('RT_DEV_CHUNKS', '0'))     # device-resident arm: two-stream chunk overlap   # site chunks of the pipelined host-buffer call
 C2_LEAVES = 32
 
@@ -365,9 +366,14 @@ def run_gpu(args):
         streams when > 1)."""
         mjp.events = sub if record else None
         mjp.set_rate_matrix(cfg['Q'])
-        r = mjp.expected_history_statistics(obs, overlap_chunks=0 if record else DEV_CHUNKS)
-        ll_sum = r['loglik_sum'] if 'loglik_sum' in r else r['loglik'].sum()
-        stats = rdist.pack_stats(ll_sum, r['dwell'], r['trans'], r['root_post_sum'])
+        if USE_GRAPH and not record:
+            # production schedule: the whole evaluation replayed as one CUDA graph
+            r = mjp.expected_history_statistics_graphed(obs)
+            stats = r['stats']
+        else:
+            r = mjp.expected_history_statistics(obs, overlap_chunks=0 if record else DEV_CHUNKS)
+            ll_sum = r['loglik_sum'] if 'loglik_sum' in r else r['loglik'].sum()
+            stats = rdist.pack_stats(ll_sum, r['dwell'], r['trans'], r['root_post_sum'])
         rdist.allreduce_stats(stats)      # the path's only collective (NCCL, 1+S+S*S+S doubles)
         state['n_levels'] = r['n_levels']
         return r, stats
@@ -417,7 +423,7 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     ms_plain = timed(step, args.steps, args.warmup, record=True)   # per-kernel events (roofline)
-    ms = timed(step, args.steps, args.warmup) if DEV_CHUNKS > 1 else ms_plain
+    ms = timed(step, args.steps, args.warmup) if (DEV_CHUNKS > 1 or USE_GRAPH) else ms_plain
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     ms_e2e_u8 = timed(lambda: step_e2e(False), args.steps, args.warmup) if E2E_PACKED else ms_e2e
@@ -550,6 +556,9 @@ def run_gpu(args):
         line = dict(
             metric='site_edge_messages_per_sec', value=value, unit='messages/s', n_gpus=world,
             steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+            ms_per_step_with_per_kernel_events=ms_plain,
+            schedule=('one CUDA graph replay per step (TreeMJP.expected_history_statistics_graphed) + the '
+                      'H2D copy of the rate matrix + the allreduce' if USE_GRAPH else 'eager launches'),
             scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
             config=c2_config(n_edges, S, world),
             # headline e2e: uint8 leaf codes exactly as a caller holds them, nothing prepared outside

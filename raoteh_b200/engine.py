@@ -656,6 +656,51 @@ class TreeMJP(object):
         _native.check(rc, 'rt_frechet_contract')
         return M
 
+    def expected_history_statistics_graphed(self, obs):
+        """expected_history_statistics for a NEW rate matrix (set_rate_matrix) replayed as one
+        CUDA graph: batched expm, up pass, down walk, Frechet contraction and the packing of the
+        statistics are ~13 small launches, and for a few hundred thousand sites per GPU (strong
+        scaling, optimiser loops) the host cannot issue them as fast as the GPU runs them.
+        Captured once per (engine, observations) -- the graph lives on the Observations object like
+        the chunked schedule's -- and replayed afterwards; the H2D copy of the rate matrix stays
+        outside (stream ordered before the replay).  Returns the same dict (static tensors, valid
+        until the next call) plus 'stats' = the packed [1 + S + S*S + S] vector for the allreduce.
+        Falls back to the eager path if the capture is refused."""
+        cache = obs.__dict__.setdefault('_rt_graphs', {})
+        prog = self._programs(obs)
+        key = ('ehs', self._serial, obs.kind, obs.data.data_ptr(), obs.n_sites, obs.stride,
+               _ptr(self.root_distn), prog['ops'].data_ptr(), self.fused)
+        entry = cache.get(key)
+        if entry is None:
+            if getattr(self, '_graph_refused', False):
+                return self._ehs_with_stats(obs)
+            self._P_valid = False
+            self._ehs_with_stats(obs)                 # eager once: workspaces, pool growth
+            torch.cuda.synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._P_valid = False
+                    out = self._ehs_with_stats(obs)
+                entry = (g, out)
+                cache[key] = entry
+            except Exception:
+                self._graph_refused = True
+                torch.cuda.synchronize()
+                self._P_valid = False
+                return self._ehs_with_stats(obs)
+        g, out = entry
+        g.replay()
+        self._P_valid = True
+        return out
+
+    def _ehs_with_stats(self, obs):
+        r = self.expected_history_statistics(obs)
+        ll_sum = r['loglik_sum'] if 'loglik_sum' in r else r['loglik'].sum()
+        r['stats'] = torch.cat([ll_sum.reshape(1), r['dwell'].reshape(-1), r['trans'].reshape(-1),
+                                r['root_post_sum'].reshape(-1)])
+        return r
+
     def expected_history_statistics(self, obs, want_node_distn=False, overlap_chunks=0):
         """Site-summed expected dwell[S], transition counts[S,S], root posterior sum[S],
         per-site loglik, per-edge contraction matrices M_edges[n,S,S].

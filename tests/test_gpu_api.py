@@ -484,3 +484,32 @@ def test_gen_histories_long_branch_birth_death():
     assert_allclose(s1.length.sum(), s0.length.sum())
     assert (s1.parent[1:] < np.arange(1, s1.n)).all()
     assert_allclose(sum(s1.length[v] for v in pieces[3]), 2.5)
+
+
+def test_graphed_evaluation_matches_eager_and_follows_the_rate_matrix():
+    """TreeMJP.expected_history_statistics_graphed: the CUDA-graph replay of the evaluation gives
+    the eager result, follows set_rate_matrix (the replay recomputes P from the new Q), and a second
+    Observations object gets its own graph."""
+    import torch
+    from raoteh_b200 import engine, synth
+    from raoteh_b200.lowering import TreeSchedule
+    cfg = synth.config_c2(n_sites=5000, n_leaves=16)
+    sched = TreeSchedule(cfg['parent'], cfg['length'])
+    mjp = engine.TreeMJP(sched, cfg['Q'], root_distn=cfg['pi'])
+    obs = engine.Observations.from_leaf_codes(sched, cfg['codes'], cfg['leaves'])
+    obs2 = engine.Observations.from_leaf_codes(sched, np.ascontiguousarray(cfg['codes'][:, :1234]), cfg['leaves'])
+    for scale in (1.0, 0.7, 1.9, 1.0):
+        Q = cfg['Q'] * scale
+        mjp.set_rate_matrix(Q)
+        ref = mjp.expected_history_statistics(obs)
+        want = {k: ref[k].clone() for k in ('loglik', 'dwell', 'trans', 'root_post_sum')}
+        for o, n in ((obs, 5000), (obs2, 1234)):
+            mjp.set_rate_matrix(Q)
+            got = mjp.expected_history_statistics_graphed(o)
+            if n == 5000:
+                for k in want:
+                    np.testing.assert_allclose(got[k].cpu().numpy(), want[k].cpu().numpy(), rtol=1e-12, atol=1e-14)
+                np.testing.assert_allclose(float(got['stats'][0]), float(want['loglik'].sum()), rtol=1e-12)
+            else:
+                np.testing.assert_allclose(got['loglik'].cpu().numpy(), want['loglik'].cpu().numpy()[:1234], rtol=1e-12)
+    assert not getattr(mjp, '_graph_refused', False)
