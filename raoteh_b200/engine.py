@@ -148,6 +148,9 @@ class TreeMJP(object):
         # has to run the up pass at the walk's lower occupancy.
         self.fused = os.environ.get('RT_FUSED', '0') == '1'
         self.fused_ctas_per_sm = int(os.environ.get('RT_FUSED_CTAS', '0'))
+        # S > 16: when the rate matrix is time-reversible w.r.t. the root distribution, contract
+        # the edge weights in its eigenbasis instead of exponentiating a 2S x 2S block per edge
+        self.auto_spectral_frechet = os.environ.get('RT_AUTO_SPECTRAL_FRECHET', '1') != '0'
 
     def _buf(self, name, shape, dtype, zero=False):
         """Reusable device workspace (avoids per-call allocation)."""
@@ -611,6 +614,8 @@ class TreeMJP(object):
         n, S = self.sched.n, self.S
         if getattr(self, '_spectral_D', None) is not None and self._P_valid and not self._spectral_dec[3]:
             return self._history_statistics_spectral(W)
+        if S > 16 and self.auto_spectral_frechet and self._reversible_decomposition() is not None:
+            return self._history_statistics_spectral(W, self._reversible_decomposition())
         M = self._buf('M', (n, S, S), torch.float64)
         dwell = torch.empty(S, dtype=torch.float64, device=self.device)
         trans = torch.empty((S, S), dtype=torch.float64, device=self.device)
@@ -620,14 +625,37 @@ class TreeMJP(object):
         _native.check(rc, 'rt_history_statistics')
         return M, dwell, trans
 
-    def _history_statistics_spectral(self, W):
+    def _reversible_decomposition(self):
+        """(A, lam, B) on the device if the (single) rate matrix is time-reversible with respect to
+        the root distribution and every state has positive weight, else None; cached per rate
+        matrix.  Used for the Frechet contraction of large state spaces (codon models are
+        reversible): the check is S^2 host work, the symmetric eigenproblem ~0.5 ms at S = 61."""
+        key = hash(self.Q_host.tobytes())
+        hit = getattr(self, '_rev_cache', None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        dec = None
+        D = self.root_distn_host
+        if D is not None and self.q_index is None and self.Q_host.shape[0] == 1 and (D > 0).all():
+            from . import qtop
+            try:
+                Sm = qtop.symmetric_factor(self.Q_host[0], D, rtol=1e-10)
+                A, lam, B = qtop.decompose_spectral_v2(Sm, D)
+                to = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(self.device)
+                dec = (to(A), to(lam), to(B), False)
+            except ValueError:
+                dec = None
+        self._rev_cache = (key, dec)
+        return dec
+
+    def _history_statistics_spectral(self, W, dec=None):
         """The same contraction in the eigenbasis of a time-reversible rate matrix (spectral scheme,
         use_spectral): with Q = A diag(lam) B, B = A^-1 (examples/p53/qtop.py:140-148),
             L(t Q^T, t W) = B^T [Phi(t) o (A^T (t W) B^T)] A^T,
             Phi_ij(t) = (e^{t lam_i} - e^{t lam_j}) / (t (lam_i - lam_j))   (e^{t lam_i} on the diagonal),
         four batched S x S products per edge (plain library GEMMs) instead of the Pade exponential
         of a 2S x 2S block matrix per edge: 0.3 ms instead of 4.0 ms for the 254 edges of C3."""
-        A, lam, B, _ = self._spectral_dec
+        A, lam, B, _ = self._spectral_dec if dec is None else dec
         t = self.length[:, None, None]
         x = lam[None, :, None] * t                 # t lam_i
         y = lam[None, None, :] * t                 # t lam_j
