@@ -471,11 +471,24 @@ def run_gpu(args):
         up_b, down_b = c2_bytes_per_site(sched, S)
         down_gbs = N * down_b / (down_ms * 1e-3) / 1e9
         up_gbs = N * up_b / (up_ms * 1e-3) / 1e9
+        # algorithmic FP64 work of the walk per site: 6S^2+2S per internal edge (m, G, D_child, W),
+        # S^2+2S per leaf edge (G from a column of P, W)
+        walk_flop = n_int_edges * (6 * S * S + 2 * S) + n_leaf * (S * S + 2 * S)
+        walk_tfl = N * walk_flop / (down_ms * 1e-3) / 1e12
+        fma_peak = fp64_peak('dfma')
         roofline = dict(bound='hbm', kernel='down_walk_kernel<4,codes> (1 launch/step, %.0f%% of the step)'
                         % (100 * down_ms / ms), achieved=down_gbs, peak=peaks['hbm_gbs'], unit='GB/s',
                         frac=down_gbs / peaks['hbm_gbs'], peak_source='%s (MEASURED_PEAKS.json hbm_gbs)' % peak_kind,
                         traffic=ncu_traffic('down_walk_kernel<4, 0'),
                         algorithmic_bytes_per_launch=N * down_b, ms=down_ms,
+                        fp64_pipe=dict(achieved=walk_tfl, peak=fma_peak, unit='TFLOP/s', frac=walk_tfl / fma_peak,
+                                       algorithmic_flop_per_site=walk_flop,
+                                       peak_source='tools/fp64_peak.cu DFMA probe (profiles/r1_fp64_peak.jsonl)',
+                                       ncu='fp64 pipe 37 %, issue slots 53 % (profiles/r2_ncu_full_summary.json)'),
+                        note='the S=4 walk reads every stored partial exactly once (ncu dram read = algorithmic '
+                             'bytes) but is bound by latency / issue slots, not by HBM; the fused up+down kernel '
+                             'that removes these bytes altogether was built and measured slower '
+                             '(profiles/r2_fused_small.md)',
                         also=dict(kernel='prune_small_kernel<4,codes,store>', achieved=up_gbs,
                                   frac=up_gbs / peaks['hbm_gbs'], ms=up_ms,
                                   algorithmic_bytes_per_launch=N * up_b,
