@@ -260,7 +260,11 @@ class ToleranceChains(object):
 
     def grow(self, cap_p=None, cap_t=None):
         """Re-allocate the jump / toggle pools with larger capacities (contents stay
-        right-aligned) and clear the capacity flags."""
+        right-aligned) and clear the capacity flags.  The toggle pool of a class is limited to 255
+        entries per trajectory (`t_total` and the per-branch counts are uint8 in the kernel's
+        layout): a tree long enough to need more toggles of ONE class in one trajectory
+        (tree length x omega_t of the order of 100) has to be cut into subtrees by the caller;
+        status 3 after growing to 255 says so loudly rather than truncating."""
         T, dev, NP = self.n_traj, self.device, self.n_parts
         if cap_p is not None and int(cap_p) > self.cap_p:
             cap_p = int(cap_p)
