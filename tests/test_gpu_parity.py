@@ -568,3 +568,65 @@ def test_fused_small_kernel_matches_oracle(rt, S, n_leaves, n_sites, kind):
         np.testing.assert_allclose(r['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
         np.testing.assert_allclose(r['root_post_sum'].cpu().numpy(), o['root_post'].sum(axis=0), rtol=RTOL)
     np.testing.assert_allclose(res[True]['W'].cpu().numpy(), res[False]['W'].cpu().numpy(), rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize('shape', ['star', 'caterpillar', 'many_tiles', 'polytomy'])
+def test_dmma_pruning_walk_edge_cases(rt, shape):
+    """The persistent per-warp walk of the DMMA pruning kernel: a star tree (no contraction at all:
+    the TMA ring is never armed), a caterpillar (every internal node has one internal and one leaf
+    child: the longest chain of fresh hand-offs), more tiles than SMs (every CTA loops over tiles and
+    the ring runs on across tile boundaries; ragged last tile), and polytomies with observed internal
+    nodes -- log-lik, stored partials' consistency (through the expectations) and expectations
+    against the oracle."""
+    from raoteh_b200 import synth
+    from raoteh_b200.lowering import TreeSchedule
+    rng = np.random.default_rng({'star': 1, 'caterpillar': 2, 'many_tiles': 3, 'polytomy': 4}[shape])
+    S = {'star': 20, 'caterpillar': 61, 'many_tiles': 11, 'polytomy': 33}[shape]
+    if shape == 'star':
+        parent = np.array([-1] + [0] * 9, dtype=np.int32)
+        n_sites = 300
+    elif shape == 'caterpillar':
+        # spine 0-2-4-6-8-10, a leaf hanging off every spine node, two leaves at the end
+        parent = np.array([-1, 0, 0, 2, 2, 4, 4, 6, 6, 8, 8, 10, 10], dtype=np.int32)
+        n_sites = 700
+    elif shape == 'many_tiles':
+        parent, _, _ = synth.random_binary_tree(6, 0.1, rng)
+        n_sites = 148 * 128 * 2 + 77
+    else:
+        parent = np.array([-1, 0, 0, 0, 0, 4, 4, 4, 4, 8, 8, 8], dtype=np.int32)
+        n_sites = 515
+    n = len(parent)
+    length = rng.exponential(0.15, size=n)
+    length[0] = 0.0
+    Q = rng.exponential(1.0, size=(S, S))
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    Q /= np.abs(np.diag(Q)).mean()
+    pi = rng.dirichlet(np.ones(S))
+    sched = TreeSchedule(parent, length)
+    leaves = sched.leaves
+    codes = synth.simulate_leaf_codes(parent, length, leaves, Q, pi, n_sites, rng, 0.05)
+    mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+    P = np_oracle.expm_edges(Q, length)
+    if shape == 'polytomy':
+        # observations as masks at every node (an observed internal node: OP_APPLY_OBS)
+        full = (1 << S) - 1
+        mask = np.full((n, n_sites), full, dtype=np.uint64)
+        for i, v in enumerate(leaves):
+            c = codes[i].astype(np.uint64)
+            mask[v] = np.where(codes[i] == 255, np.uint64(full), np.uint64(1) << c)
+        mask[4] = np.where(rng.random(n_sites) < 0.5, np.uint64(full), np.uint64(full) ^ np.uint64(5))
+        obs = rt.Observations.from_masks(sched, mask)
+        oobs = np_oracle.Obs('mask', S, n_sites, mask=mask)
+    else:
+        obs = rt.Observations.from_leaf_codes(sched, codes, leaves)
+        oobs = np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes)
+    r = mjp.log_likelihood(obs)
+    ll, st = np_oracle.log_likelihood(parent, P, oobs, pi)
+    assert (r['status'].cpu().numpy() == st).all()
+    np.testing.assert_allclose(r['loglik'].cpu().numpy(), ll, rtol=RTOL)
+    if n_sites <= 1000:
+        e = mjp.expected_history_statistics(obs)
+        o = np_oracle.expected_history_statistics(parent, length, Q, P, oobs, pi)
+        np.testing.assert_allclose(e['dwell'].cpu().numpy(), o['dwell'], rtol=RTOL)
+        np.testing.assert_allclose(e['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
