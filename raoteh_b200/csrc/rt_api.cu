@@ -3,6 +3,7 @@
 #include "../../include/rt_b200.h"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -288,9 +289,12 @@ static int raoteh_run_impl(const rt_raoteh_args& R, void* stream) {
   if (R.traj_stride < R.n_traj || R.n_sites <= 0 || R.cap <= 0) return arg_error("sizes");
   if (R.n_traj <= 0) return RT_OK;
   const int S = R.S;
-  if ((S > 8 || S == 7) && S <= 64) {
+  // RT_RAOTEH_FORCE_WARP=1: run the warp-per-trajectory kernel for small state spaces too (the
+  // measurement that justifies thread-per-trajectory for S <= 8: profiles/r2_raoteh_warp_vs_thread.md)
+  static const bool force_warp = [] { const char* e = getenv("RT_RAOTEH_FORCE_WARP"); return e && e[0] == '1'; }();
+  if (((S > 8 || S == 7) || (force_warp && !R.time_f64)) && S <= 64) {
     if (R.time_f64) return unsupported("fp64 event times: S in {2,3,4,5,6,8} only");
-    if (R.sweep_count) return unsupported("sweep_count: S in {2,3,4,5,6,8} only");
+    if (R.sweep_count && !force_warp) return unsupported("sweep_count: S in {2,3,4,5,6,8} only");
     // warp-per-trajectory kernel (csrc/rt_tmjp.cu) on the same trajectory layout
     rt_tmjp_args A;
     memset(&A, 0, sizeof(A));
