@@ -353,6 +353,20 @@ down_walk_kernel(int64_t n_sites, int64_t stride, const int4* __restrict__ progr
   const int64_t tiles = (n_sites + tile_sites - 1) / tile_sites;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t site0 = tile * tile_sites + tid;            // site of q: site0 + q*kWalkBlock
+    // the NEXT tile's leaf-code rows: pulled into L2 a whole tile ahead (the byte loads one op ahead
+    // of their use cannot hide a DRAM round trip behind a short leaf op: 9 % of the warp samples
+    // sat on that load, ncu source view)
+    if (OBS == OBS_CODES && tile + gridDim.x < tiles) {
+      const int64_t row_bytes = obs_packed ? tile_sites / 2 : tile_sites;
+      const int lines_per_row = (int)((row_bytes + 127) / 128);
+      const int64_t nb = (tile + gridDim.x) * row_bytes;
+      for (int i = tid; i < n_ops * lines_per_row; i += kWalkBlock) {
+        const int4 px = prog_s[i / lines_per_row];
+        if ((px.x & 0xff) == OP_MSG_OBS)
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const uint8_t*>(obs) +
+                       off_s[i / lines_per_row] + nb + (i % lines_per_row) * 128));
+      }
+    }
     bool live[NS];
 #pragma unroll
     for (int q = 0; q < NS; ++q) {
