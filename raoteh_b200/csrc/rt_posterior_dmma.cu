@@ -87,7 +87,7 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
                  const double* __restrict__ P, const void* __restrict__ obs,
                  const double* __restrict__ partials, const int8_t* __restrict__ status,
                  double* __restrict__ node_distn, double* __restrict__ W,
-                 const double* __restrict__ Kmat, double* __restrict__ branch_out) {
+                 const double* __restrict__ Kmat, double* __restrict__ branch_out, int skip_coded_leaves) {
   constexpr int SP = 8 * MT;
   constexpr int LDP = SP + 4;
   constexpr int KS = SP / 4;
@@ -103,6 +103,9 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
   const int g = lane >> 2, t = lane & 3;
   const int4 e = edges[blockIdx.y];    // (child node, parent store, child store, child obs slot)
   const int b = e.x;
+  // coded leaf: down_leaf_scatter_kernel's edge.  (A run-time flag: as a template parameter the
+  // same early exit changed the register allocation of the rest and cost 34 % on internal edges.)
+  if (skip_coded_leaves && e.z < 0 && e.w >= 0) return;
   for (int idx = tid; idx < SP * LDP; idx += kThreads) {
     const int r = idx / LDP, c = idx % LDP;
     Ps[idx] = (r < S && c < S) ? P[(size_t)b * S * S + r * S + c] : 0.0;
@@ -389,6 +392,132 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
   }
 }
 
+// Leaf edges with hard codes, no DMMA at all.  With a one-hot L_b the three contractions of an
+// edge collapse: m = P_b[:, k], G = D_a / P_b[:, k], and W_b = sum_sites G L_b^T only ever touches
+// column k of the site -- W_b[:, k] = (sum over the sites with code k of D_a) / P_b[:, k].  So a
+// coded leaf edge is a column sum of the parent marginals segmented by the code: 512 B of HBM
+// per site and edge, one shared-memory read-modify-write per (state, site).  Run as a dense
+// G L^T contraction it was 128 of the 506 contraction units of the C3 downward pass.
+//
+// One thread per parent state r: row r of the CTA's W tile in shared memory belongs to that
+// thread alone, so the scatter needs neither atomics nor barriers; the codes are warp-uniform.
+// A lane reads 16 consecutive sites of its row per group (128 contiguous bytes, whole sectors),
+// the next group in flight under the scatter of the current one.  Sites whose code is unobserved
+// (L_b = ones) go to a per-row register and are spread over the row at the flush; invalid codes and
+// failed sites land in the pad column.
+constexpr int kLeafThreads = 64;
+constexpr int kLeafLd = 65;            // odd: lanes (rows) hit distinct banks for one column
+constexpr int kLeafGroup = 16;
+constexpr int kLeafSitesPerCta = 2048;
+
+template <bool V4>
+__global__ void __launch_bounds__(kLeafThreads)
+down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict__ edges,
+                         const double* __restrict__ P, const uint8_t* __restrict__ obs,
+                         const int8_t* __restrict__ status, const double* __restrict__ node_distn,
+                         double* __restrict__ W, int sites_per_cta) {
+  const int4 e = edges[blockIdx.y];
+  if (e.z >= 0 || e.w < 0) return;     // internal child / unobserved leaf: the DMMA kernel's edge
+  extern __shared__ double Ws[];       // [64][kLeafLd]; column 64 is the bin for skipped sites
+  const int r = threadIdx.x, lane = r & 31;
+  const bool act = r < S;
+  double* Wr = Ws + r * kLeafLd;
+  for (int c = 0; c < kLeafLd; ++c) Wr[c] = 0.0;
+  const int64_t c0 = (int64_t)blockIdx.x * sites_per_cta;
+  const int64_t c1 = c0 + sites_per_cta < n_sites ? c0 + sites_per_cta : n_sites;
+  // lanes past the last state read row 0 into rows of the tile that are never flushed
+  const double* Dp = node_distn + ((int64_t)e.y * S + (act ? r : 0)) * stride;
+  const uint8_t* code = obs + (int64_t)e.w * stride;
+  double miss = 0.0;
+
+  auto load = [&](double (&dn)[kLeafGroup], int2& kn, int64_t s0) {
+    if (s0 + kLeafGroup <= c1) {
+      if (V4) {
+        // 32 bytes per lane and instruction: one whole sector (two 16-byte loads of a sector,
+        // streaming, fetched it from L2 twice: 10.8 GB of L2 reads for 6.25 GB of data, ncu)
+#pragma unroll
+        for (int i = 0; i < kLeafGroup; i += 4)
+          asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                       : "=d"(dn[i]), "=d"(dn[i + 1]), "=d"(dn[i + 2]), "=d"(dn[i + 3]) : "l"(Dp + s0 + i));
+      } else {
+#pragma unroll
+        for (int i = 0; i < kLeafGroup; ++i) dn[i] = __ldg(Dp + s0 + i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kLeafGroup; ++i) dn[i] = s0 + i < c1 ? __ldg(Dp + s0 + i) : 0.0;
+    }
+    const int64_t sg = s0 + (lane & (kLeafGroup - 1));
+    const bool in = sg < c1;
+    // both loads issued together and NOT combined here: the first use of a loaded value blocks
+    // the warp, so it belongs to the scatter two groups later (a third of the warp samples sat
+    // on this line when the select was here, ncu source view)
+    kn.x = in ? (int)reinterpret_cast<const uint8_t*>(status)[sg] : 1;   // (no sign extension: that is a use)
+    kn.y = in ? (int)code[sg] : 254;
+  };
+  auto scatter = [&](const double (&d)[kLeafGroup], int2 ks) {
+    const int kv = ks.x == RT_SITE_OK ? ks.y : 254;     // failed sites and the tail go to the bin
+#pragma unroll
+    for (int q = 0; q < kLeafGroup; q += 4) {
+      int k[4];
+      double w[4], v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = __shfl_sync(0xffffffffu, kv, q + i);
+        if (kk == RT_MISSING) miss += d[q + i];
+        k[i] = kk < S ? kk : 64;
+        w[i] = Wr[k[i]];
+      }
+      // four read-modify-writes with their loads issued together: a repeated column takes the
+      // running value instead of the stale load, the stores stay in program order
+      v[0] = w[0] + d[q];
+      v[1] = (k[1] == k[0] ? v[0] : w[1]) + d[q + 1];
+      v[2] = (k[2] == k[1] ? v[1] : (k[2] == k[0] ? v[0] : w[2])) + d[q + 2];
+      v[3] = (k[3] == k[2] ? v[2] : (k[3] == k[1] ? v[1] : (k[3] == k[0] ? v[0] : w[3]))) + d[q + 3];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Wr[k[i]] = v[i];
+    }
+  };
+  // three register buffers in rotation: a group is loaded two scatters before its own.  (The
+  // parent marginal of a site that passed is a product of non-negative factors: no clamping.)
+  double da[kLeafGroup], db[kLeafGroup], dc[kLeafGroup];
+  int2 ka = make_int2(1, 254), kb = ka, kc = ka;
+  const int64_t G = kLeafGroup;
+  if (c0 < c1) load(da, ka, c0);
+  if (c0 + G < c1) load(db, kb, c0 + G);
+  for (int64_t s0 = c0; s0 < c1; s0 += 3 * G) {
+    if (s0 + 2 * G < c1) load(dc, kc, s0 + 2 * G);
+    scatter(da, ka);
+    if (s0 + G >= c1) break;
+    if (s0 + 3 * G < c1) load(da, ka, s0 + 3 * G);
+    scatter(db, kb);
+    if (s0 + 2 * G >= c1) break;
+    if (s0 + 4 * G < c1) load(db, kb, s0 + 4 * G);
+    scatter(dc, kc);
+  }
+  if (!act) return;
+  const double* Pr = P + ((size_t)e.x * S + r) * S;
+  double* Wg = W + ((size_t)e.x * S + r) * S;
+  double spread = 0.0;
+  if (miss != 0.0) {
+    double rs = 0.0;
+    for (int c = 0; c < S; ++c) rs += Pr[c];
+    spread = rs > 0.0 ? miss / rs : 0.0;
+  }
+  for (int c = 0; c < S; ++c) {
+    const double p = Pr[c];
+    if (p > 0.0) {
+      const double val = Wr[c] / p + spread;
+      if (val != 0.0) atomicAdd(&Wg[c], val);
+    }
+  }
+}
+
+static bool leaf_scatter_enabled() {
+  static const bool on = [] { const char* e = getenv("RT_DOWN_LEAF_SCATTER"); return !e || atoi(e) != 0; }();
+  return on;
+}
+
 template <int MT>
 int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edges_dev,
         const int32_t* level_ptr_h, int n_levels, const double* P, const double* root_distn,
@@ -403,17 +532,18 @@ int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edg
   const size_t smem = sizeof(double) * ((size_t)SP * LDP + 2 * (size_t)kWarps * SP * kLd + 2 * SP);
   const int4* edges = reinterpret_cast<const int4*>(edges_dev);
   const unsigned gx = (unsigned)((n_sites + kTilesPerCta * kTileSites - 1) / (kTilesPerCta * kTileSites));
+  const bool scatter = obs_kind == OBS_CODES && !branch_out && leaf_scatter_enabled();
 #define RT_LAUNCH(OBSK)                                                                           \
   if (branch_out) {                                                                               \
     auto kern = down_dmma_kernel<MT, OBSK, true>;                                                 \
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, kThreads, smem, stream>>>(S, n_sites, stride, edges + e0, P, obs, partials,     \
-                                           status, node_distn, W, Kmat, branch_out);              \
+                                           status, node_distn, W, Kmat, branch_out, 0);           \
   } else {                                                                                        \
     auto kern = down_dmma_kernel<MT, OBSK, false>;                                                \
     RT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, kThreads, smem, stream>>>(S, n_sites, stride, edges + e0, P, obs, partials,     \
-                                           status, node_distn, W, nullptr, nullptr);              \
+                                           status, node_distn, W, nullptr, nullptr, scatter ? 1 : 0); \
   }
   for (int l = 0; l < n_levels; ++l) {
     const int e0 = level_ptr_h[l], e1 = level_ptr_h[l + 1];
@@ -427,6 +557,23 @@ int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edg
     }
   }
 #undef RT_LAUNCH
+  if (scatter && level_ptr_h[n_levels] > 0) {
+    // every coded leaf edge of the tree in one launch: its parent's marginal is final by now
+    const size_t lsm = sizeof(double) * 64 * kLeafLd;
+    static const int spc = [] {
+      const char* e = getenv("RT_LEAF_SITES");
+      const int v = e ? atoi(e) : kLeafSitesPerCta;
+      return v >= kLeafGroup ? v / kLeafGroup * kLeafGroup : kLeafSitesPerCta;
+    }();
+    dim3 grid((unsigned)((n_sites + spc - 1) / spc), (unsigned)level_ptr_h[n_levels]);
+    const bool v4 = stride % 4 == 0 && (reinterpret_cast<uintptr_t>(node_distn) & 31) == 0;
+    if (v4)
+      down_leaf_scatter_kernel<true><<<grid, kLeafThreads, lsm, stream>>>(
+          S, n_sites, stride, edges, P, reinterpret_cast<const uint8_t*>(obs), status, node_distn, W, spc);
+    else
+      down_leaf_scatter_kernel<false><<<grid, kLeafThreads, lsm, stream>>>(
+          S, n_sites, stride, edges, P, reinterpret_cast<const uint8_t*>(obs), status, node_distn, W, spc);
+  }
   RT_CUDA_CHECK(cudaGetLastError());
   return RT_OK;
 }

@@ -238,12 +238,15 @@ def test_expectations_match_oracle(rt, S, n_leaves, n_sites):
 
 
 @pytest.mark.parametrize('S,n_leaves,n_sites,kind', [(20, 9, 2500, 'codes'), (61, 10, 2100, 'codes'),
+                                                     (13, 8, 4133, 'codes'),     # odd row stride: scalar loads of the leaf scatter
                                                      (20, 7, 1300, 'mask'), (11, 6, 1100, 'dense')])
 def test_large_state_down_pass_tiles_and_observation_kinds(rt, S, n_leaves, n_sites, kind):
     """The DMMA down pass (9 <= S <= 64) across several CTAs of the site axis (1024 sites each: the
     next tile's rows are prefetched across tile ends and past the last site), with 30 % unobserved
-    leaf cells (row-sum gathers on leaf edges), and with mask / dense observations (contracted,
-    not gathered), against the oracle (_mjp_dense.py:410-539)."""
+    leaf cells, and with mask / dense observations (contracted, not gathered), against the oracle
+    (_mjp_dense.py:410-539).  Coded leaf edges go through down_leaf_scatter_kernel (2048 sites per
+    CTA, groups of 16 sites, 256-bit loads when the row stride allows): the site counts cover
+    several CTAs, a ragged last group, both load paths and the unobserved-site spread."""
     from raoteh_b200.lowering import TreeSchedule
     from raoteh_b200 import synth
     rng = np.random.default_rng(77 + S)
