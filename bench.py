@@ -679,7 +679,8 @@ def bench_c3(dev, args):
     b.record()
     torch.cuda.synchronize()
     # expectations at the same size: up pass with stored partials + level-synchronous DMMA down pass
-    # (three contractions per internal edge; a leaf edge with hard codes gathers m and contracts W only)
+    # (three contractions per internal edge; a leaf edge with hard codes is a column sum of the parent
+    # marginals segmented by the code -- down_leaf_scatter_kernel, HBM-bound, no DMMA)
     exp = {}
     try:
         mjp.events = {}
@@ -699,10 +700,16 @@ def bench_c3(dev, args):
         up_ms = float(np.mean([x.elapsed_time(y) for x, y in pair(sub['up'])]))
         down_ms = float(np.mean([x.elapsed_time(y) for x, y in pair(sub['down'])]))
         n_leaf_edges = E - n_int_edges
-        flops_down = N * (3.0 * n_int_edges + 1.0 * n_leaf_edges) * 2.0 * 64 * 64
+        flops_down = N * 3.0 * n_int_edges * 2.0 * 64 * 64
+        # the floor of the whole evaluation on the FP64 tensor pipe: 1 (up) + 3 (down) padded 64 x 64
+        # contractions per internal edge and site at the measured DMMA peak
+        floor_ms = N * 4.0 * n_int_edges * 2.0 * 64 * 64 / (peak * 1e12) * 1e3
         exp = dict(expectations_ms=float(np.mean(te)), up_store_ms=up_ms, down_ms=down_ms,
                    down_tflops_executed_on_tensor_pipe=flops_down / (down_ms * 1e-3) / 1e12,
-                   down_frac_executed=flops_down / (down_ms * 1e-3) / 1e12 / peak)
+                   down_frac_executed=flops_down / (down_ms * 1e-3) / 1e12 / peak,
+                   leaf_edges_bytes=float(N) * n_leaf_edges * 61 * 8,
+                   tensor_pipe_floor_ms=floor_ms,
+                   frac_of_tensor_pipe_floor=floor_ms / float(np.mean(te)))
         mjp.events = None
         # the same evaluation with the spectral scheme for this time-reversible model: P(t) and the
         # Frechet contraction in the eigenbasis (host eigh once per rate matrix, batched products)
