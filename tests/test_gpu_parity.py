@@ -633,3 +633,43 @@ def test_dmma_pruning_walk_edge_cases(rt, shape):
         o = np_oracle.expected_history_statistics(parent, length, Q, P, oobs, pi)
         np.testing.assert_allclose(e['dwell'].cpu().numpy(), o['dwell'], rtol=RTOL)
         np.testing.assert_allclose(e['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize('S,n_leaves,n_sites', [(12, 5, 3000), (61, 6, 2300)])
+def test_large_state_expectations_skip_infeasible_sites(rt, S, n_leaves, n_sites):
+    """A reducible rate matrix (two closed classes) and uniformly random leaf codes: most sites have
+    probability zero (StructuralZeroProb in the reference, _mjp_dense.py:186-190) and must contribute
+    nothing to the expectations -- in the DMMA kernel their rows are zero, in down_leaf_scatter_kernel
+    they go to the pad column of the W tile.  Feasible sites against the oracle."""
+    from raoteh_b200.lowering import TreeSchedule
+    from raoteh_b200 import synth
+    rng = np.random.default_rng(4242 + S)
+    parent, length, leaves = synth.random_binary_tree(n_leaves, 0.3, rng)
+    h = S // 2
+    Q = np.zeros((S, S))
+    Q[:h, :h] = rng.exponential(1.0, size=(h, h))
+    Q[h:, h:] = rng.exponential(1.0, size=(S - h, S - h))
+    np.fill_diagonal(Q, 0)
+    Q -= np.diag(Q.sum(axis=1))
+    pi = rng.dirichlet(np.ones(S))
+    # leaves drawn from one class with probability 0.8 per site, anywhere otherwise
+    cls = rng.integers(0, 2, size=n_sites)
+    codes = np.where(cls[None, :] == 0, rng.integers(0, h, size=(len(leaves), n_sites)),
+                     rng.integers(h, S, size=(len(leaves), n_sites)))
+    stray = rng.random((len(leaves), n_sites)) < 0.08
+    codes = np.where(stray, rng.integers(0, S, size=codes.shape), codes).astype(np.uint8)
+    codes[rng.random(codes.shape) < 0.05] = 255          # some unobserved cells as well
+    sched = TreeSchedule(parent, length)
+    mjp = rt.TreeMJP(sched, Q, root_distn=pi)
+    obs = rt.Observations.from_leaf_codes(sched, codes, leaves)
+    r = mjp.expected_history_statistics(obs)
+    P = np_oracle.expm_edges(Q, length)
+    o = np_oracle.expected_history_statistics(
+        parent, length, Q, P, np_oracle.Obs('codes', S, n_sites, leaf_nodes=leaves, codes=codes), pi)
+    ok = np.isfinite(o['loglik'])
+    assert 0.2 * n_sites < ok.sum() < 0.95 * n_sites
+    np.testing.assert_array_equal(r['status'].cpu().numpy() == 0, ok)
+    np.testing.assert_allclose(r['loglik'].cpu().numpy()[ok], o['loglik'][ok], rtol=RTOL)
+    np.testing.assert_allclose(r['dwell'].cpu().numpy(), o['dwell'], rtol=RTOL)
+    np.testing.assert_allclose(r['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(float(r['dwell'].sum()), length.sum() * ok.sum(), rtol=1e-10)
