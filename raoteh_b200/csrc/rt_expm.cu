@@ -60,7 +60,7 @@ __device__ void mm(double* __restrict__ C, const double* __restrict__ A,
 #pragma unroll
           for (int i = 0; i < 4; ++i) a[i] = As[ty * 4 + i][k];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+          for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];     // lanes on consecutive columns: no bank conflicts
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -71,7 +71,7 @@ __device__ void mm(double* __restrict__ C, const double* __restrict__ A,
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          int gi = i0 + ty * 4 + i, gj = j0 + tx * 4 + j;
+          int gi = i0 + ty * 4 + i, gj = j0 + tx + 16 * j;
           if (gi < n && gj < n) C[(size_t)gi * n + gj] = acc[i][j];
         }
     }
@@ -92,18 +92,22 @@ __device__ double block_max(double v, double* red) {
   return r;
 }
 
-// In-place expm of mats[blockIdx.x] (n x n).  scratch: 7 n^2 doubles per matrix.
+// In-place expm of mats[blockIdx.x] (n x n).  Six n x n work matrices: in dynamic shared memory
+// when they fit (SMEM_WS: n <= 64, 6 * 32 KB -- the elimination below is 61 dependent steps of
+// short loads, which took most of the 235 us per matrix when they went to L2), else in `scratch`
+// (7 n^2 doubles per matrix are reserved there).
+template <bool SMEM_WS>
 __global__ void __launch_bounds__(kThreads)
 expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
   __shared__ double sm[kTile * (kTK + 1) + kTK * (kTile + 4)];
   __shared__ double red[kThreads / 32];
   __shared__ int piv_s;
+  extern __shared__ double ws_dyn[];
   const int tid = threadIdx.x;
   const size_t nn = (size_t)n * n;
   double* A = mats + (size_t)blockIdx.x * nn;
-  double* W = scratch + (size_t)blockIdx.x * 7 * nn;
-  double *A2 = W, *A4 = W + nn, *A6 = W + 2 * nn, *T1 = W + 3 * nn, *U = W + 4 * nn,
-         *V = W + 5 * nn, *T2 = W + 6 * nn;
+  double* W = SMEM_WS ? ws_dyn : scratch + (size_t)blockIdx.x * 7 * nn;
+  double *A2 = W, *A4 = W + nn, *A6 = W + 2 * nn, *T1 = W + 3 * nn, *U = W + 4 * nn, *V = W + 5 * nn;
 
   // 1-norm (max column sum of |a_ij|)
   double cmax = 0.0;
@@ -126,15 +130,13 @@ expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
   mm(A2, A, A, n, sm);
   mm(A4, A2, A2, n, sm);
   mm(A6, A4, A2, n, sm);
-  // T1 = b13 A6 + b11 A4 + b9 A2 ; T2 = b12 A6 + b10 A4 + b8 A2
-  for (size_t i = tid; i < nn; i += kThreads) {
-    const double a2 = A2[i], a4 = A4[i], a6 = A6[i];
-    T1[i] = b[13] * a6 + b[11] * a4 + b[9] * a2;
-    T2[i] = b[12] * a6 + b[10] * a4 + b[8] * a2;
-  }
+  // U = A6 (b13 A6 + b11 A4 + b9 A2), V = A6 (b12 A6 + b10 A4 + b8 A2), one temporary for both
+  for (size_t i = tid; i < nn; i += kThreads) T1[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
   __syncthreads();
-  mm(U, A6, T1, n, sm);     // U = A6*T1
-  mm(V, A6, T2, n, sm);     // V = A6*T2
+  mm(U, A6, T1, n, sm);
+  for (size_t i = tid; i < nn; i += kThreads) T1[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
+  __syncthreads();
+  mm(V, A6, T1, n, sm);
   for (size_t i = tid; i < nn; i += kThreads) {
     const double a2 = A2[i], a4 = A4[i], a6 = A6[i];
     const bool diag = (i / n) == (i % n);
@@ -143,17 +145,18 @@ expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
   }
   __syncthreads();
   mm(U, A, T1, n, sm);      // U = A * (...)
-  // M = V - U (into T1), B = V + U (into T2)
+  // M = V - U (into A2), B = V + U (into A4): the powers are dead
+  double* M = A2;
+  double* B = A4;
   for (size_t i = tid; i < nn; i += kThreads) {
     const double u = U[i], v = V[i];
-    T1[i] = v - u;
-    T2[i] = v + u;
+    M[i] = v - u;
+    B[i] = v + u;
   }
   __syncthreads();
 
-  // Solve T1 * X = T2 by Gaussian elimination with partial pivoting; X -> T2.
-  double* M = T1;
-  double* B = T2;
+  // Solve M X = B by Gauss-Jordan elimination with partial pivoting (every other row is
+  // eliminated in step k, so there is no serial back substitution); X -> B.
   for (int k = 0; k < n; ++k) {
     if (tid < 32) {
       double best = -1.0;
@@ -183,36 +186,62 @@ expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
       __syncthreads();
     }
     const double pinv = 1.0 / M[(size_t)k * n + k];
-    // eliminate rows below k: each thread handles (row i, column chunk)
-    const int rows = n - k - 1;
-    const int cols = (n - k - 1) + n;   // M columns k+1..n-1, then all B columns
-    for (long idx = tid; idx < (long)rows * cols; idx += kThreads) {
-      const int i = k + 1 + (int)(idx / cols);
-      const int c = (int)(idx % cols);
-      const double l = M[(size_t)i * n + k] * pinv;
-      if (c < n - k - 1) {
-        const int j = k + 1 + c;
-        M[(size_t)i * n + j] = fma(-l, M[(size_t)k * n + j], M[(size_t)i * n + j]);
+    // rows i != k, columns k+1..n-1 of M and all columns of B; column k of M is only read.
+    // 64 column lanes x 4 row groups.  (The flattened (row, column) loop of the first version
+    // spent 70 % of the kernel's instructions here, ~30 per update in 64-bit index arithmetic
+    // and integer divisions: ncu source view, 415 k cycles per 61 x 61 matrix.)
+    {
+      const int tx = tid & 63, ty = tid >> 6;
+      if (n <= 64) {
+        // one column of M and one of B per thread; row k is read once per step.  Four rows at
+        // a time, all loads before the first store (the compiler must assume M and B alias and
+        // otherwise serialises load -> fma -> store row by row: 100 cycles per row, latency bound);
+        // row k itself takes a zero multiplier instead of a branch.
+        const bool cm = tx > k && tx < n, cb = tx < n;
+        const double mk = cm ? M[k * n + tx] : 0.0, bk = cb ? B[k * n + tx] : 0.0;
+        for (int i0 = ty; i0 < n; i0 += 4 * (kThreads / 64)) {
+          double l[4], mv[4], bv[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r * (kThreads / 64);
+            const bool ok = i < n;
+            const int o = i * n;
+            l[r] = (ok && i != k) ? M[o + k] : 0.0;
+            mv[r] = (ok && cm) ? M[o + tx] : 0.0;
+            bv[r] = (ok && cb) ? B[o + tx] : 0.0;
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r * (kThreads / 64);
+            const bool ok = i < n;
+            const int o = i * n;
+            const double ll = l[r] * pinv;
+            if (ok && cm) M[o + tx] = fma(-ll, mk, mv[r]);
+            if (ok && cb) B[o + tx] = fma(-ll, bk, bv[r]);
+          }
+        }
       } else {
-        const int j = c - (n - k - 1);
-        B[(size_t)i * n + j] = fma(-l, B[(size_t)k * n + j], B[(size_t)i * n + j]);
+        for (int i = ty; i < n; i += kThreads / 64) {
+          if (i == k) continue;
+          const double l = M[(size_t)i * n + k] * pinv;
+          for (int j = k + 1 + tx; j < n; j += 64)
+            M[(size_t)i * n + j] = fma(-l, M[(size_t)k * n + j], M[(size_t)i * n + j]);
+          for (int j = tx; j < n; j += 64)
+            B[(size_t)i * n + j] = fma(-l, B[(size_t)k * n + j], B[(size_t)i * n + j]);
+        }
       }
     }
     __syncthreads();
   }
-  // back substitution, one thread per column of B
-  for (int j = tid; j < n; j += kThreads) {
-    for (int k = n - 1; k >= 0; --k) {
-      double v = B[(size_t)k * n + j];
-      for (int c = k + 1; c < n; ++c) v = fma(-M[(size_t)k * n + c], B[(size_t)c * n + j], v);
-      B[(size_t)k * n + j] = v / M[(size_t)k * n + k];
-    }
+  for (size_t i = tid; i < nn; i += kThreads) {
+    const size_t r = i / n;
+    B[i] = B[i] / M[r * n + r];
   }
   __syncthreads();
 
-  // squaring: R = B; ping-pong between B(T2) and U
+  // squaring: R = B; ping-pong between B (A4) and A6
   double* R = B;
-  double* O = U;
+  double* O = A6;
   for (int i = 0; i < s; ++i) {
     mm(O, R, R, n, sm);
     double* t = R; R = O; O = t;
@@ -366,7 +395,13 @@ static int launch_expm(double* mats, int n, int n_mat, double* scratch, cudaStre
     expm_small_kernel<<<(n_mat + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, smem, stream>>>(
         mats, n, n_mat);
   } else {
-    expm_kernel<<<n_mat, kThreads, 0, stream>>>(mats, n, scratch);
+    const size_t ws = sizeof(double) * 6 * (size_t)n * n;
+    if (ws + 20 * 1024 <= 227 * 1024) {
+      cudaFuncSetAttribute(expm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws);
+      expm_kernel<true><<<n_mat, kThreads, ws, stream>>>(mats, n, scratch);
+    } else {
+      expm_kernel<false><<<n_mat, kThreads, 0, stream>>>(mats, n, scratch);
+    }
   }
   return 0;
 }
