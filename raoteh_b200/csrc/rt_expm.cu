@@ -92,10 +92,10 @@ __device__ double block_max(double v, double* red) {
   return r;
 }
 
-// In-place expm of mats[blockIdx.x] (n x n).  Six n x n work matrices: in dynamic shared memory
-// when they fit (SMEM_WS: n <= 64, 6 * 32 KB -- the elimination below is 61 dependent steps of
-// short loads, which took most of the 235 us per matrix when they went to L2), else in `scratch`
-// (7 n^2 doubles per matrix are reserved there).
+// In-place expm of mats[blockIdx.x] (n x n).  Six n x n work matrices in `scratch` (7 n^2 doubles
+// per matrix are reserved there); with SMEM_WS (n <= 64 or so) the three that the elimination and
+// the squarings work on are in dynamic shared memory instead -- the elimination is 61 dependent
+// steps of short loads, which took most of the 235 us per matrix when they went to L2.
 template <bool SMEM_WS>
 __global__ void __launch_bounds__(kThreads)
 expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
@@ -106,8 +106,13 @@ expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
   const int tid = threadIdx.x;
   const size_t nn = (size_t)n * n;
   double* A = mats + (size_t)blockIdx.x * nn;
-  double* W = SMEM_WS ? ws_dyn : scratch + (size_t)blockIdx.x * 7 * nn;
-  double *A2 = W, *A4 = W + nn, *A6 = W + 2 * nn, *T1 = W + 3 * nn, *U = W + 4 * nn, *V = W + 5 * nn;
+  // the powers (read through the tile staging of mm and by streaming loops only) stay in the
+  // global scratch; the three matrices the elimination and the squarings work on are in shared
+  // memory: 3 * 30 KB at n = 61, so two CTAs share an SM and 255 matrices are one wave
+  double* G = scratch + (size_t)blockIdx.x * 7 * nn;
+  double *A2 = G, *A4 = G + nn, *A6 = G + 2 * nn;
+  double* W = SMEM_WS ? ws_dyn : G + 3 * nn;
+  double *T1 = W, *U = W + nn, *V = W + 2 * nn;
 
   // 1-norm (max column sum of |a_ij|)
   double cmax = 0.0;
@@ -145,9 +150,9 @@ expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
   }
   __syncthreads();
   mm(U, A, T1, n, sm);      // U = A * (...)
-  // M = V - U (into A2), B = V + U (into A4): the powers are dead
-  double* M = A2;
-  double* B = A4;
+  // M = V - U (into T1, dead after the product), B = V + U (in place)
+  double* M = T1;
+  double* B = V;
   for (size_t i = tid; i < nn; i += kThreads) {
     const double u = U[i], v = V[i];
     M[i] = v - u;
@@ -239,9 +244,9 @@ expm_kernel(double* __restrict__ mats, int n, double* __restrict__ scratch) {
   }
   __syncthreads();
 
-  // squaring: R = B; ping-pong between B (A4) and A6
+  // squaring: R = B; ping-pong between B (V) and U
   double* R = B;
-  double* O = A6;
+  double* O = U;
   for (int i = 0; i < s; ++i) {
     mm(O, R, R, n, sm);
     double* t = R; R = O; O = t;
@@ -395,7 +400,7 @@ static int launch_expm(double* mats, int n, int n_mat, double* scratch, cudaStre
     expm_small_kernel<<<(n_mat + kSmallWarps - 1) / kSmallWarps, kSmallWarps * 32, smem, stream>>>(
         mats, n, n_mat);
   } else {
-    const size_t ws = sizeof(double) * 6 * (size_t)n * n;
+    const size_t ws = sizeof(double) * 3 * (size_t)n * n;
     if (ws + 20 * 1024 <= 227 * 1024) {
       cudaFuncSetAttribute(expm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws);
       expm_kernel<true><<<n_mat, kThreads, ws, stream>>>(mats, n, scratch);
