@@ -63,6 +63,25 @@ prune_small_kernel(int64_t n_sites, int64_t stride,
     prog_s[i] = d;
   }
   __syncthreads();
+  if constexpr (OBS == OBS_CODES) {
+    // every code row of this CTA's sites into L2 now, while the tables below are set up: a leaf
+    // op is four multiplies, so the one-op-ahead fetch of its code byte cannot hide a DRAM round
+    // trip (19 % of the warp samples sat on the first use of the byte, ncu source view)
+    const int64_t s0 = (int64_t)blockIdx.x * NS * kBlock;
+    const int64_t b0 = obs_packed ? (s0 >> 1) : s0;
+    const int64_t nb = obs_packed ? (NS * kBlock / 2) : (NS * kBlock);
+    const int lines = (int)((nb + 127) / 128) + 1;          // + 1: rows are not line aligned
+    const int64_t row_bytes = obs_packed ? ((stride + 1) >> 1) : stride;
+    for (int i = tid; i < n_ops * lines; i += kBlock) {
+      const int4 d = prog_s[i / lines];
+      if (d.x == OP_MSG_OBS || d.x == OP_APPLY_OBS) {
+        int64_t off = b0 + (int64_t)(i % lines) * 128;
+        if (off >= row_bytes) off = row_bytes - 1;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const uint8_t*>(obs) +
+                     (int64_t)d.z * row_bytes + off));
+      }
+    }
+  }
   if (tid == 0) {
     // pre_s[ip]: element offset of the row consumed by the next obs-consuming op after ip
     long long nxt = -1;
