@@ -11,6 +11,8 @@ timeout 600 ncu --set full --clock-control none -k regex:'prune_small_kernel|dow
 ncu -i /tmp/${T}_c2c3.ncu-rep --page raw --csv > gpurun_out/${T}_c2c3_raw.csv 2>/dev/null
 timeout 300 ncu --set full --clock-control none -k regex:down_dmma_kernel --launch-skip 6 -c 1 -f -o /tmp/${T}_c3down python tools/profile_kernels.py c3 down > gpurun_out/${T}_ncu_down.log 2>&1
 ncu -i /tmp/${T}_c3down.ncu-rep --page raw --csv > gpurun_out/${T}_c3down_raw.csv 2>/dev/null
+timeout 300 ncu --set full --clock-control none -k regex:'down_leaf_scatter|expm_kernel' -c 2 -f -o /tmp/${T}_c3leaf python tools/c3_down_one.py > gpurun_out/${T}_ncu_leaf.log 2>&1
+ncu -i /tmp/${T}_c3leaf.ncu-rep --page raw --csv > gpurun_out/${T}_c3leaf_raw.csv 2>/dev/null
 timeout 300 ncu --set full --clock-control none -k regex:raoteh_kernel --launch-skip 2 -c 1 -f -o /tmp/${T}_c4 python tools/c4_one.py > gpurun_out/${T}_ncu_c4.log 2>&1
 ncu -i /tmp/${T}_c4.ncu-rep --page raw --csv > gpurun_out/${T}_c4_raw.csv 2>/dev/null
 RT_FUSED=1 timeout 300 ncu --set full --clock-control none -k regex:fused_small --launch-skip 2 -c 1 -f -o /tmp/${T}_fused python tools/fused_one.py > gpurun_out/${T}_ncu_fused.log 2>&1
