@@ -484,7 +484,7 @@ def run_gpu(args):
                         fp64_pipe=dict(achieved=walk_tfl, peak=fma_peak, unit='TFLOP/s', frac=walk_tfl / fma_peak,
                                        algorithmic_flop_per_site=walk_flop,
                                        peak_source='tools/fp64_peak.cu DFMA probe (profiles/r1_fp64_peak.jsonl)',
-                                       ncu='fp64 pipe 37 %, issue slots 53 % (profiles/r2_ncu_full_summary.json)'),
+                                       ncu='fp64 pipe 34 %, issue slots 52 % (profiles/r2_ncu_full_summary.json)'),
                         note='the S=4 walk reads every stored partial exactly once (ncu dram read = algorithmic '
                              'bytes) but is bound by latency / issue slots, not by HBM; the fused up+down kernel '
                              'that removes these bytes altogether was built and measured slower '
