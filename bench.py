@@ -624,8 +624,17 @@ def bench_c2_loglik(dev, cfg, sched, obs, args, peaks):
         return float(np.mean(ts))
     ms = time_it(obs)
     b_site = len(sched.leaves) + 9
+    # with hard codes the input is 41 B per site, so the honest roof is the FP64 FMA pipe / issue slots:
+    # a mat-vec per internal edge (2 S^2 flop), one product per message (S), a leaf message is a gather
+    n_leaf = len(sched.leaves)
+    flop_site = (sched.n_edges - n_leaf) * 2 * S * S + sched.n_edges * S
+    fp64_peak = 33.55        # TFLOP/s, tools/fp64_peak.cu DFMA probe (profiles/r1_fp64_peak.jsonl)
     res['codes'] = dict(ms=ms, messages_per_sec=N * sched.n_edges / (ms * 1e-3), bytes_per_site=b_site,
-                        hbm_gbs=N * b_site / (ms * 1e-3) / 1e9, hbm_frac=N * b_site / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'])
+                        hbm_gbs=N * b_site / (ms * 1e-3) / 1e9, hbm_frac=N * b_site / (ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                        bound='fp64 pipe / issue slots', fp64_flop_per_site=flop_site,
+                        fp64_tflops=N * flop_site / (ms * 1e-3) / 1e12,
+                        fp64_frac=N * flop_site / (ms * 1e-3) / 1e12 / fp64_peak,
+                        ncu='issue slots 60 %, fp64 pipe 24 % (profiles/r2_ncu_full_summary.json)')
     # dense emission likelihoods (obs type z): [n_leaves, S, N] fp64 = 1 KiB / site
     codes = obs.data.long()
     lik = torch.zeros((len(sched.leaves), S, N), dtype=torch.float64, device=dev)
