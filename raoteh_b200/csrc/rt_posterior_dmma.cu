@@ -417,8 +417,8 @@ constexpr int kLeafLd = 65;            // odd: lanes (rows) hit distinct banks f
 constexpr int kLeafGroup = 16;
 constexpr int kLeafSitesPerCta = 2048;
 
-template <bool V4>
-__global__ void __launch_bounds__(kLeafThreads)
+template <bool V4, bool K16>
+__global__ void __launch_bounds__(kLeafThreads, 6)
 down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict__ edges,
                          const double* __restrict__ P, const uint8_t* __restrict__ obs,
                          const int8_t* __restrict__ status, const double* __restrict__ node_distn,
@@ -437,11 +437,17 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
   const uint8_t* code = obs + (int64_t)e.w * stride;
   double miss = 0.0;
 
-  auto load = [&](double (&dn)[kLeafGroup], int2& kn, int64_t s0) {
+  // Codes of a group.  K16 (rows 16-byte aligned): every lane loads the same 16 code bytes with
+  // one vector load and picks its bytes with ALU instructions -- the shuffles that broadcast them
+  // otherwise share the MIO queue with the read-modify-writes the kernel waits on (short
+  // scoreboard: 6.2 stalls per issue, ncu).  The marginal of a site that failed is exactly zero
+  // (root_distn_generic_kernel writes 0, the contraction kernel propagates it), so the vector path
+  // does not read the status row.  Ragged last group / unaligned rows: one byte per lane + shuffles.
+  struct Codes { uint4 v; int k, st; };
+  auto load = [&](double (&dn)[kLeafGroup], Codes& kn, int64_t s0) {
     if (s0 + kLeafGroup <= c1) {
       if (V4) {
-        // 32 bytes per lane and instruction: one whole sector (two 16-byte loads of a sector,
-        // streaming, fetched it from L2 twice: 10.8 GB of L2 reads for 6.25 GB of data, ncu)
+        // 32 bytes per lane and instruction: one whole sector
 #pragma unroll
         for (int i = 0; i < kLeafGroup; i += 4)
           asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -450,6 +456,10 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
 #pragma unroll
         for (int i = 0; i < kLeafGroup; ++i) dn[i] = __ldg(Dp + s0 + i);
       }
+      if (K16) {
+        kn.v = __ldg(reinterpret_cast<const uint4*>(code + s0));
+        return;
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < kLeafGroup; ++i) dn[i] = s0 + i < c1 ? __ldg(Dp + s0 + i) : 0.0;
@@ -457,20 +467,22 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
     const int64_t sg = s0 + (lane & (kLeafGroup - 1));
     const bool in = sg < c1;
     // both loads issued together and NOT combined here: the first use of a loaded value blocks
-    // the warp, so it belongs to the scatter two groups later (a third of the warp samples sat
-    // on this line when the select was here, ncu source view)
-    kn.x = in ? (int)reinterpret_cast<const uint8_t*>(status)[sg] : 1;   // (no sign extension: that is a use)
-    kn.y = in ? (int)code[sg] : 254;
+    // the warp, so it belongs to the scatter two groups later
+    kn.st = in ? (int)reinterpret_cast<const uint8_t*>(status)[sg] : 1;   // (no sign extension: that is a use)
+    kn.k = in ? (int)code[sg] : 254;
   };
-  auto scatter = [&](const double (&d)[kLeafGroup], int2 ks) {
-    const int kv = ks.x == RT_SITE_OK ? ks.y : 254;     // failed sites and the tail go to the bin
+  auto scatter = [&](const double (&d)[kLeafGroup], const Codes& ks, bool vec) {
+    const int kv = ks.st == RT_SITE_OK ? ks.k : 254;     // failed sites and the tail go to the bin
+    const unsigned wv[4] = {ks.v.x, ks.v.y, ks.v.z, ks.v.w};
 #pragma unroll
     for (int q = 0; q < kLeafGroup; q += 4) {
       int k[4];
       double w[4], v[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int kk = __shfl_sync(0xffffffffu, kv, q + i);
+        int kk;
+        if (K16 && vec) kk = (int)((wv[q / 4] >> (8 * i)) & 0xffu);
+        else kk = __shfl_sync(0xffffffffu, kv, q + i);
         if (kk == RT_MISSING) miss += d[q + i];
         k[i] = kk < S ? kk : 64;
         w[i] = Wr[k[i]];
@@ -488,19 +500,21 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
   // three register buffers in rotation: a group is loaded two scatters before its own.  (The
   // parent marginal of a site that passed is a product of non-negative factors: no clamping.)
   double da[kLeafGroup], db[kLeafGroup], dc[kLeafGroup];
-  int2 ka = make_int2(1, 254), kb = ka, kc = ka;
+  Codes ka, kb, kc;
+  ka.v = make_uint4(0, 0, 0, 0); ka.k = 254; ka.st = 1;
+  kb = ka; kc = ka;
   const int64_t G = kLeafGroup;
   if (c0 < c1) load(da, ka, c0);
   if (c0 + G < c1) load(db, kb, c0 + G);
   for (int64_t s0 = c0; s0 < c1; s0 += 3 * G) {
     if (s0 + 2 * G < c1) load(dc, kc, s0 + 2 * G);
-    scatter(da, ka);
+    scatter(da, ka, s0 + G <= c1);
     if (s0 + G >= c1) break;
     if (s0 + 3 * G < c1) load(da, ka, s0 + 3 * G);
-    scatter(db, kb);
+    scatter(db, kb, s0 + 2 * G <= c1);
     if (s0 + 2 * G >= c1) break;
     if (s0 + 4 * G < c1) load(db, kb, s0 + 4 * G);
-    scatter(dc, kc);
+    scatter(dc, kc, s0 + 3 * G <= c1);
   }
   if (!act) return;
   const double* Pr = P + ((size_t)e.x * S + r) * S;
@@ -574,12 +588,17 @@ int run(int S, int obs_kind, int64_t n_sites, int64_t stride, const int32_t* edg
     }();
     dim3 grid((unsigned)((n_sites + spc - 1) / spc), (unsigned)level_ptr_h[n_levels]);
     const bool v4 = stride % 4 == 0 && (reinterpret_cast<uintptr_t>(node_distn) & 31) == 0;
-    if (v4)
-      down_leaf_scatter_kernel<true><<<grid, kLeafThreads, lsm, stream>>>(
-          S, n_sites, stride, edges, P, reinterpret_cast<const uint8_t*>(obs), status, node_distn, W, spc);
+    const bool k16 = v4 && stride % 16 == 0 && (reinterpret_cast<uintptr_t>(obs) & 15) == 0 && spc % 16 == 0;
+    const uint8_t* codes = reinterpret_cast<const uint8_t*>(obs);
+    if (k16)
+      down_leaf_scatter_kernel<true, true><<<grid, kLeafThreads, lsm, stream>>>(
+          S, n_sites, stride, edges, P, codes, status, node_distn, W, spc);
+    else if (v4)
+      down_leaf_scatter_kernel<true, false><<<grid, kLeafThreads, lsm, stream>>>(
+          S, n_sites, stride, edges, P, codes, status, node_distn, W, spc);
     else
-      down_leaf_scatter_kernel<false><<<grid, kLeafThreads, lsm, stream>>>(
-          S, n_sites, stride, edges, P, reinterpret_cast<const uint8_t*>(obs), status, node_distn, W, spc);
+      down_leaf_scatter_kernel<false, false><<<grid, kLeafThreads, lsm, stream>>>(
+          S, n_sites, stride, edges, P, codes, status, node_distn, W, spc);
   }
   RT_CUDA_CHECK(cudaGetLastError());
   return RT_OK;
