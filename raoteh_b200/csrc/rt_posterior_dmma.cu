@@ -487,12 +487,21 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
         k[i] = kk < S ? kk : 64;
         w[i] = Wr[k[i]];
       }
-      // four read-modify-writes with their loads issued together: a repeated column takes the
-      // running value instead of the stale load, the stores stay in program order
-      v[0] = w[0] + d[q];
-      v[1] = (k[1] == k[0] ? v[0] : w[1]) + d[q + 1];
-      v[2] = (k[2] == k[1] ? v[1] : (k[2] == k[0] ? v[0] : w[2])) + d[q + 2];
-      v[3] = (k[3] == k[2] ? v[2] : (k[3] == k[1] ? v[1] : (k[3] == k[0] ? v[0] : w[3]))) + d[q + 3];
+      // four read-modify-writes with their loads issued together.  The codes are warp uniform, so
+      // "no column repeats among the four" is a uniform branch: then the four adds are independent;
+      // otherwise a repeated column takes the running value instead of the stale load.  The
+      // stores stay in program order either way.
+      const bool rep = (k[1] == k[0]) | (k[2] == k[0]) | (k[2] == k[1]) |
+                       (k[3] == k[0]) | (k[3] == k[1]) | (k[3] == k[2]);
+      if (!rep) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = w[i] + d[q + i];
+      } else {
+        v[0] = w[0] + d[q];
+        v[1] = (k[1] == k[0] ? v[0] : w[1]) + d[q + 1];
+        v[2] = (k[2] == k[1] ? v[1] : (k[2] == k[0] ? v[0] : w[2])) + d[q + 2];
+        v[3] = (k[3] == k[2] ? v[2] : (k[3] == k[1] ? v[1] : (k[3] == k[0] ? v[0] : w[3]))) + d[q + 3];
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) Wr[k[i]] = v[i];
     }
