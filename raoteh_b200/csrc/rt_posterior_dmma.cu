@@ -413,7 +413,7 @@ down_dmma_kernel(int S, int64_t n_sites, int64_t stride, const int4* __restrict_
 // (L_b = ones) go to a per-row register and are spread over the row at the flush; invalid codes and
 // failed sites land in the pad column.
 constexpr int kLeafThreads = 64;
-constexpr int kLeafLd = 65;            // odd: lanes (rows) hit distinct banks for one column
+constexpr int kLeafLd = 67;            // odd: lanes (rows) hit distinct banks for one column; 64 = bin, 65 = unobserved
 constexpr int kLeafGroup = 16;
 constexpr int kLeafSitesPerCta = 2048;
 
@@ -425,7 +425,7 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
                          double* __restrict__ W, int sites_per_cta) {
   const int4 e = edges[blockIdx.y];
   if (e.z >= 0 || e.w < 0) return;     // internal child / unobserved leaf: the DMMA kernel's edge
-  extern __shared__ double Ws[];       // [64][kLeafLd]; column 64 is the bin for skipped sites
+  extern __shared__ double Ws[];       // [64][kLeafLd]; column 64: bin for skipped sites, 65: unobserved sites
   const int r = threadIdx.x, lane = r & 31;
   const bool act = r < S;
   double* Wr = Ws + r * kLeafLd;
@@ -435,7 +435,6 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
   // lanes past the last state read row 0 into rows of the tile that are never flushed
   const double* Dp = node_distn + ((int64_t)e.y * S + (act ? r : 0)) * stride;
   const uint8_t* code = obs + (int64_t)e.w * stride;
-  double miss = 0.0;
 
   // Codes of a group.  K16 (rows 16-byte aligned): every lane loads the same 16 code bytes with
   // one vector load and picks its bytes with ALU instructions -- the shuffles that broadcast them
@@ -483,8 +482,7 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
         int kk;
         if (K16 && vec) kk = (int)((wv[q / 4] >> (8 * i)) & 0xffu);
         else kk = __shfl_sync(0xffffffffu, kv, q + i);
-        if (kk == RT_MISSING) miss += d[q + i];
-        k[i] = kk < S ? kk : 64;
+        k[i] = kk < S ? kk : (kk == RT_MISSING ? 65 : 64);     // unobserved sites have their own column
         w[i] = Wr[k[i]];
       }
       // four read-modify-writes with their loads issued together.  The codes are warp uniform, so
@@ -528,17 +526,25 @@ down_leaf_scatter_kernel(int S, int64_t n_sites, int64_t stride, const int4* __r
   if (!act) return;
   const double* Pr = P + ((size_t)e.x * S + r) * S;
   double* Wg = W + ((size_t)e.x * S + r) * S;
+  // flush: W_b[r][c] += C[r][c] / P_b[r][c] (+ the unobserved sites' share of the row), the P row
+  // loaded eight entries at a time ahead of their use
+  const double miss = Wr[65];
   double spread = 0.0;
   if (miss != 0.0) {
     double rs = 0.0;
     for (int c = 0; c < S; ++c) rs += Pr[c];
     spread = rs > 0.0 ? miss / rs : 0.0;
   }
-  for (int c = 0; c < S; ++c) {
-    const double p = Pr[c];
-    if (p > 0.0) {
-      const double val = Wr[c] / p + spread;
-      if (val != 0.0) atomicAdd(&Wg[c], val);
+  for (int c0f = 0; c0f < S; c0f += 8) {
+    double p[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = c0f + i < S ? __ldg(Pr + c0f + i) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (p[i] > 0.0) {
+        const double val = Wr[c0f + i] / p[i] + spread;
+        if (val != 0.0) atomicAdd(&Wg[c0f + i], val);
+      }
     }
   }
 }
