@@ -237,7 +237,7 @@ def test_expectations_match_oracle(rt, S, n_leaves, n_sites):
     np.testing.assert_allclose(float(r['dwell'].sum()), length.sum() * n_sites, rtol=1e-10)
 
 
-@pytest.mark.parametrize('S,n_leaves,n_sites,kind', [(20, 9, 2500, 'codes'), (61, 10, 2100, 'codes'),
+@pytest.mark.parametrize('S,n_leaves,n_sites,kind', [(20, 9, 2500, 'codes'), (61, 10, 2112, 'codes'),     # 2112 = 16 * 132: vector code loads of the leaf scatter
                                                      (13, 8, 4133, 'codes'),     # odd row stride: scalar loads of the leaf scatter
                                                      (20, 7, 1300, 'mask'), (11, 6, 1100, 'dense')])
 def test_large_state_down_pass_tiles_and_observation_kinds(rt, S, n_leaves, n_sites, kind):
@@ -635,7 +635,7 @@ def test_dmma_pruning_walk_edge_cases(rt, shape):
         np.testing.assert_allclose(e['trans'].cpu().numpy(), o['trans'], rtol=RTOL, atol=1e-12)
 
 
-@pytest.mark.parametrize('S,n_leaves,n_sites', [(12, 5, 3000), (61, 6, 2300)])
+@pytest.mark.parametrize('S,n_leaves,n_sites', [(12, 5, 3000), (61, 6, 2304)])      # 2304 % 16 == 0: the leaf scatter's vector path, which does not read the status row
 def test_large_state_expectations_skip_infeasible_sites(rt, S, n_leaves, n_sites):
     """A reducible rate matrix (two closed classes) and uniformly random leaf codes: most sites have
     probability zero (StructuralZeroProb in the reference, _mjp_dense.py:186-190) and must contribute
