@@ -15,6 +15,10 @@
 // run back to back; W_b (= sum_sites J_b / P_b) stays in registers for the whole
 // chunk and is flushed with one masked atomicAdd per entry.  The joint J_b is
 // never materialised (7.6 MB per site at S = 61).
+//
+// Leaf edges with hard codes (half of the edges of a binary tree) do not run on
+// the tensor pipe at all: down_leaf_scatter_kernel below sums the parent
+// marginals by leaf code, one launch for all of them after the level launches.
 #include "rt_common.cuh"
 
 namespace {
