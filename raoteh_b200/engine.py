@@ -550,7 +550,8 @@ class TreeMJP(object):
             # two compute streams, chunks alternate: the kernels of consecutive chunks are
             # independent, so the tail wave of one chunk's kernel (a chunk is only ~1.3-1.7
             # waves of CTAs) is filled with CTAs of the next chunk's kernels
-            self._compute_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            self._compute_streams = tuple(torch.cuda.Stream(device=dev)
+                                          for _ in range(int(os.environ.get('RT_E2E_STREAMS', '3'))))
         s_in, s_out = self._copy_streams
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
@@ -568,7 +569,7 @@ class TreeMJP(object):
             e.record(s_in)
             ev_in.append(e)
         for k, ((lo, hi), e) in enumerate(zip(bounds, ev_in)):
-            cs = self._compute_streams[k % 2]
+            cs = self._compute_streams[k % len(self._compute_streams)]
             cs.wait_event(e)
             if use_fused:
                 handled = ctypes.c_int(0)
