@@ -547,9 +547,9 @@ class TreeMJP(object):
         cur = torch.cuda.current_stream()
         if getattr(self, '_copy_streams', None) is None:
             self._copy_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-            # two compute streams, chunks alternate: the kernels of consecutive chunks are
-            # independent, so the tail wave of one chunk's kernel (a chunk is only ~1.3-1.7
-            # waves of CTAs) is filled with CTAs of the next chunk's kernels
+            # several compute streams (three by default), chunks take turns: the kernels of
+            # consecutive chunks are independent, so the tail wave of one chunk's kernel (a chunk
+            # is only ~1.3-1.7 waves of CTAs) is filled with CTAs of the next chunks' kernels
             self._compute_streams = tuple(torch.cuda.Stream(device=dev)
                                           for _ in range(int(os.environ.get('RT_E2E_STREAMS', '3'))))
         s_in, s_out = self._copy_streams
